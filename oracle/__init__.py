@@ -1,0 +1,331 @@
+"""oracle -- TEST INFRASTRUCTURE (checker), never the product.
+
+ctypes bindings for
+  * ``liboracle.so``            : the C restatement in oracle/oracle.c            -> ``oracle.orc``
+  * ``_ref/libonika_ref.so``    : the real reference OpenMP path (oracle/ref_driver.cpp + reference sources,
+                                  built by ``make -C oracle ref`` where /root/reference exists) -> ``oracle.ref``
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may
+import this package.  ``onika_b200`` (the product) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libonika_ref.so")
+REFERENCE_TREE = "/root/reference"
+
+_dp = C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+_i64p = C.POINTER(C.c_int64)
+
+
+def _host_env():
+    # the image exports CC/CXX pointing at a wrapper without libgomp.spec; use the PATH compilers
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    return env
+
+
+def build(ref: bool | None = None, verbose: bool = False) -> None:
+    """Compile oracle/liboracle.so, and oracle/_ref when the reference tree is present (ref=None => auto)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", HERE, "all"], stdout=out, env=_host_env())
+    if ref is None:
+        ref = os.path.isdir(REFERENCE_TREE)
+    if ref:
+        subprocess.check_call(["make", "-C", HERE, "ref"], stdout=out, env=_host_env())
+
+
+def _ptr(a: np.ndarray, typ):
+    assert a.flags["C_CONTIGUOUS"], "oracle arrays must be contiguous"
+    return a.ctypes.data_as(typ)
+
+
+def _f64(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a
+
+
+class _Oracle:
+    """C restatement (oracle.c).  Every method cites the C function; the C function cites the reference."""
+
+    def __init__(self):
+        self._lib = None
+
+    @property
+    def lib(self):
+        if self._lib is None:
+            if not os.path.exists(ORACLE_SO):
+                build(ref=False)
+            L = C.CDLL(ORACLE_SO)
+            L.orc_num_threads.restype = C.c_int
+            for name in ("orc_reduce_min_f64", "orc_reduce_max_f64", "orc_reduce_sum_f64_ld"):
+                f = getattr(L, name)
+                f.restype = C.c_double
+                f.argtypes = [_dp, C.c_uint64]
+            L.orc_reduce_sum_f64.restype = C.c_double
+            L.orc_reduce_sum_f64.argtypes = [_dp, C.c_uint64, C.c_int]
+            L.orc_axpy_f64.argtypes = [_dp, _dp, C.c_double, C.c_uint64]
+            L.orc_memset_f64.argtypes = [_dp, C.c_uint64, C.c_double]
+            L.orc_value_add_f64.argtypes = [_dp, C.c_uint64, C.c_uint64, C.c_double]
+            L.orc_parallel_for_3d_f64.argtypes = [_dp, C.c_int64, _i64p, _i64p]
+            L.orc_soatl_update_capacity.restype = C.c_uint64
+            L.orc_soatl_update_capacity.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+            L.orc_soatl_layout.restype = C.c_uint64
+            L.orc_soatl_layout.argtypes = [C.c_uint64, _u32p, C.c_int, C.c_uint64, _u64p]
+            L.orc_soatl_storage_size_calc.restype = C.c_uint64
+            L.orc_soatl_storage_size_calc.argtypes = [C.c_uint64, C.c_uint64, _u32p, C.c_int, C.c_uint64]
+            L.orc_soatl_dist_f64.argtypes = [_dp, _dp, _dp, _dp, C.c_uint64, C.c_double, C.c_double, C.c_double]
+            L.orc_soatl_rmw_f64.argtypes = [_u8p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_double, _dp]
+            L.orc_soatl_repack.argtypes = [_u8p, C.c_uint64, C.c_uint64, _u8p, C.c_uint64, C.c_uint64, _u32p, C.c_int, C.c_uint64]
+            L.orc_cell_sum_f64.argtypes = [_u8p, _u64p, _u32p, _u32p, C.c_uint64, C.c_uint64, _u32p, C.c_int, C.c_int, _dp, _dp]
+            L.orc_cell_grid_layout.restype = C.c_uint64
+            L.orc_cell_grid_layout.argtypes = [_u32p, C.c_uint64, C.c_uint64, C.c_uint64, _u32p, C.c_int, C.c_uint64, _u32p, _u64p]
+            L.orc_lane_sequence_f64.argtypes = [_dp, _dp, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double]
+            self._lib = L
+        return self._lib
+
+    def num_threads(self) -> int:
+        return self.lib.orc_num_threads()
+
+    # ---- reductions ----
+    def reduce_min(self, d) -> float:
+        d = _f64(d)
+        return self.lib.orc_reduce_min_f64(_ptr(d, _dp), d.size)
+
+    def reduce_max(self, d) -> float:
+        d = _f64(d)
+        return self.lib.orc_reduce_max_f64(_ptr(d, _dp), d.size)
+
+    def reduce_sum(self, d, nthreads: int = 8) -> float:
+        d = _f64(d)
+        return self.lib.orc_reduce_sum_f64(_ptr(d, _dp), d.size, nthreads)
+
+    def reduce_sum_ld(self, d) -> float:
+        d = _f64(d)
+        return self.lib.orc_reduce_sum_f64_ld(_ptr(d, _dp), d.size)
+
+    # ---- streaming (in place on the given numpy arrays) ----
+    def axpy(self, y: np.ndarray, x: np.ndarray, a: float) -> None:
+        assert y.dtype == np.float64 and x.dtype == np.float64 and y.size == x.size
+        self.lib.orc_axpy_f64(_ptr(y, _dp), _ptr(x, _dp), a, y.size)
+
+    def memset(self, d: np.ndarray, v: float) -> None:
+        assert d.dtype == np.float64
+        self.lib.orc_memset_f64(_ptr(d, _dp), d.size, v)
+
+    def value_add(self, a: np.ndarray, v: float) -> None:
+        assert a.dtype == np.float64 and a.ndim == 2
+        self.lib.orc_value_add_f64(_ptr(a, _dp), a.shape[0], a.shape[1], v)
+
+    def parallel_for_3d(self, m: np.ndarray, n: int, start, end) -> None:
+        s = np.asarray(start, dtype=np.int64)
+        e = np.asarray(end, dtype=np.int64)
+        self.lib.orc_parallel_for_3d_f64(_ptr(m, _dp), n, _ptr(s, _i64p), _ptr(e, _i64p))
+
+    # ---- SOATL layout ----
+    def update_capacity(self, s: int, capacity: int, chunk: int) -> int:
+        return self.lib.orc_soatl_update_capacity(s, capacity, chunk)
+
+    def layout(self, align: int, field_sizes, capacity: int):
+        fs = np.asarray(field_sizes, dtype=np.uint32)
+        offs = np.zeros(len(fs), dtype=np.uint64)
+        total = self.lib.orc_soatl_layout(align, _ptr(fs, _u32p), len(fs), capacity, _ptr(offs, _u64p))
+        return int(total), [int(o) for o in offs]
+
+    def storage_size_calc(self, align: int, chunk: int, field_sizes, capacity: int) -> int:
+        fs = np.asarray(field_sizes, dtype=np.uint32)
+        return int(self.lib.orc_soatl_storage_size_calc(align, chunk, _ptr(fs, _u32p), len(fs), capacity))
+
+    # ---- SOATL streaming ----
+    def soatl_dist(self, rx, ry, rz, chunk: int = 16) -> np.ndarray:
+        """tests/benchmark.cpp kernel on FieldArrays<64,16,rx,ry,rz,e>; returns e[0:n]."""
+        n = len(rx)
+        npad = ((n + chunk - 1) // chunk) * chunk
+        pad = lambda a, v: np.concatenate([_f64(a), np.full(npad - n, v)])
+        px, py, pz = pad(rx, 2.0), pad(ry, 3.0), pad(rz, 4.0)
+        e = np.zeros(npad)
+        self.lib.orc_soatl_dist_f64(_ptr(e, _dp), _ptr(px, _dp), _ptr(py, _dp), _ptr(pz, _dp), npad,
+                                    float(px[0]), float(py[0]), float(pz[0]))
+        return e[:n].copy()
+
+    def soatl_rmw(self, storage: np.ndarray, align: int, chunk: int, nfields: int, n: int, capacity: int, s: float, c) -> None:
+        assert storage.dtype == np.uint8
+        c = _f64(c)
+        self.lib.orc_soatl_rmw_f64(_ptr(storage, _u8p), align, chunk, nfields, n, capacity, s, _ptr(c, _dp))
+
+    def soatl_repack(self, dst: np.ndarray, dst_align: int, dst_cap: int, src: np.ndarray, src_align: int, src_cap: int,
+                     field_sizes, n: int) -> None:
+        fs = np.asarray(field_sizes, dtype=np.uint32)
+        self.lib.orc_soatl_repack(_ptr(dst, _u8p), dst_align, dst_cap, _ptr(src, _u8p), src_align, src_cap,
+                                  _ptr(fs, _u32p), len(fs), n)
+
+    # ---- cell grid ----
+    def cell_grid_layout(self, cell_size, align: int, chunk: int, field_sizes, cell_align: int):
+        cs = np.ascontiguousarray(cell_size, dtype=np.uint32)
+        fs = np.asarray(field_sizes, dtype=np.uint32)
+        cap = np.zeros(cs.size, dtype=np.uint32)
+        off = np.zeros(cs.size, dtype=np.uint64)
+        total = self.lib.orc_cell_grid_layout(_ptr(cs, _u32p), cs.size, align, chunk, _ptr(fs, _u32p), len(fs), cell_align,
+                                              _ptr(cap, _u32p), _ptr(off, _u64p))
+        return int(total), cap, off
+
+    def cell_sum(self, arena: np.ndarray, cell_off, cell_size, cell_cap, align: int, field_sizes, field: int):
+        fs = np.asarray(field_sizes, dtype=np.uint32)
+        n = len(cell_size)
+        sums = np.zeros(n)
+        total = C.c_double(0.0)
+        self.lib.orc_cell_sum_f64(_ptr(arena, _u8p), _ptr(cell_off, _u64p), _ptr(cell_size, _u32p), _ptr(cell_cap, _u32p),
+                                  n, align, _ptr(fs, _u32p), len(fs), field, _ptr(sums, _dp), C.byref(total))
+        return sums, total.value
+
+    # ---- lanes ----
+    def lane_sequence(self, a1: np.ndarray, a2: np.ndarray, v11, v12, v21, v22) -> None:
+        assert a1.shape == a2.shape and a1.ndim == 2
+        self.lib.orc_lane_sequence_f64(_ptr(a1, _dp), _ptr(a2, _dp), a1.shape[0], a1.shape[1], v11, v12, v21, v22)
+
+
+class _Reference:
+    """The real reference OpenMP path (oracle/_ref/libonika_ref.so).  Methods return the seconds spent inside
+    the reference call (plus results where applicable)."""
+
+    SOATL_CONFIGS = {
+        0: dict(align=64, chunk=16, fields=[8, 8, 8, 8]),
+        1: dict(align=64, chunk=8, fields=[8, 1, 8, 4, 8, 8]),
+        2: dict(align=1, chunk=1, fields=[8, 1, 8, 4, 8, 8]),
+        3: dict(align=64, chunk=16, fields=[8, 8, 8, 1, 8, 4]),
+        4: dict(align=64, chunk=16, fields=[8] * 8),
+        5: dict(align=256, chunk=16, fields=[8] * 8),
+        6: dict(align=32, chunk=4, fields=[4, 2, 1, 1, 8]),
+    }
+
+    def __init__(self):
+        self._lib = None
+
+    def available(self) -> bool:
+        return os.path.exists(REF_SO)
+
+    @property
+    def lib(self):
+        if self._lib is None:
+            if not os.path.exists(REF_SO):
+                raise RuntimeError("oracle/_ref/libonika_ref.so missing: run `make -C oracle ref` where /root/reference exists")
+            L = C.CDLL(REF_SO)
+            L.ref_num_threads.restype = C.c_int
+            L.ref_parallel_for_axpy.restype = C.c_double
+            L.ref_parallel_for_axpy.argtypes = [_dp, _dp, C.c_double, C.c_uint64]
+            L.ref_parallel_memset_f64.restype = C.c_double
+            L.ref_parallel_memset_f64.argtypes = [_dp, C.c_uint64, C.c_double]
+            L.ref_block_value_add.restype = C.c_double
+            L.ref_block_value_add.argtypes = [_dp, C.c_uint64, C.c_uint64, C.c_double, C.c_int]
+            L.ref_reduce_min_chunks.restype = C.c_double
+            L.ref_reduce_min_chunks.argtypes = [_dp, C.c_uint64, _dp]
+            L.ref_reduce_min_init_1m.argtypes = [_dp]
+            L.ref_parallel_for_3d.restype = C.c_double
+            L.ref_parallel_for_3d.argtypes = [_dp, C.c_long, C.POINTER(C.c_long), C.POINTER(C.c_long), C.c_int]
+            L.ref_lane_sequence.restype = C.c_double
+            L.ref_lane_sequence.argtypes = [_dp, _dp, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+            L.ref_soatl_layout.restype = C.c_int
+            L.ref_soatl_layout.argtypes = [C.c_int, _u64p, C.c_int, _u64p, _u64p, _u64p]
+            L.ref_soatl_dist.restype = C.c_double
+            L.ref_soatl_dist.argtypes = [C.c_uint64, _dp, _dp, _dp, _dp]
+            L.ref_soatl_rmw8.restype = C.c_double
+            L.ref_soatl_rmw8.argtypes = [C.c_uint64, C.POINTER(_dp), C.c_double, _dp, C.c_int]
+            L.ref_soatl_serialize.restype = C.c_uint64
+            L.ref_soatl_serialize.argtypes = [C.c_uint64, _dp, _u8p, _dp, C.POINTER(C.c_int32), _dp, _dp, _u8p, C.c_uint64]
+            L.ref_cell_sum.restype = C.c_double
+            L.ref_cell_sum.argtypes = [C.c_uint64, _u32p, _dp, _dp, _dp, _u64p, C.c_int]
+            self._lib = L
+        return self._lib
+
+    def num_threads(self) -> int:
+        return self.lib.ref_num_threads()
+
+    def axpy(self, y: np.ndarray, x: np.ndarray, a: float) -> float:
+        assert y.dtype == np.float64 and x.dtype == np.float64
+        return self.lib.ref_parallel_for_axpy(_ptr(y, _dp), _ptr(x, _dp), a, y.size)
+
+    def memset(self, d: np.ndarray, v: float) -> float:
+        return self.lib.ref_parallel_memset_f64(_ptr(d, _dp), d.size, v)
+
+    def value_add(self, a: np.ndarray, v: float, ndims: int = 1) -> float:
+        assert a.dtype == np.float64 and a.ndim == 2
+        return self.lib.ref_block_value_add(_ptr(a, _dp), a.shape[0], a.shape[1], v, ndims)
+
+    def reduce_min_chunks(self, d: np.ndarray):
+        """d.size must be a multiple of 2**20 (the reference test hard-codes N = 1024*1024)."""
+        assert d.dtype == np.float64 and d.size % (1 << 20) == 0 and d.size > 0
+        out = C.c_double(0.0)
+        t = self.lib.ref_reduce_min_chunks(_ptr(d, _dp), d.size >> 20, C.byref(out))
+        return out.value, t
+
+    def reduce_min_init_1m(self) -> np.ndarray:
+        d = np.empty(1 << 20)
+        self.lib.ref_reduce_min_init_1m(_ptr(d, _dp))
+        return d
+
+    def parallel_for_3d(self, m: np.ndarray, n: int, start, end, block: bool = False) -> float:
+        s = (C.c_long * 3)(*start)
+        e = (C.c_long * 3)(*end)
+        return self.lib.ref_parallel_for_3d(_ptr(m, _dp), n, s, e, int(block))
+
+    def lane_sequence(self, a1, a2, v11, v12, v21, v22, mode: int = 0, use_tasks: bool = False) -> float:
+        return self.lib.ref_lane_sequence(_ptr(a1, _dp), _ptr(a2, _dp), a1.shape[0], a1.shape[1], v11, v12, v21, v22,
+                                          mode, int(use_tasks))
+
+    def soatl_layout(self, cfg: int, sizes):
+        sizes = np.asarray(sizes, dtype=np.uint64)
+        k = sizes.size
+        cap = np.zeros(k, np.uint64)
+        by = np.zeros(k, np.uint64)
+        offs = np.zeros(k * 8, np.uint64)
+        nf = self.lib.ref_soatl_layout(cfg, _ptr(sizes, _u64p), k, _ptr(cap, _u64p), _ptr(by, _u64p), _ptr(offs, _u64p))
+        assert nf > 0
+        return [int(c) for c in cap], [int(b) for b in by], [[int(o) for o in row[:nf]] for row in offs.reshape(k, 8)]
+
+    def soatl_dist(self, rx, ry, rz):
+        rx, ry, rz = _f64(rx), _f64(ry), _f64(rz)
+        e = np.zeros(rx.size)
+        t = self.lib.ref_soatl_dist(rx.size, _ptr(rx, _dp), _ptr(ry, _dp), _ptr(rz, _dp), _ptr(e, _dp))
+        return e, t
+
+    def soatl_rmw8(self, cols, s: float, c, align: int = 64) -> float:
+        assert len(cols) == 8
+        n = cols[0].size
+        arr = (_dp * 8)(*[_ptr(col, _dp) for col in cols])
+        c = _f64(c)
+        return self.lib.ref_soatl_rmw8(n, arr, s, _ptr(c, _dp), align)
+
+    def soatl_serialize(self, e, atype, rx, mid, ry, rz) -> np.ndarray:
+        n = len(e)
+        e, rx, ry, rz = _f64(e), _f64(rx), _f64(ry), _f64(rz)
+        atype = np.ascontiguousarray(atype, dtype=np.uint8)
+        mid = np.ascontiguousarray(mid, dtype=np.int32)
+        out = np.zeros(n * 37 + 64, dtype=np.uint8)
+        sz = self.lib.ref_soatl_serialize(n, _ptr(e, _dp), _ptr(atype, _u8p), _ptr(rx, _dp), _ptr(mid, C.POINTER(C.c_int32)),
+                                          _ptr(ry, _dp), _ptr(rz, _dp), _ptr(out, _u8p), out.size)
+        return out[:sz].copy()
+
+    def cell_sum(self, counts, e_concat, schedule: int = 1):
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        e_concat = _f64(e_concat)
+        sums = np.zeros(counts.size)
+        total = C.c_double(0.0)
+        nbytes = C.c_uint64(0)
+        t = self.lib.ref_cell_sum(counts.size, _ptr(counts, _u32p), _ptr(e_concat, _dp), _ptr(sums, _dp), C.byref(total),
+                                  C.byref(nbytes), schedule)
+        return sums, total.value, int(nbytes.value), t
+
+
+orc = _Oracle()
+ref = _Reference()
