@@ -1,0 +1,194 @@
+/* onika_b200.h -- C ABI of the B200-native onika data-parallel execution layer (libonika_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of Collab4exaNBody/onika: onika::parallel
+ * (block_parallel_for / parallel_for dispatch on ParallelExecutionContext / ParallelExecutionStream / queue lanes),
+ * its block reductions and the SOATL field-array streaming.  The reference has no C ABI of its own; its natural
+ * seam is the non-template library code in src/parallel/parallel_execution_queue.cpp (schedule(), sync_and_remove())
+ * calling into per-functor template code.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference tree).  The C++20 front end in include/onika/ (same names and signatures as the
+ * reference headers) and the Python host mirror in onika_b200/ are both thin layers over exactly these symbols.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.  All pointers named *_dev must be device-accessible
+ *     (cudaMalloc / managed / mapped pinned memory).  Pointers named *_host are ordinary host memory.
+ *   - every function returns ONK_OK (0) or a negative ONK_ERR_* code; onk_last_error() gives the message.  The
+ *     reference aborts on error (fatal_error(), src/core/log.cpp:195-204; ONIKA_CU_CHECK_ERRORS,
+ *     include/onika/cuda/cuda_error.h:27-42); the C++ front end turns a non-zero status into fatal_error().
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with ONK_ERR_NO_DEVICE.
+ *   - `lane` is an execution lane as in the reference (include/onika/parallel/constants.h:36-38):
+ *     0..ONK_MAX_LANES-1, ONK_LANE_DEFAULT (-1) means lane 0.  Lane i <-> one non-blocking CUDA stream
+ *     (src/cuda/cuda_context.cpp:70-82).  Work queued on one lane executes in order; lanes may overlap.
+ *   - all compute entry points are asynchronous with respect to the host unless stated; use onk_lane_sync().
+ *   - floating point: unfused IEEE-754 double operations, round-to-nearest (see DESIGN.md "parity rules").
+ */
+#ifndef ONIKA_B200_H
+#define ONIKA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ONK_ABI_VERSION 1
+
+/* ---- status ---- */
+#define ONK_OK               0
+#define ONK_ERR_NO_DEVICE   -1   /* no usable CUDA device / driver */
+#define ONK_ERR_CUDA        -2   /* a CUDA runtime/driver call failed */
+#define ONK_ERR_ARG         -3   /* invalid argument */
+#define ONK_ERR_STATE       -4   /* onk_init() not called, or object in the wrong state */
+#define ONK_ERR_NOMEM       -5
+
+#define ONK_LANE_DEFAULT    -1   /* DEFAULT_EXECUTION_LANE, include/onika/parallel/constants.h:36 */
+#define ONK_LANE_ALL        -2   /* UNDEFINED_EXECUTION_LANE used as "every lane" by wait()/schedule_all() (:37) */
+#define ONK_MAX_LANES      256   /* MAX_EXECUTION_LANES (:38) */
+
+#define ONK_MEM_DEVICE       0   /* cudaMalloc */
+#define ONK_MEM_MANAGED      1   /* cudaMallocManaged: HostAllocationPolicy::CUDA_HOST, include/onika/memory/allocator.h:36-40 */
+#define ONK_MEM_PINNED       2   /* cudaHostAlloc(mapped) : staging buffers and host result slots */
+
+#define ONK_OP_MIN           0
+#define ONK_OP_MAX           1
+#define ONK_OP_SUM           2
+
+int         onk_abi_version(void);
+const char* onk_last_error(void);           /* thread-local message of the last failing call */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * context / device       replaces CudaContext::default_cuda_ctx (src/cuda/cuda_context.cpp:42-58) and the device
+ *                        selection of init_cuda (src/scg-builtin-components/init_cuda.cpp:84-111): one process drives
+ *                        one device.
+ * ------------------------------------------------------------------------------------------------------------ */
+int onk_device_count(int* count);
+int onk_init(int device);                   /* idempotent for the same device */
+int onk_finalize(void);                     /* syncs and destroys lanes, frees scratch */
+int onk_device_info(int* device, int* sm_count, size_t* total_mem, char* name, size_t name_len);
+int onk_device_sync(void);                  /* ONIKA_CU_DEVICE_SYNCHRONIZE */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * lanes -> streams       replaces CudaContext::getThreadStream(lane) (src/cuda/cuda_context.cpp:70-82),
+ *                        ParallelExecutionStreamAutoAllocator (src/parallel/parallel_execution_queue.cpp:32-64),
+ *                        ParallelExecutionStream::wait (include/onika/parallel/parallel_execution_stream.h:55-83)
+ *                        and ParallelExecutionQueue::query_status (parallel_execution_queue.cpp:420-456).
+ * ------------------------------------------------------------------------------------------------------------ */
+int onk_lane_stream(int lane, void** cuda_stream);     /* lazily creates the lane's non-blocking stream */
+int onk_lane_bind_stream(int lane, void* cuda_stream); /* run the lane on a caller-owned stream (e.g. a framework's) */
+int onk_lane_sync(int lane);                           /* ONK_LANE_ALL: every lane */
+int onk_lane_query(int lane, int* idle);               /* *idle = 1 when nothing is pending on the lane */
+int onk_lane_wait_lane(int lane, int other_lane);      /* lane waits (on device) for what is queued on other_lane */
+int onk_lane_host_func(int lane, void (*fn)(void*), void* user);  /* ONIKA_CU_STREAM_HOST_FUNC: hybrid CPU ops ordered in a lane
+                                                                     (block_parallel_for_adapter.h:473-490) */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * memory                 replaces GenericHostAllocator::allocate/deallocate/is_gpu_addressable
+ *                        (src/cuda/allocator.cpp:98-205) and CudaDeviceStorage<T>::New (include/onika/cuda/device_storage.h:48-58).
+ *                        The reference's 12-byte {size,flags} trailer is replaced by a side table keyed by pointer.
+ * ------------------------------------------------------------------------------------------------------------ */
+int onk_alloc(size_t bytes, size_t align, int kind, void** ptr);
+int onk_free(void* ptr, size_t bytes);                 /* bytes must match the allocation (0 = do not check) */
+int onk_is_gpu_addressable(const void* ptr, int* yes);
+int onk_memcpy(void* dst, const void* src, size_t bytes, int lane);   /* ONIKA_CU_MEMCPY: cudaMemcpyDefault, async */
+int onk_memset_bytes(void* dst_dev, int byte, size_t bytes, int lane);/* ONIKA_CU_MEMSET */
+int onk_prefetch(const void* ptr, size_t bytes, int to_device, int lane); /* ONIKA_CU_MEM_PREFETCH (managed memory) */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * parallel-operation bracket   replaces the CUDA branch of ParallelExecutionQueue::schedule
+ *                        (src/parallel/parallel_execution_queue.cpp:316-358): start event, H2D copy of the return-data
+ *                        initial value, counter reset, [kernel], epilog callback, D2H copy of return data, stop event;
+ *                        and the timing read-back of sync_and_remove (:387-392).
+ *                        The device scratch is the reference's GPUKernelExecutionScratch (1 KiB: 8 x u64 counters +
+ *                        960 B return data, include/onika/parallel/parallel_execution_context.h:56-66).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct onk_op onk_op;
+#define ONK_OP_SCRATCH_BYTES      1024
+#define ONK_OP_MAX_RETURN_BYTES    960
+int onk_op_create(onk_op** op);
+int onk_op_destroy(onk_op* op);
+int onk_op_device_scratch(onk_op* op, void** scratch_dev);   /* init_device_scratch(), parallel_execution_context.cpp:102-118 */
+int onk_op_begin(onk_op* op, int lane, const void* return_init_host, size_t return_bytes, int reset_counters);
+int onk_op_end(onk_op* op, void* return_out_host, size_t return_bytes, void (*epilog)(void*), void* user);
+int onk_op_elapsed_ms(onk_op* op, float* ms);                /* valid after the lane was synchronised */
+
+/* generic kernel launch  replaces ONIKA_CU_LAUNCH_KERNEL (include/onika/cuda/cuda.h:264) at its three call sites
+ *                        (block_parallel_for_adapter.h:186,197,206).  `cu_function` is a CUfunction handle
+ *                        (cudaGetFuncBySymbol in the plugin's translation unit), so device code for user functors
+ *                        stays in the plugin, as in the reference. */
+int onk_launch(void* cu_function, const unsigned grid[3], const unsigned block[3], size_t shared_bytes, int lane, void** args);
+int onk_launch_count(uint64_t* n);          /* kernels launched by this library since onk_init (all entry points) */
+
+/* lane sequence capture  CUDA-graph capture of everything queued on a set of lanes between begin and end
+ *                        (the per-op overhead the reference pays on every schedule(), SURVEY 7 "hard parts" (e)). */
+typedef struct onk_graph onk_graph;
+int onk_graph_begin(int origin_lane, const int* other_lanes, int n_other);
+int onk_graph_end(onk_graph** graph);
+int onk_graph_launch(onk_graph* graph, int lane);
+int onk_graph_destroy(onk_graph* graph);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * typed fast paths       (none in the reference: its GPU side is three 10-line trampolines, one functor call per
+ *                        block: block_parallel_for_adapter.h:51-104.)  Each names the reference *behaviour* it
+ *                        reproduces; results are bit-identical to the reference OpenMP path unless noted.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* reductions.  MIN follows cpu_compute, tests/gpu_reduce_min_fp64.cu:46-55 (identity DBL_MAX, `if(d[i]<m) m=d[i]`,
+ * NaNs ignored); MAX is its mirror (identity -DBL_MAX); SUM is the return-data accumulation idiom
+ * with a fixed, run-to-run reproducible summation tree (|err| <= 1e-12 * sum|d| against any order).
+ * out_dev receives one double.  n == 0 yields the identity. */
+int onk_reduce_f64(int op, const double* in_dev, uint64_t n, double* out_dev, int lane);
+/* fixed-order combine of `count` partials (cross-GPU: all-gathered per-rank partials; the counterpart of
+ * mpi::all_reduce_multi, include/onika/mpi/all_reduce_multi.h:30-37) */
+int onk_combine_f64(int op, const double* partials_dev, uint32_t count, double* out_dev, int lane);
+
+/* parallel_for(N, y[i] += a*x[i])   include/onika/parallel/parallel_for.h:91-112 (config C1) */
+int onk_axpy_f64(double* y_dev, const double* x_dev, double a, uint64_t n, int lane);
+/* parallel_memset<T>                include/onika/parallel/memset.h:30-51 ; elem_bytes in {1,2,4,8}, value = low bytes of pattern */
+int onk_parallel_memset(void* data_dev, uint64_t n, uint64_t pattern, int elem_bytes, int lane);
+/* block_parallel_for(rows, BlockParallelValueAddFunctor)   include/onika/extras/block_parallel_value_add_functor.h:15-58 */
+int onk_value_add_f64(double* array_dev, uint64_t rows, uint64_t cols, double value, int lane);
+
+/* ---- SOATL (include/onika/soatl) ---- */
+/* ChunkLogAllocationStrategy::update_capacity, include/onika/memory/alloc_strategy.h:44-67 (host arithmetic) */
+uint64_t onk_soatl_update_capacity(uint64_t size, uint64_t capacity, uint64_t chunk);
+/* column offsets of FieldArrays<A,C,ids...> for a given capacity, field_arrays.h:494-512; returns storage bytes */
+uint64_t onk_soatl_layout(uint64_t align, const uint32_t* field_bytes, int nfields, uint64_t capacity, uint64_t* offsets);
+/* soatl::parallel_apply_simd over nfields fp64 columns of one packed allocation: f_k[i] = f_k[i]*s + c_k
+ * (config C3; compute.h:214-232 semantics incl. the ceil(n/chunk)*chunk padding sweep) */
+int onk_soatl_rmw_f64(void* storage_dev, uint64_t align, uint64_t chunk, int nfields, uint64_t n, uint64_t capacity,
+                      double s, const double* c_host, int lane);
+/* the stock benchmark kernel tests/benchmark.cpp:96-104 (3 reads + 1 write), columns given by pointer */
+int onk_soatl_dist_f64(double* e_dev, const double* rx_dev, const double* ry_dev, const double* rz_dev,
+                       uint64_t n_padded, double ax, double ay, double az, int lane);
+/* soatl::copy between two layouts of the same field list (include/onika/soatl/copy.h:29-97;
+ * tests/soatlserializetest.cpp:86-104): e.g. <64,8,...> <-> the <1,1,...> wire format */
+int onk_soatl_repack(void* dst_dev, uint64_t dst_align, uint64_t dst_capacity,
+                     const void* src_dev, uint64_t src_align, uint64_t src_capacity,
+                     const uint32_t* field_bytes, int nfields, uint64_t n, int lane);
+
+/* ---- cell grid (config C4): cells = SOATL blocks packed back to back in one arena ---- */
+/* capacity/offset of every cell (host arithmetic; cell c's block starts at cell_off[c], aligned to cell_align) */
+uint64_t onk_cell_grid_layout(const uint32_t* cell_size, uint64_t ncells, uint64_t align, uint64_t chunk,
+                              const uint32_t* field_bytes, int nfields, uint64_t cell_align,
+                              uint32_t* cell_cap, uint64_t* cell_off);
+/* block_parallel_for(ncells, per-cell sum of an fp64 field) + global sum.  cell_sum_dev[c] is the in-order sum of the
+ * cell's particles for sizes <= 32 and a fixed tree above (|err| <= 1e-12 relative); total_dev (optional) is the
+ * fixed-order sum of the cell sums.  field_offset_fn: the field is column `field` of FieldArrays<align,chunk,...>. */
+int onk_cell_sum_f64(const void* arena_dev, const uint64_t* cell_off_dev, const uint32_t* cell_size_dev,
+                     const uint32_t* cell_cap_dev, uint64_t ncells, uint64_t align,
+                     const uint32_t* field_bytes, int nfields, int field,
+                     double* cell_sum_dev, double* total_dev, int lane);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * host-buffer entry points   what a reference plugin holding HOST data calls: input in ordinary host memory, result in
+ *                        host memory, synchronous.  Host<->device copies are chunked and overlapped with the kernels on
+ *                        two internal lanes (pinned staging).  These are the `e2e` calls of bench.py.
+ * ------------------------------------------------------------------------------------------------------------ */
+int onk_host_reduce_f64(int op, const double* in_host, uint64_t n, double* out_host);
+int onk_host_axpy_f64(double* y_host, const double* x_host, double a, uint64_t n);
+int onk_host_value_add_f64(double* array_host, uint64_t rows, uint64_t cols, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONIKA_B200_H */

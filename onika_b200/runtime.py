@@ -1,0 +1,64 @@
+"""Context, lanes and small helpers over the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _capi
+from ._capi import check, lib
+
+
+def init(device: int = 0) -> None:
+    """onk_init: one process drives one device (reference: init_cuda device selection, init_cuda.cpp:84-111)."""
+    check(lib().onk_init(device))
+
+
+def finalize() -> None:
+    check(lib().onk_finalize())
+
+
+def device_info() -> dict:
+    dev, sms, mem = C.c_int(), C.c_int(), C.c_size_t()
+    name = C.create_string_buffer(256)
+    check(lib().onk_device_info(C.byref(dev), C.byref(sms), C.byref(mem), name, 256))
+    return {"device": dev.value, "sm_count": sms.value, "total_mem": mem.value, "name": name.value.decode()}
+
+
+def launch_count() -> int:
+    n = C.c_uint64()
+    check(lib().onk_launch_count(C.byref(n)))
+    return n.value
+
+
+def lane_sync(lane: int = _capi.LANE_ALL) -> None:
+    check(lib().onk_lane_sync(lane))
+
+
+def lane_idle(lane: int = _capi.LANE_ALL) -> bool:
+    idle = C.c_int()
+    check(lib().onk_lane_query(lane, C.byref(idle)))
+    return bool(idle.value)
+
+
+def lane_stream(lane: int) -> int:
+    s = C.c_void_p()
+    check(lib().onk_lane_stream(lane, C.byref(s)))
+    return s.value or 0
+
+
+def bind_lane_to_torch_stream(lane: int, stream=None) -> None:
+    """Run `lane` on a torch stream (default: torch's current stream) so torch.cuda.Event timing sees the kernels."""
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    check(lib().onk_lane_bind_stream(lane, C.c_void_p(stream.cuda_stream)))
+
+
+def ptr(t) -> C.c_void_p:
+    """Device (or pinned host) pointer of a torch tensor / numpy array / int."""
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    if hasattr(t, "data_ptr"):
+        return C.c_void_p(t.data_ptr())
+    if hasattr(t, "ctypes"):
+        return C.c_void_p(t.ctypes.data)
+    raise TypeError(f"cannot take the address of {type(t)}")

@@ -1,0 +1,466 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle on the same seeded inputs, against the
+committed golden vectors (produced by the real reference), and -- at BASELINE.json's full sizes -- through
+size-independent properties.  Bit-exact for min/max, element-wise streaming, integer/index work and in-cell sums;
+|err| <= 1e-12 * sum|x| for order-dependent fp64 sums."""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")
+SUM_RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(GOLD) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import torch
+    import onika_b200 as ob
+    assert torch.cuda.is_available()
+    ob.init(0)
+    yield ob
+    ob.lane_sync()
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+# ---------------------------------------------------------------- reductions
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 255, 256, 4095, 4096, 4097, 65536 + 7, 1_000_003, (1 << 22) + 5])
+def test_reduce_vs_oracle(ob, orc, n):
+    from tests._inputs import lcg_uniform
+    from onika_b200 import parallel as P
+    d = lcg_uniform(n, 17 + n % 13, -1.0, 1.0)
+    t = dev(d) if n else dev(np.zeros(1))[:0]
+    assert host(P.reduce_min(t, n=n))[0] == orc.reduce_min(d)
+    assert host(P.reduce_max(t, n=n))[0] == orc.reduce_max(d)
+    s = host(P.reduce_sum(t, n=n))[0]
+    assert abs(s - orc.reduce_sum_ld(d)) <= SUM_RTOL * max(np.abs(d).sum(), 1e-300)
+    assert abs(s - orc.reduce_sum(d, 8)) <= SUM_RTOL * max(np.abs(d).sum(), 1e-300)
+    if n:
+        assert s == host(P.reduce_sum(t, n=n))[0]          # run-to-run reproducible
+
+
+def test_reduce_misaligned_views(ob, orc):
+    from tests._inputs import lcg_uniform
+    from onika_b200 import parallel as P
+    d = lcg_uniform(300_000, 5)
+    t = dev(d)
+    for start in (1, 2, 3, 5):
+        for n in (1, 100, 4096, 200_001):
+            v = t[start:start + n]
+            assert host(P.reduce_min(v))[0] == orc.reduce_min(d[start:start + n])
+            assert abs(host(P.reduce_sum(v))[0] - orc.reduce_sum_ld(d[start:start + n])) <= SUM_RTOL * np.abs(d[start:start + n]).sum()
+
+
+def test_reduce_min_reference_fixture_and_golden(ob, gold):
+    from tests._inputs import lcg_uniform
+    from onika_b200 import parallel as P
+    n = 1 << 20
+    ramp = np.arange(n, dtype=np.float64) * 1.0 / n       # tests/gpu_reduce_min_fp64.cu:38-43
+    assert host(P.reduce_min(dev(ramp)))[0] == float.fromhex(gold["reduce_min"][0]["min"]) == 0.0
+    for g in gold["reduce_min"][1:]:
+        d = lcg_uniform(g["n"], g["seed"])
+        if g["kind"] == "lcg_planted":
+            d[g["planted_index"]] = float.fromhex(g["planted_value"])
+        assert host(P.reduce_min(dev(d)))[0] == float.fromhex(g["min"])
+
+
+def test_reduce_nan_and_identity_semantics(ob):
+    from onika_b200 import parallel as P
+    d = np.array([5.0, np.nan, 2.0, np.nan, 7.0] * 1000)
+    assert host(P.reduce_min(dev(d)))[0] == 2.0            # `d[i] < m` ignores NaNs
+    assert host(P.reduce_max(dev(d)))[0] == 7.0
+    e = dev(np.zeros(1))[:0]
+    assert host(P.reduce_min(e, n=0))[0] == sys.float_info.max
+    assert host(P.reduce_max(e, n=0))[0] == -sys.float_info.max
+    assert host(P.reduce_sum(e, n=0))[0] == 0.0
+
+
+def test_reduce_min_full_size_2pow28_properties(ob):
+    """config C2 at full size: 2^28 doubles = 2 GiB; a planted minimum must be found wherever it sits, min of the
+    untouched array equals min over halves (min of mins), and the result is bit-reproducible."""
+    import torch
+    from onika_b200 import parallel as P
+    n = 1 << 28
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    t = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * (1.0 - 1e-3) + 1e-3
+    m = host(P.reduce_min(t))[0]
+    assert m == float(t.min().item())
+    lo, hi = host(P.reduce_min(t[: n // 2]))[0], host(P.reduce_min(t[n // 2:]))[0]
+    assert m == min(lo, hi)
+    for idx in (0, 1, 4095, 4096, n // 3, n - 2, n - 1):
+        old = t[idx].item()
+        t[idx] = 1e-9
+        assert host(P.reduce_min(t))[0] == 1e-9, idx
+        t[idx] = old
+    assert host(P.reduce_min(t))[0] == m
+    s1, s2 = host(P.reduce_sum(t))[0], host(P.reduce_sum(t))[0]
+    assert s1 == s2
+    ref = float(t.sum().item())
+    assert abs(s1 - ref) <= SUM_RTOL * ref                  # all positive: sum|x| = sum
+    del t
+
+
+# ---------------------------------------------------------------- streaming
+@pytest.mark.parametrize("n", [1, 7, 2047, 2048, 2049, 100_003, 1_000_003])
+def test_axpy_vs_oracle(ob, orc, n):
+    from tests._inputs import lcg_uniform
+    from onika_b200 import parallel as P
+    x, y = lcg_uniform(n, 1, -1, 1), lcg_uniform(n, 2, -1, 1)
+    yo = y.copy()
+    orc.axpy(yo, x, 0.5)
+    ty, tx = dev(y), dev(x)
+    P.parallel_for(n, P.AxpyFunctor(ty, tx, 0.5)).run()
+    assert np.array_equal(host(ty), yo)
+
+
+def test_axpy_golden_and_misaligned(ob, orc, gold):
+    from tests._inputs import unhx, lcg_uniform
+    from onika_b200 import parallel as P
+    g = gold["axpy"]
+    ty, tx = dev(unhx(g["y"])), dev(unhx(g["x"]))
+    P.parallel_for(g["n"], P.AxpyFunctor(ty, tx, g["a"])).run()
+    assert np.array_equal(host(ty), unhx(g["y_out"]))
+    n = 50_000
+    x, y = lcg_uniform(n + 8, 3, -1, 1), lcg_uniform(n + 8, 4, -1, 1)
+    for sx, sy in ((1, 0), (0, 3), (1, 1), (2, 3)):
+        ty, tx = dev(y), dev(x)
+        yo = y.copy()
+        orc.axpy(yo[sy:sy + n], x[sx:sx + n], -1.25)
+        P.parallel_for(n, P.AxpyFunctor(ty[sy:], tx[sx:], -1.25)).run()
+        assert np.array_equal(host(ty), yo)               # also proves nothing outside the range was touched
+
+
+def test_axpy_config_c1_10m(ob, orc):
+    from tests._inputs import lcg_uniform
+    from onika_b200 import parallel as P
+    n = 10_000_000
+    x, y = lcg_uniform(n, 1234, -1, 1), lcg_uniform(n, 4321, -1, 1)
+    yo = y.copy()
+    orc.axpy(yo, x, 0.5)
+    ty, tx = dev(y), dev(x)
+    P.parallel_for(n, P.AxpyFunctor(ty, tx, 0.5)).run()
+    assert np.array_equal(host(ty), yo)
+
+
+def test_parallel_memset(ob, gold):
+    import torch
+    from tests._inputs import unhx
+    from onika_b200 import parallel as P, _capi
+    g = gold["memset"]
+    t = torch.zeros(g["n"], dtype=torch.float64, device="cuda")
+    P.parallel_memset(t, g["n"], g["v"]).run()
+    assert np.array_equal(host(t), unhx(g["out"]))
+    # every element size, unaligned starts, guard bytes untouched
+    for eb, dt in ((1, torch.uint8), (2, torch.int16), (4, torch.int32), (8, torch.int64)):
+        for start in (0, 1, 3):
+            for n in (1, 5, 63, 4096, 100_001):
+                buf = torch.full((n + 16,), 7, dtype=dt, device="cuda")
+                pat = 0xA1B2C3D4E5F60718 & ((1 << (8 * eb)) - 1)
+                _capi.check(_capi.lib().onk_parallel_memset(buf[start:].data_ptr(), n, pat, eb, 0))
+                ob.lane_sync()
+                h = buf.cpu().numpy()
+                want = np.array([pat], dtype=np.uint64).astype({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[eb]).view(h.dtype)[0]
+                assert (h[start:start + n] == want).all() and (h[:start] == 7).all() and (h[start + n:] == 7).all()
+
+
+def test_value_add_and_lane_sequence(ob, orc, gold):
+    from tests._inputs import unhx, lcg_uniform
+    from onika_b200 import parallel as P
+    g = gold["value_add"]
+    t = dev(unhx(g["a"]).reshape(g["rows"], g["cols"]))
+    P.block_parallel_for(g["rows"], P.BlockParallelValueAddFunctor(t, g["v"])).run()
+    assert np.array_equal(host(t).ravel(), unhx(g["out_1d"]))
+    # tests/parallel_queue_lane.cu "hybrid-lane" / "hybrid-delayed-lane" / "hybrid-sequence" with value-add kernels
+    gl = gold["lane_sequence"]
+    v = gl["v"]
+    for mode in (0, 1, 2):
+        a1 = dev(unhx(gl["a1"]).reshape(gl["rows"], gl["cols"]))
+        a2 = dev(unhx(gl["a2"]).reshape(gl["rows"], gl["cols"]))
+        q = P.ParallelExecutionQueue()
+        op11 = P.block_parallel_for(gl["rows"], P.BlockParallelValueAddFunctor(a1, v[0]))
+        op12 = P.block_parallel_for(gl["rows"], P.BlockParallelValueAddFunctor(a1, v[1]))
+        op21 = P.block_parallel_for(gl["rows"], P.BlockParallelValueAddFunctor(a2, v[2]))
+        op22 = P.block_parallel_for(gl["rows"], P.BlockParallelValueAddFunctor(a2, v[3]))
+        if mode == 0:
+            q << P.set_lane(0) << op11 << P.set_lane(1) << op21 << P.set_lane(0) << op12 << P.set_lane(1) << op22
+        elif mode == 1:
+            qa, qb = P.ParallelExecutionQueueBase(), P.ParallelExecutionQueueBase()
+            qa << P.set_lane(0) << op11 << P.set_lane(1) << op21
+            qb << P.set_lane(0) << op12 << P.set_lane(1) << op22
+            q << qa << qb
+        else:
+            q << op11 << op12 << op21 << op22
+        q << P.flush << P.synchronize
+        run = [r for r in gl["runs"] if r["mode"] == mode][0]
+        assert np.array_equal(host(a1).ravel(), unhx(run["a1_out"]))
+        assert np.array_equal(host(a2).ravel(), unhx(run["a2_out"]))
+    # larger arrays against the oracle, with sums and mins of the result (config C5 shape, scaled down)
+    rows, cols = 1024, 1024
+    h1, h2 = lcg_uniform(rows * cols, 8).reshape(rows, cols), lcg_uniform(rows * cols, 9).reshape(rows, cols)
+    a1, a2 = dev(h1), dev(h2)
+    q = P.ParallelExecutionQueue()
+    q << P.set_lane(0) << P.block_parallel_for(rows, P.BlockParallelValueAddFunctor(a1, 1.1)) \
+      << P.set_lane(1) << P.block_parallel_for(rows, P.BlockParallelValueAddFunctor(a2, 1.3)) \
+      << P.set_lane(0) << P.block_parallel_for(rows, P.BlockParallelValueAddFunctor(a1, 1.2)) \
+      << P.set_lane(1) << P.block_parallel_for(rows, P.BlockParallelValueAddFunctor(a2, 1.4)) << P.flush
+    m1 = P.reduce_min(a1, lane=0)
+    m2 = P.reduce_min(a2, lane=1)
+    s1 = P.reduce_sum(a1, lane=0)
+    q << P.synchronize
+    ob.lane_sync()
+    orc.lane_sequence(h1, h2, 1.1, 1.2, 1.3, 1.4)
+    assert np.array_equal(host(a1), h1) and np.array_equal(host(a2), h2)
+    assert host(m1)[0] == h1.min() and host(m2)[0] == h2.min()
+    assert abs(host(s1)[0] - orc.reduce_sum_ld(h1.ravel())) <= SUM_RTOL * np.abs(h1).sum()
+
+
+def test_lane_graph_capture_replays_the_sequence(ob, orc):
+    import torch
+    from tests._inputs import lcg_uniform
+    from onika_b200 import _capi
+    L = _capi.lib()
+    rows, cols = 512, 512
+    h1, h2 = lcg_uniform(rows * cols, 8).reshape(rows, cols), lcg_uniform(rows * cols, 9).reshape(rows, cols)
+    a1, a2 = dev(h1), dev(h2)
+    ob.lane_sync()
+    others = (C.c_int * 1)(1)
+    n0 = ob.launch_count()
+    _capi.check(L.onk_graph_begin(0, others, 1))
+    _capi.check(L.onk_value_add_f64(a1.data_ptr(), rows, cols, 1.1, 0))
+    _capi.check(L.onk_value_add_f64(a2.data_ptr(), rows, cols, 1.3, 1))
+    _capi.check(L.onk_value_add_f64(a1.data_ptr(), rows, cols, 1.2, 0))
+    _capi.check(L.onk_value_add_f64(a2.data_ptr(), rows, cols, 1.4, 1))
+    gph = C.c_void_p()
+    _capi.check(L.onk_graph_end(C.byref(gph)))
+    assert ob.launch_count() == n0                          # capture launches nothing
+    assert np.array_equal(host(a1), h1)
+    for _ in range(3):
+        _capi.check(L.onk_graph_launch(gph, 0))
+        orc.lane_sequence(h1, h2, 1.1, 1.2, 1.3, 1.4)
+    ob.lane_sync()
+    assert ob.launch_count() == n0 + 12
+    assert np.array_equal(host(a1), h1) and np.array_equal(host(a2), h2)
+    _capi.check(L.onk_graph_destroy(gph))
+
+
+# ---------------------------------------------------------------- SOATL
+def test_soatl_field_arrays_layout_resize_and_serialize(ob, orc, gold):
+    from tests._inputs import unhx
+    from onika_b200 import soatl
+    g = gold["soatl_serialize"]
+    n = g["n"]
+    fields = [("e", "f8"), ("atype", "u1"), ("rx", "f8"), ("mid", "i4"), ("ry", "f8"), ("rz", "f8")]
+    fa = soatl.make_hybrid_field_arrays(64, 8, fields)
+    fa.resize(n)
+    assert fa.capacity() == 16 and fa.storage_size() == orc.layout(64, [8, 1, 8, 4, 8, 8], 16)[0]
+    fa.set_column("e", unhx(g["e"])); fa.set_column("atype", np.array(g["atype"], np.uint8))
+    fa.set_column("rx", unhx(g["rx"])); fa.set_column("mid", np.array(g["mid"], np.int32))
+    fa.set_column("ry", unhx(g["ry"])); fa.set_column("rz", unhx(g["rz"]))
+    wire = soatl.make_hybrid_field_arrays(1, 1, fields)
+    wire.copy_from(fa)
+    ob.lane_sync()
+    assert host(wire.storage).tobytes().hex() == g["packed_hex"]      # byte-identical to the reference's wire format
+    back = soatl.make_hybrid_field_arrays(64, 8, fields)
+    back.copy_from(wire)
+    ob.lane_sync()
+    for name, _ in fields:
+        assert np.array_equal(host(back[name])[:n], host(fa[name])[:n])
+    # growth keeps the contents (reallocate + per-column copy, field_arrays.h:513-580)
+    fa.resize(1000)
+    assert fa.capacity() == 1000
+    assert np.array_equal(host(fa["rx"])[:n], unhx(g["rx"])) and np.array_equal(host(fa["mid"])[:n], np.array(g["mid"], np.int32))
+    fa.resize(0)
+    assert fa.capacity() == 0 and fa.storage is None                  # tests/soatupletest.cpp:74-119
+    wire.clear(); back.clear()
+
+
+@pytest.mark.parametrize("align", [64, 256])
+@pytest.mark.parametrize("n", [1, 37, 4096, 100_003, 1_048_576 + 5])
+def test_soatl_rmw8_vs_oracle(ob, orc, gold, align, n):
+    from tests._inputs import lcg_uniform, unhx
+    from onika_b200 import soatl
+    fields = [(f"f{k}", "f8") for k in range(8)]
+    fa = soatl.make_hybrid_field_arrays(align, 16, fields)
+    fa.resize(n)
+    fa.storage.zero_()
+    if n == 37:
+        g = gold["soatl_rmw8"]
+        cols, s, c = [unhx(col) for col in g["cols"]], g["s"], g["c"]
+    else:
+        cols, s, c = [lcg_uniform(n, 20 + k, 0, 1) for k in range(8)], 1.0000001, [0.125 * (k + 1) for k in range(8)]
+    for k in range(8):
+        fa.set_column(f"f{k}", cols[k])
+    st = host(fa.storage).copy()
+    fa.parallel_apply_rmw(s, c)
+    ob.lane_sync()
+    orc.soatl_rmw(st, align, 16, 8, n, fa.capacity(), s, c)
+    assert np.array_equal(host(fa.storage), st)            # whole allocation, padding sweep included
+    if n == 37:
+        for k in range(8):
+            assert np.array_equal(host(fa[f"f{k}"])[:n], unhx(gold["soatl_rmw8"]["out"][k]))
+    fa.clear()
+
+
+@pytest.mark.parametrize("n", [53, 4096, 100_003])
+def test_soatl_dist_vs_oracle(ob, orc, gold, n):
+    from tests._inputs import lcg_uniform, unhx
+    from onika_b200 import soatl
+    if n == 53:
+        g = gold["soatl_dist"]
+        rx, ry, rz = unhx(g["rx"]), unhx(g["ry"]), unhx(g["rz"])
+    else:
+        rx, ry, rz = lcg_uniform(n, 10, 0, 1), lcg_uniform(n, 11, 0, 1), lcg_uniform(n, 12, 0, 1)
+    fa = soatl.make_hybrid_field_arrays(64, 16, [("rx", "f8"), ("ry", "f8"), ("rz", "f8"), ("e", "f8")])
+    fa.resize(n)
+    for name, v, pad in (("rx", rx, 2.0), ("ry", ry, 3.0), ("rz", rz, 4.0)):
+        fa[name].fill_(pad)
+        fa.set_column(name, v)
+    fa.parallel_apply_dist("e", "rx", "ry", "rz", float(rx[0]), float(ry[0]), float(rz[0]))
+    ob.lane_sync()
+    e = host(fa["e"])[:n]
+    want = orc.soatl_dist(rx, ry, rz)
+    assert np.isnan(e[0]) and np.array_equal(e, want, equal_nan=True)
+    if n == 53:
+        assert np.array_equal(e, unhx(gold["soatl_dist"]["e"]), equal_nan=True)
+    fa.clear()
+
+
+# ---------------------------------------------------------------- cell grid
+def test_cell_sum_golden(ob, gold):
+    from tests._inputs import unhx
+    from onika_b200 import cellgrid
+    g = gold["cell_sum"]
+    counts = np.array(g["counts"], np.uint32)
+    e = unhx(g["e"])
+    cg = cellgrid.CellGrid(counts, 64, 16, (8, 8, 8, 8), 64)
+    assert cg.arena_bytes == g["allocated_bytes"]
+    cg.upload(cg.host_arena_with_field(3, e))
+    sums, total = cg.cell_sum(3)
+    ob.lane_sync()
+    assert np.array_equal(host(sums), unhx(g["cell_sum"]))
+    assert abs(host(total)[0] - float.fromhex(g["total"])) <= SUM_RTOL * np.abs(e).sum()
+
+
+@pytest.mark.parametrize("side,maxn", [(1, 64), (7, 64), (32, 64), (64, 200)])
+def test_cell_sum_vs_oracle(ob, orc, side, maxn):
+    from tests._inputs import lcg_uniform, poisson_counts
+    from onika_b200 import cellgrid
+    counts = poisson_counts(side ** 3, 16.0, 42, 0, maxn)
+    if maxn > 64:
+        counts[::97] = maxn            # a few long cells exercise the multi-round path
+        counts[5] = 0
+    e = lcg_uniform(int(counts.sum()), 40, -1, 1)
+    for field, fb in ((3, (8, 8, 8, 8)), (0, (8, 8, 8, 8)), (4, (8, 8, 8, 1, 8, 4))):
+        cg = cellgrid.CellGrid(counts, 64, 16, fb, 64)
+        arena = cg.host_arena_with_field(field, e)
+        cg.upload(arena)
+        sums, total = cg.cell_sum(field)
+        ob.lane_sync()
+        so, to = orc.cell_sum(arena, cg.cell_off_host, cg.cell_size_host, cg.cell_cap_host, 64, list(fb), field)
+        assert np.array_equal(host(sums), so)               # in-cell order is sequential on both sides
+        assert abs(host(total)[0] - to) <= SUM_RTOL * max(np.abs(e).sum(), 1e-300)
+        s2, t2 = cg.cell_sum(field)
+        ob.lane_sync()
+        assert host(t2)[0] == host(total)[0]                # reproducible total
+
+
+def test_cell_sum_config_c4_full_size_properties(ob):
+    """128^3 cells x ~16 particles: every e = 1.0 makes the sums exact integers => cell_sum == counts, total == N."""
+    from tests._inputs import poisson_counts
+    from onika_b200 import cellgrid
+    counts = poisson_counts(128 ** 3)
+    cg = cellgrid.CellGrid(counts, 64, 16, (8, 8, 8, 8), 64)
+    cg.upload(cg.host_arena_with_field(3, np.ones(int(counts.sum()))))
+    sums, total = cg.cell_sum(3)
+    ob.lane_sync()
+    assert np.array_equal(host(sums), counts.astype(np.float64))
+    assert host(total)[0] == float(counts.sum())
+
+
+# ---------------------------------------------------------------- op bracket, host-buffer paths, errors
+def test_op_bracket_return_data_and_timing(ob):
+    """the return-data protocol of schedule(): host value copied in before, out after (parallel_execution_queue.cpp:331-352)"""
+    import torch
+    from onika_b200 import _capi
+    L = _capi.lib()
+    op = C.c_void_p()
+    _capi.check(L.onk_op_create(C.byref(op)))
+    scratch = C.c_void_p()
+    _capi.check(L.onk_op_device_scratch(op, C.byref(scratch)))
+    init = np.array([1.5, -2.5], np.float64)
+    out = np.zeros(2)
+    fired = []
+    CB = C.CFUNCTYPE(None, C.c_void_p)
+    cb = CB(lambda p: fired.append(1))
+    _capi.check(L.onk_op_begin(op, 2, init.ctypes.data, 16, 1))
+    # a kernel working on the device-side return data: value-add on the 2 doubles at scratch+64
+    _capi.check(L.onk_value_add_f64(scratch.value + 64, 1, 2, 10.0, 2))
+    _capi.check(L.onk_op_end(op, out.ctypes.data, 16, C.cast(cb, C.c_void_p), None))
+    ob.lane_sync(2)
+    assert np.array_equal(out, init + 10.0) and fired == [1]
+    ms = C.c_float()
+    _capi.check(L.onk_op_elapsed_ms(op, C.byref(ms)))
+    assert ms.value >= 0.0
+    assert L.onk_op_begin(op, 2, init.ctypes.data, 2000, 0) == _capi.ERR_ARG   # > 960 B of return data is rejected
+    _capi.check(L.onk_op_destroy(op))
+
+
+def test_host_buffer_entry_points(ob, orc):
+    import torch
+    from tests._inputs import lcg_uniform
+    from onika_b200 import parallel as P, _capi
+    n = (20 << 20) + 12345                                   # > 2 staging chunks, ragged tail
+    d = lcg_uniform(n, 77, -1, 1)
+    pinned = torch.from_numpy(d).pin_memory()
+    for src in (d, pinned):                                  # pageable and pinned host memory
+        assert P.host_reduce(_capi.OP_MIN, src) == orc.reduce_min(d)
+        assert P.host_reduce(_capi.OP_MAX, src) == orc.reduce_max(d)
+        assert abs(P.host_reduce(_capi.OP_SUM, src) - orc.reduce_sum_ld(d)) <= SUM_RTOL * np.abs(d).sum()
+    x, y = lcg_uniform(n, 1, -1, 1), lcg_uniform(n, 2, -1, 1)
+    yo = y.copy()
+    orc.axpy(yo, x, 0.5)
+    P.host_axpy(y, x, 0.5)
+    assert np.array_equal(y, yo)
+    a = lcg_uniform(3000 * 3001, 3).reshape(3000, 3001)
+    ao = a.copy()
+    orc.value_add(ao, 1.1)
+    P.host_value_add(a, 1.1)
+    assert np.array_equal(a, ao)
+
+
+def test_errors_and_memory_api(ob):
+    from onika_b200 import _capi
+    L = _capi.lib()
+    p = C.c_void_p()
+    _capi.check(L.onk_alloc(1 << 20, 256, _capi.MEM_DEVICE, C.byref(p)))
+    yes = C.c_int()
+    _capi.check(L.onk_is_gpu_addressable(p, C.byref(yes)))
+    assert yes.value == 1 and p.value % 256 == 0
+    assert L.onk_free(p, 123) == _capi.ERR_ARG               # size mismatch is an error (allocator.cpp:73-96)
+    _capi.check(L.onk_free(p, 1 << 20))
+    h = np.zeros(4)
+    _capi.check(L.onk_is_gpu_addressable(h.ctypes.data, C.byref(yes)))
+    assert yes.value == 0
+    assert L.onk_reduce_f64(9, None, 0, p, 0) == _capi.ERR_ARG
+    assert L.onk_lane_sync(300) == _capi.ERR_ARG
+    info = ob.device_info()
+    assert info["sm_count"] > 0 and "B200" in info["name"]
+    assert ob.launch_count() > 0
