@@ -20,6 +20,7 @@ namespace onk
   int fail_cuda(cudaError_t e, const char* what, const char* file, int line)
   {
     set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    cudaGetLastError();   // reset the (non-sticky) last-error state so that the next call does not report it again
     if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return ONK_ERR_NO_DEVICE;
     if (e == cudaErrorMemoryAllocation) return ONK_ERR_NOMEM;
     return ONK_ERR_CUDA;
@@ -449,6 +450,8 @@ int onk_graph_begin(int origin_lane, const int* other_lanes, int n_other)
   ONK_REQUIRE(!g_capture.active, "onk_graph_begin: a capture is already active");
   ONK_REQUIRE(n_other == 0 || other_lanes != nullptr, "onk_graph_begin: null lane list");
   Lane* O; if (int rc = lane_get(origin_lane, &O)) return rc;
+  ONK_REQUIRE(O->stream != nullptr && O->stream != cudaStreamLegacy,
+              "onk_graph_begin: lane %d runs on the legacy default stream, which cannot be captured", origin_lane);
   std::vector<cudaStream_t> others;
   for (int i = 0; i < n_other; i++) { Lane* L; if (int rc = lane_get(other_lanes[i], &L)) return rc; if (L->stream != O->stream) others.push_back(L->stream); }
   ONK_CUDA(cudaStreamBeginCapture(O->stream, cudaStreamCaptureModeThreadLocal));

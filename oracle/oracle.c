@@ -16,6 +16,18 @@
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
 
+void orc_fill_lcg_f64(double* d, uint64_t n, uint64_t seed, double lo, double hi)
+{
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)n; i++)
+  {
+    uint64_t h = ((uint64_t)i * 2654435761ull + seed * 40503ull + 12345ull) & 0xFFFFFFFFull;
+    h = ((h ^ (h >> 15)) * 2246822519ull) & 0xFFFFFFFFull;
+    h = (h ^ (h >> 13)) & 0xFFFFFFFFull;
+    d[i] = lo + (hi - lo) * ((double)h / 4294967296.0);
+  }
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* reductions                                                                                        */
 /* ------------------------------------------------------------------------------------------------ */

@@ -20,6 +20,11 @@ extern "C" {
 
 int orc_num_threads(void);
 
+/* deterministic hashed inputs in [lo,hi), filled with the same static OpenMP partition the reductions use, so pages are
+ * first-touched by the thread that will read them (what cpu_init does: tests/gpu_reduce_min_fp64.cu:30-44).
+ * Same values as tests/_inputs.py:lcg_uniform. */
+void orc_fill_lcg_f64(double* d, uint64_t n, uint64_t seed, double lo, double hi);
+
 /* ---- reductions ---- */
 /* tests/gpu_reduce_min_fp64.cu:46-55 : m = DBL_MAX ; omp parallel for schedule(static) reduction(min:m) ; if(d[i]<m) m=d[i] */
 double orc_reduce_min_f64(const double* d, uint64_t n);

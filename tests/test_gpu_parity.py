@@ -28,6 +28,9 @@ def ob():
     import onika_b200 as ob
     assert torch.cuda.is_available()
     ob.init(0)
+    # lane 0 runs on torch's current stream so kernels are ordered with the tensors torch produces asynchronously;
+    # every other lane is an independent non-blocking stream (tests sync explicitly before using those)
+    ob.bind_lane_to_torch_stream(0)
     yield ob
     ob.lane_sync()
 
@@ -182,6 +185,7 @@ def test_parallel_memset(ob, gold):
 
 
 def test_value_add_and_lane_sequence(ob, orc, gold):
+    import torch
     from tests._inputs import unhx, lcg_uniform
     from onika_b200 import parallel as P
     g = gold["value_add"]
@@ -194,6 +198,7 @@ def test_value_add_and_lane_sequence(ob, orc, gold):
     for mode in (0, 1, 2):
         a1 = dev(unhx(gl["a1"]).reshape(gl["rows"], gl["cols"]))
         a2 = dev(unhx(gl["a2"]).reshape(gl["rows"], gl["cols"]))
+        torch.cuda.synchronize()
         q = P.ParallelExecutionQueue()
         op11 = P.block_parallel_for(gl["rows"], P.BlockParallelValueAddFunctor(a1, v[0]))
         op12 = P.block_parallel_for(gl["rows"], P.BlockParallelValueAddFunctor(a1, v[1]))
@@ -216,6 +221,7 @@ def test_value_add_and_lane_sequence(ob, orc, gold):
     rows, cols = 1024, 1024
     h1, h2 = lcg_uniform(rows * cols, 8).reshape(rows, cols), lcg_uniform(rows * cols, 9).reshape(rows, cols)
     a1, a2 = dev(h1), dev(h2)
+    torch.cuda.synchronize()
     q = P.ParallelExecutionQueue()
     q << P.set_lane(0) << P.block_parallel_for(rows, P.BlockParallelValueAddFunctor(a1, 1.1)) \
       << P.set_lane(1) << P.block_parallel_for(rows, P.BlockParallelValueAddFunctor(a2, 1.3)) \
@@ -240,20 +246,23 @@ def test_lane_graph_capture_replays_the_sequence(ob, orc):
     rows, cols = 512, 512
     h1, h2 = lcg_uniform(rows * cols, 8).reshape(rows, cols), lcg_uniform(rows * cols, 9).reshape(rows, cols)
     a1, a2 = dev(h1), dev(h2)
+    torch.cuda.synchronize()
     ob.lane_sync()
-    others = (C.c_int * 1)(1)
+    # lane 0 is bound to torch's legacy default stream in this suite, which CUDA cannot capture: refused, state intact
+    assert L.onk_graph_begin(0, None, 0) == _capi.ERR_ARG
+    others = (C.c_int * 1)(5)
     n0 = ob.launch_count()
-    _capi.check(L.onk_graph_begin(0, others, 1))
-    _capi.check(L.onk_value_add_f64(a1.data_ptr(), rows, cols, 1.1, 0))
-    _capi.check(L.onk_value_add_f64(a2.data_ptr(), rows, cols, 1.3, 1))
-    _capi.check(L.onk_value_add_f64(a1.data_ptr(), rows, cols, 1.2, 0))
-    _capi.check(L.onk_value_add_f64(a2.data_ptr(), rows, cols, 1.4, 1))
+    _capi.check(L.onk_graph_begin(4, others, 1))
+    _capi.check(L.onk_value_add_f64(a1.data_ptr(), rows, cols, 1.1, 4))
+    _capi.check(L.onk_value_add_f64(a2.data_ptr(), rows, cols, 1.3, 5))
+    _capi.check(L.onk_value_add_f64(a1.data_ptr(), rows, cols, 1.2, 4))
+    _capi.check(L.onk_value_add_f64(a2.data_ptr(), rows, cols, 1.4, 5))
     gph = C.c_void_p()
     _capi.check(L.onk_graph_end(C.byref(gph)))
     assert ob.launch_count() == n0                          # capture launches nothing
     assert np.array_equal(host(a1), h1)
     for _ in range(3):
-        _capi.check(L.onk_graph_launch(gph, 0))
+        _capi.check(L.onk_graph_launch(gph, 4))
         orc.lane_sequence(h1, h2, 1.1, 1.2, 1.3, 1.4)
     ob.lane_sync()
     assert ob.launch_count() == n0 + 12
