@@ -1,0 +1,26 @@
+// onika/cuda/cuda_error.h -- ONIKA_CU_CHECK_ERRORS: print file:line and abort on a CUDA error (the reference's policy).
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#endif
+
+namespace onika { namespace cuda {
+  inline void assert_success(int code, const char* what, const char* file, int line)
+  {
+    if (code != 0)
+    {
+#if defined(__CUDACC__)
+      std::fprintf(stderr, "GPU error %d (%s) : %s @ %s:%d\n", code, cudaGetErrorString((cudaError_t)code), what, file, line);
+#else
+      std::fprintf(stderr, "GPU error %d : %s @ %s:%d\n", code, what, file, line);
+#endif
+      std::abort();
+    }
+  }
+} }
+#define ONIKA_CU_CHECK_ERRORS(expr) ::onika::cuda::assert_success( int(expr) , #expr , __FILE__ , __LINE__ )
+
+// status of a C-ABI call (include/onika_b200.h) -> fatal error with the library's message
+#define ONIKA_B200_CHECK(expr) do { if( (expr) != 0 ) { std::fprintf(stderr,"onika_b200: %s @ %s:%d\n", onk_last_error(), __FILE__, __LINE__); std::abort(); } } while(0)

@@ -1,0 +1,68 @@
+// onika/extras/block_parallel_value_add_functor.h -- the functors the tutorials and lane tests launch:
+// BlockParallelValueAddFunctor (a[i][j] += v; memory bound) and BlockParallelIterativeValueAddFunctor (a pow/sin chain
+// per element; compute bound).  Row i is one block item; its columns are shared by the threads of the block.
+#pragma once
+#include <cmath>
+#include <onika/cuda/cuda.h>
+#include <onika/cuda/cuda_context.h>
+#include <onika/extras/array2d.h>
+#include <onika/parallel/block_parallel_for_functor.h>
+
+namespace onika { namespace extras {
+
+  template<bool AllowGpuExec = true, bool SingleTaskMode = false>
+  struct BlockParallelValueAddFunctor
+  {
+    Array2DReference m_array;
+    double m_value_to_add = 0.0;
+
+    // whole array in one host call (single-task mode)
+    ONIKA_HOST_DEVICE_FUNC inline void operator () ( parallel::block_parallel_for_single_task_t ) const requires(SingleTaskMode)
+    {
+      const size_t rows = m_array.rows() , cols = m_array.columns();
+      for(size_t i=0;i<rows;i++) for(size_t j=0;j<cols;j++) m_array[i][j] += m_value_to_add;
+    }
+    // one row per block item
+    ONIKA_HOST_DEVICE_FUNC inline void operator () (size_t i) const
+    {
+      const size_t cols = m_array.columns();
+      double * __restrict__ row = m_array[i];
+      ONIKA_CU_BLOCK_SIMD_FOR(size_t, j, 0, cols) { row[j] += m_value_to_add; }
+    }
+    // one element per item of a 2D space
+    ONIKA_HOST_DEVICE_FUNC inline void operator () (const onikaInt3_t& c) const { m_array[c.x][c.y] += m_value_to_add; }
+  };
+
+  template<bool AllowGpuExec = true>
+  struct BlockParallelIterativeValueAddFunctor
+  {
+    Array2DReference m_array;
+    double m_value_to_add = 0.0;
+    const long m_iterations = 0;
+
+    ONIKA_HOST_DEVICE_FUNC inline double chain(double x) const
+    {
+      double y = pow( x , sin(x) );
+      for(long k=0;k<m_iterations;k++) { x = x + y + m_value_to_add; y = pow( x , sin(x) ); }
+      return x * y;
+    }
+    ONIKA_HOST_DEVICE_FUNC inline void operator () (size_t i) const
+    {
+      const size_t cols = m_array.columns();
+      double * __restrict__ row = m_array[i];
+      ONIKA_CU_BLOCK_SIMD_FOR(size_t, j, 0, cols) { row[j] = chain( row[j] ); }
+    }
+    ONIKA_HOST_DEVICE_FUNC inline void operator () (const onikaInt3_t& c) const { m_array[c.x][c.y] = chain( m_array[c.x][c.y] ); }
+  };
+
+} 
+
+namespace parallel
+{
+  template<bool GpuEnable, bool SingleTaskMode>
+  struct BlockParallelForFunctorTraits< extras::BlockParallelValueAddFunctor<GpuEnable,SingleTaskMode> > { static constexpr bool CudaCompatible = GpuEnable && !SingleTaskMode; };
+  template<bool GpuEnable>
+  struct BlockParallelForFunctorTraits< extras::BlockParallelIterativeValueAddFunctor<GpuEnable> > { static constexpr bool CudaCompatible = GpuEnable; };
+}
+
+}

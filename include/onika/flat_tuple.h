@@ -22,8 +22,7 @@ namespace onika
   {
     static constexpr size_t tuple_size = sizeof...(T);
     FlatTuple() = default;
-    ONIKA_HOST_DEVICE_FUNC constexpr FlatTuple(const T&... a) requires (sizeof...(T) > 0)
-      : flat_tuple_details::Storage<std::index_sequence_for<T...>, T...>{ flat_tuple_details::Leaf<0,T>{a}... } { assign(std::index_sequence_for<T...>{}, a...); }
+    ONIKA_HOST_DEVICE_FUNC constexpr FlatTuple(const T&... a) requires (sizeof...(T) > 0) { assign(std::index_sequence_for<T...>{}, a...); }
     template<size_t I> ONIKA_HOST_DEVICE_FUNC constexpr auto& get(TupleIndex<I> = {}) { return leaf<I>(*this).v; }
     template<size_t I> ONIKA_HOST_DEVICE_FUNC constexpr const auto& get(TupleIndex<I> = {}) const { return leaf<I>(*this).v; }
     template<size_t I> ONIKA_HOST_DEVICE_FUNC constexpr auto& get_nth() { return leaf<I>(*this).v; }

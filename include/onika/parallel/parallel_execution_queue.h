@@ -1,0 +1,262 @@
+// onika/parallel/parallel_execution_queue.h -- queues of parallel operations and their scheduling onto lanes.
+//
+// Semantics kept from the reference: operations are enqueued with the queue's current lane, scheduled at flush in FIFO
+// order, ordered inside a lane and free to overlap across lanes; a delay queue (ParallelExecutionQueueBase) can be
+// spliced into a schedulable queue keeping each operation's lane; wait() synchronises, runs the finalize callback
+// (returning the PEC to its pool) and destroys the type-erased functor in place.
+// B200 runtime underneath: lane i <-> stream i of libonika_b200 (onk_lane_*); the CUDA bracket of an operation
+// (events, return-data copies, counter reset, epilog callback) is onk_op_begin / onk_op_end; host-only functors run as
+// host nodes of the lane's stream (onk_lane_host_func) so they stay ordered with the kernels of that lane.
+#pragma once
+#include <memory>
+#include <mutex>
+#include <utility>
+#include <vector>
+#include <onika/cuda/cuda_context.h>
+#include <onika/parallel/parallel_execution_context.h>
+#include <onika/parallel/parallel_execution_stream.h>
+#include <onika/parallel/parallel_data_access.h>
+#include <onika/parallel/constants.h>
+#include <onika/parallel/block_parallel_for_functor.h>
+#include <onika/log.h>
+
+#ifndef ONIKA_AUTO_LANE_CYCLE_HINT
+#define ONIKA_AUTO_LANE_CYCLE_HINT 16
+#endif
+#ifndef ONIKA_PARALLEL_QUEUE_MAX_LANES
+#define ONIKA_PARALLEL_QUEUE_MAX_LANES 32
+#endif
+
+namespace onika { namespace parallel {
+
+  // callback returning the execution stream of a lane
+  struct ParallelExecutionStreamPool
+  {
+    ParallelExecutionStream* (*m_func) (void*,int) = nullptr;
+    void *m_priv = nullptr;
+    inline ParallelExecutionStream* operator () (int lane) { return (*m_func)(m_priv,lane); }
+  };
+
+  // lazily creates one ParallelExecutionStream per lane
+  struct ParallelExecutionStreamAutoAllocator
+  {
+    onika::cuda::CudaContext * m_cuda_ctx = nullptr;
+    std::vector< std::shared_ptr< ParallelExecutionStream > > m_pes;
+    std::mutex m_mutex;
+
+    inline ParallelExecutionStream * parallel_execution_stream(int lane = DEFAULT_EXECUTION_LANE)
+    {
+      if( lane == DEFAULT_EXECUTION_LANE ) lane = 0;
+      if( lane < 0 || lane >= MAX_EXECUTION_LANES ) fatal_error() << "Invalid execution stream id (" << lane << ")" << std::endl;
+      std::lock_guard<std::mutex> lock(m_mutex);
+      if( size_t(lane) >= m_pes.size() ) m_pes.resize( lane+1 );
+      if( m_pes[lane] == nullptr )
+      {
+        auto s = std::make_shared<ParallelExecutionStream>();
+        s->m_stream_id = lane;
+        if( m_cuda_ctx != nullptr ) { s->m_cuda_ctx = m_cuda_ctx; s->m_cu_stream = m_cuda_ctx->getThreadStream(lane); }
+        m_pes[lane] = s;
+      }
+      return m_pes[lane].get();
+    }
+    static inline ParallelExecutionStream* parallel_execution_stream_cb(void* self, int lane)
+    {
+      return static_cast<ParallelExecutionStreamAutoAllocator*>(self)->parallel_execution_stream(lane);
+    }
+    inline ParallelExecutionStreamPool parallel_execution_stream_pool() { return { parallel_execution_stream_cb , this }; }
+  };
+
+  struct ParallelExecutionQueueBase
+  {
+    int m_lane = DEFAULT_EXECUTION_LANE;
+    int m_auto_lane_cycle = ONIKA_AUTO_LANE_CYCLE_HINT;
+    ParallelExecutionContext* m_queue_list = nullptr;
+    ParallelDataAccessVector m_data_access;
+    std::mutex m_mutex;
+
+    inline ~ParallelExecutionQueueBase() { assert( m_queue_list == nullptr ); }
+
+    inline void set_lane(int l , int lane_cycle = ONIKA_AUTO_LANE_CYCLE_HINT)
+    {
+      m_lane = l;
+      m_auto_lane_cycle = ( lane_cycle < int(ONIKA_PARALLEL_QUEUE_MAX_LANES) ) ? lane_cycle : int(ONIKA_PARALLEL_QUEUE_MAX_LANES);
+    }
+    inline void reset_data_access() { const std::lock_guard lk( m_mutex ); m_data_access.clear(); }
+    inline void add_data_access(const ParallelDataAccess& pda) { m_data_access.push_back(pda); }
+
+    inline void enqueue(ParallelExecutionContext* pec, bool from_other_queue = false)
+    {
+      assert( pec->m_next == nullptr && pec->m_stream == nullptr );
+      const std::lock_guard lk( m_mutex );
+      if( ! from_other_queue )
+      {
+        pec->m_lane = m_lane;
+        std::swap( pec->m_data_access , m_data_access );
+      }
+      m_data_access.clear();
+      m_queue_list = pec_list_append( m_queue_list , pec );
+    }
+
+    // lane assignment of operations queued under any_lane(): those that cannot conflict by declaration (single tasks,
+    // or no declared data access) are spread round robin over the auto-lane cycle; operations that declare data
+    // accesses keep an undefined lane and are serialised on lane 0 by schedule() (safe default, as in the reference
+    // where conflict-driven splitting is not implemented: src/parallel/parallel_execution_queue.cpp:171-207)
+    inline void pre_process_queue( ParallelExecutionContext* head )
+    {
+      int cycle = 0;
+      const int ncycle = ( m_auto_lane_cycle > 0 ) ? m_auto_lane_cycle : 1;
+      for(auto* pec=head; pec!=nullptr; pec=pec->m_next)
+      {
+        if( pec->m_lane == DEFAULT_EXECUTION_LANE ) pec->m_lane = 0;
+        else if( pec->m_lane == UNDEFINED_EXECUTION_LANE && ( get_block_parallel_functor(pec).is_single_task() || pec->m_data_access.empty() ) )
+        {
+          pec->m_lane = cycle;
+          cycle = ( cycle + 1 ) % ncycle;
+        }
+      }
+    }
+  };
+
+  struct ParallelExecutionQueue : public ParallelExecutionQueueBase
+  {
+    ParallelExecutionStreamPool m_stream_pool = {};
+    ParallelExecutionContext* m_exec_list = nullptr;
+
+    static inline std::shared_ptr<ParallelExecutionQueue> s_default_queue = nullptr;
+    static inline std::shared_ptr<ParallelExecutionStreamAutoAllocator> s_default_stream_allocator = nullptr;
+
+    static inline ParallelExecutionQueue& default_queue()
+    {
+      if( s_default_stream_allocator == nullptr )
+      {
+        s_default_stream_allocator = std::make_shared<ParallelExecutionStreamAutoAllocator>();
+        s_default_stream_allocator->m_cuda_ctx = onika::cuda::CudaContext::default_cuda_ctx();
+      }
+      if( s_default_queue == nullptr )
+      {
+        s_default_queue = std::make_shared<ParallelExecutionQueue>();
+        s_default_queue->m_stream_pool = s_default_stream_allocator->parallel_execution_stream_pool();
+      }
+      return * s_default_queue;
+    }
+
+    inline ~ParallelExecutionQueue() { schedule_all(); wait(); assert( m_exec_list == nullptr ); }
+
+    inline void schedule_all(int lane = UNDEFINED_EXECUTION_LANE )
+    {
+      const std::lock_guard lk( m_mutex );
+      // operations pushed under any_lane() carry an undefined lane: give them lanes before scheduling
+      bool any_undefined = false;
+      for(auto* p=m_queue_list; p!=nullptr; p=p->m_next) any_undefined = any_undefined || ( p->m_lane == UNDEFINED_EXECUTION_LANE );
+      if( any_undefined ) pre_process_queue( m_queue_list );
+      ParallelExecutionContext *keep = nullptr, *scheduled = nullptr;
+      auto* p = m_queue_list;
+      while( p != nullptr )
+      {
+        auto* next = p->m_next;
+        p->m_next = nullptr;
+        if( lane < 0 || p->m_lane == lane ) { schedule(p); scheduled = pec_list_append( scheduled , p ); }
+        else keep = pec_list_append( keep , p );
+        p = next;
+      }
+      m_queue_list = keep;
+      m_exec_list = pec_list_append( m_exec_list , scheduled );
+    }
+
+    static inline void host_operation_trampoline(void* p)
+    {
+      auto* pec = static_cast<ParallelExecutionContext*>(p);
+      get_block_parallel_functor(pec).execute_omp_parallel_region( pec , pec->m_stream );
+    }
+    static inline void gpu_epilog_trampoline(void* p)
+    {
+      auto* pec = static_cast<const ParallelExecutionContext*>(p);
+      get_block_parallel_functor(pec).execute_gpu_epilog( pec );
+    }
+
+    inline void schedule(ParallelExecutionContext* pec)
+    {
+      assert( pec->m_stream == nullptr && pec->m_next == nullptr );
+      int lane = pec->m_lane;
+      if( lane == UNDEFINED_EXECUTION_LANE || lane == DEFAULT_EXECUTION_LANE ) lane = 0;
+      pec->m_lane = lane;
+      auto exec_stream = m_stream_pool( lane );
+      std::lock_guard lk_stream( exec_stream->m_mutex );
+      pec->m_stream = exec_stream;
+      const auto & func = get_block_parallel_functor( pec );
+
+      if( pec->m_execution_target == ParallelExecutionContext::EXECUTION_TARGET_CUDA )
+      {
+        if( exec_stream->m_cuda_ctx == nullptr || exec_stream->m_cuda_ctx != pec->m_cuda_ctx )
+          fatal_error() << "Cannot schedule GPU parallel operation onto stream with no GPU context" << std::endl;
+        pec->init_device_scratch();
+        pec->m_scheduled_on_gpu = true;
+        ONIKA_B200_CHECK( onk_op_begin( pec->m_native_op , lane , pec->m_return_data_input , pec->m_return_data_size ,
+                                        ( pec->m_reset_counters || pec->m_grid_size.x > 0 ) ? 1 : 0 ) );
+        func.stream_gpu_initialize( pec , exec_stream );
+        func.stream_gpu_kernel( pec , exec_stream );
+        func.stream_gpu_finalize( pec , exec_stream );
+        ONIKA_B200_CHECK( onk_op_end( pec->m_native_op , pec->m_return_data_output , pec->m_return_data_size ,
+                                      func.needs_gpu_epilog(pec) ? gpu_epilog_trampoline : nullptr , pec ) );
+      }
+      else
+      {
+        // user-declared host-only functor: a host node in the lane's stream keeps it ordered with the lane's kernels
+        pec->m_scheduled_on_gpu = false;
+        exec_stream->m_omp_execution_count.fetch_add(1);
+        ONIKA_B200_CHECK( onk_lane_host_func( lane , host_operation_trampoline , pec ) );
+      }
+    }
+
+    inline ParallelExecutionContext* sync_and_remove(ParallelExecutionContext* head, int lane = UNDEFINED_EXECUTION_LANE)
+    {
+      ParallelExecutionContext *keep = nullptr;
+      auto* pec = head;
+      while( pec != nullptr )
+      {
+        auto* next = pec->m_next;
+        pec->m_next = nullptr;
+        if( lane < 0 || pec->m_lane == lane )
+        {
+          std::lock_guard lk( pec->m_stream->m_mutex );
+          pec->m_stream->wait_nolock();
+          if( pec->m_scheduled_on_gpu )
+          {
+            float ms = 0.0f;
+            ONIKA_B200_CHECK( onk_op_elapsed_ms( pec->m_native_op , &ms ) );
+            pec->m_total_gpu_execution_time = ms;
+          }
+          pec->m_stream = nullptr;
+          auto finalize = pec->m_finalize;
+          reinterpret_cast<BlockParallelForHostFunctor*>( pec->m_host_scratch.functor_data ) -> ~BlockParallelForHostFunctor();
+          if( finalize.m_func != nullptr ) ( * finalize.m_func ) ( pec , finalize.m_data );
+        }
+        else keep = pec_list_append( keep , pec );
+        pec = next;
+      }
+      return keep;
+    }
+
+    inline void wait_nolock(int lane = UNDEFINED_EXECUTION_LANE) { m_exec_list = sync_and_remove( m_exec_list , lane ); }
+    inline void wait(int lane = UNDEFINED_EXECUTION_LANE) { std::lock_guard lk( m_mutex ); wait_nolock(lane); }
+
+    inline bool query_status(int lane = UNDEFINED_EXECUTION_LANE)
+    {
+      const std::lock_guard lk( m_mutex );
+      if( m_exec_list == nullptr && m_queue_list == nullptr ) return true;
+      if( m_queue_list != nullptr ) return false;
+      for(auto* pec=m_exec_list; pec!=nullptr; pec=pec->m_next)
+      {
+        if( lane >= 0 && pec->m_lane != lane ) continue;
+        int idle = 0;
+        ONIKA_B200_CHECK( onk_lane_query( pec->m_lane , &idle ) );
+        if( ! idle ) return false;
+      }
+      wait_nolock( lane );
+      return true;
+    }
+
+    inline bool empty() { const std::lock_guard lk( m_mutex ); return m_exec_list == nullptr && m_queue_list == nullptr; }
+  };
+
+} }

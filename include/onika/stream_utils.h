@@ -1,0 +1,3 @@
+// onika/stream_utils.h -- placeholder kept for include compatibility.
+#pragma once
+#include <iostream>

@@ -1,0 +1,60 @@
+"""Build recipe for programs written against the C++ front end (include/onika/**) -- the way a plugin is compiled:
+nvcc, C++20, extended lambdas, sm_100a, linked against libonika_b200.so."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+from . import _build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INCLUDE = os.path.join(ROOT, "include")
+CXX_TESTS = os.path.join(ROOT, "tests", "cxx")
+PLUGIN_FLAGS = [
+    "-std=c++20", "--extended-lambda", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O2",
+    "--fmad=false", "-Xcompiler", "-fopenmp", "-Xcompiler", "-Wno-deprecated-declarations", "-I" + INCLUDE,
+]
+PROGRAMS = {"frontend_test": ["frontend_test.cu"]}
+
+
+def compile_program(sources, output, extra_flags=(), verbose=False):
+    lib_dir = os.path.dirname(_build.build())
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    cmd = [_build.nvcc(), *PLUGIN_FLAGS, *extra_flags, "-o", output, *sources, "-L" + lib_dir, "-lonika_b200",
+           "-Xlinker", "-rpath=" + lib_dir, "-Xlinker", "-rpath=$ORIGIN/../../onika_b200"]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd, env=env)
+    return output
+
+
+def program_path(name: str) -> str:
+    return os.path.join(CXX_TESTS, name)
+
+
+def needs_build(name: str) -> bool:
+    out = program_path(name)
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    deps = [os.path.join(CXX_TESTS, f) for f in os.listdir(CXX_TESTS) if f.endswith((".cu", ".h"))]
+    for base, _, files in os.walk(INCLUDE):
+        deps += [os.path.join(base, f) for f in files]
+    deps.append(_build.LIB)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_all(force: bool = False, verbose: bool = False):
+    outs = []
+    for name, srcs in PROGRAMS.items():
+        if force or needs_build(name):
+            compile_program([os.path.join(CXX_TESTS, s) for s in srcs], program_path(name), verbose=verbose)
+        outs.append(program_path(name))
+    return outs
+
+
+if __name__ == "__main__":
+    print(build_all(force=True, verbose=True))

@@ -1,0 +1,391 @@
+// tests/cxx/frontend_test.cu -- scenarios written against the onika API exactly as reference plugins / tests use it
+// (onikaParallelTutorial plugins, tests/parallel_queue_lane.cu, tests/benchmark.cpp, tests/soatlserializetest.cpp,
+// tests/soatupletest.cpp), compiled against THIS repo's include/onika front end and libonika_b200.so.
+// usage: frontend_test <scenario> <output file> [args...] ; raw little-endian doubles (or bytes) are written to the
+// output file and compared with the oracle by tests/test_gpu_cxx_frontend.py.
+#include <onika/parallel/block_parallel_for.h>
+#include <onika/parallel/parallel_for.h>
+#include <onika/parallel/memset.h>
+#include <onika/parallel/parallel_execution_context_allocator.h>
+#include <onika/parallel/parallel_execution_queue.h>
+#include <onika/parallel/parallel_execution_operators.h>
+#include <onika/extras/array2d.h>
+#include <onika/extras/block_parallel_value_add_functor.h>
+#include <onika/cuda/cuda_reduction.h>
+#include <onika/soatl/field_arrays.h>
+#include <onika/soatl/compute.h>
+#include <onika/soatl/copy.h>
+#include <onika/memory/allocator.h>
+#include "declare_fields.h"
+
+#include <cfloat>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace onika;
+using namespace onika::parallel;
+using onika::memory::CudaMMVector;
+
+// same hash as tests/_inputs.py:lcg_uniform
+static double lcg(uint64_t i, uint64_t seed, double lo, double hi)
+{
+  uint64_t h = ( i * 2654435761ull + seed * 40503ull + 12345ull ) & 0xFFFFFFFFull;
+  h = ( ( h ^ ( h >> 15 ) ) * 2246822519ull ) & 0xFFFFFFFFull;
+  h = ( h ^ ( h >> 13 ) ) & 0xFFFFFFFFull;
+  return lo + ( hi - lo ) * ( double(h) / 4294967296.0 );
+}
+template<class V> static void fill(V& v, uint64_t seed, double lo, double hi) { for(size_t i=0;i<v.size();i++) v[i] = lcg(i,seed,lo,hi); }
+
+struct Out
+{
+  FILE* f;
+  explicit Out(const char* path) : f( std::fopen(path,"wb") ) { if(!f) { std::perror(path); std::exit(2); } }
+  ~Out() { std::fclose(f); }
+  void doubles(const double* p, size_t n) { std::fwrite( p , sizeof(double) , n , f ); }
+  void bytes(const void* p, size_t n) { std::fwrite( p , 1 , n , f ); }
+  void u64(uint64_t v) { std::fwrite( &v , 8 , 1 , f ); }
+};
+
+static ParallelExecutionContextAllocator& peca() { static auto* a = new ParallelExecutionContextAllocator(); return *a; }
+static ParallelExecutionContext* parallel_execution_context(const char* tag, const char* sub = "")
+{
+  return peca().create( tag , sub , & ParallelExecutionQueue::default_queue() , onika::cuda::CudaContext::default_cuda_ctx() );
+}
+
+// ---------------------------------------------------------------- user functors (what a plugin author writes)
+struct AxpyFunctor
+{
+  double * __restrict__ y; const double * __restrict__ x; double a;
+  ONIKA_HOST_DEVICE_FUNC inline void operator () ( size_t i ) const { y[i] = y[i] + a * x[i]; }
+};
+namespace onika { namespace parallel { template<> struct ParallelForFunctorTraits<AxpyFunctor> { static inline constexpr bool CudaCompatible = true; }; } }
+
+struct Grid3DFunctor   // plugins/onikaParallelTutorial/parallel_for_3d_benchmark.cu: Grid3DBenchmarkFunctor
+{
+  double * const __restrict__ m_array = nullptr;
+  const long m_size = 0;
+  ONIKA_HOST_DEVICE_FUNC inline void operator () ( onikaInt3_t c ) const
+  {
+    const unsigned long N = m_size, i = c.x, j = c.y, k = c.z;
+    ONIKA_CU_ATOMIC_ADD( m_array[ (k*N+j)*N+i ] , 1.0 );
+  }
+};
+namespace onika { namespace parallel {
+  template<> struct BlockParallelForFunctorTraits<Grid3DFunctor> { static inline constexpr bool CudaCompatible = true; };
+  template<> struct ParallelForFunctorTraits<Grid3DFunctor> { static inline constexpr bool CudaCompatible = true; };
+} }
+
+// reduction through the return-data channel: block_reduce_* then one atomic per block
+struct ReduceResult { double vmin; double vmax; double vsum; unsigned long long count; };
+struct RowReduceFunctor
+{
+  const double * __restrict__ data; size_t cols; ReduceResult* result;   // result: device return-data pointer
+  ONIKA_HOST_DEVICE_FUNC inline void operator () ( size_t row ) const
+  {
+    double mn = DBL_MAX, mx = -DBL_MAX, sm = 0.0; unsigned long long cnt = 0;
+    ONIKA_CU_BLOCK_SIMD_FOR(size_t, j, 0, cols)
+    {
+      const double v = data[ row*cols + j ];
+      if( v < mn ) mn = v;
+      if( v > mx ) mx = v;
+      sm += v; ++cnt;
+    }
+    mn = onika::cuda::block_reduce_min( mn , onika::IntConst<ONIKA_CU_MAX_THREADS_PER_BLOCK>{} );
+    mx = onika::cuda::block_reduce_max( mx , onika::IntConst<ONIKA_CU_MAX_THREADS_PER_BLOCK>{} );
+    sm = onika::cuda::block_reduce_add( sm , onika::IntConst<ONIKA_CU_MAX_THREADS_PER_BLOCK>{} );
+    cnt = onika::cuda::block_reduce_add( cnt , onika::IntConst<ONIKA_CU_MAX_THREADS_PER_BLOCK>{} );
+    if( ONIKA_CU_THREAD_IDX == 0 )
+    {
+      ONIKA_CU_ATOMIC_MIN( result->vmin , mn );
+      ONIKA_CU_ATOMIC_MAX( result->vmax , mx );
+      ONIKA_CU_ATOMIC_ADD( result->vsum , sm );
+      ONIKA_CU_ATOMIC_ADD( result->count , cnt );
+    }
+  }
+};
+namespace onika { namespace parallel { template<> struct BlockParallelForFunctorTraits<RowReduceFunctor> { static inline constexpr bool CudaCompatible = true; }; } }
+
+// cell grid the way an exaNBody operator sees it: an array of per-cell FieldArrays
+using CellArrays = soatl::FieldArrays<64,16,_tag_particle_rx,_tag_particle_ry,_tag_particle_rz,_tag_particle_e>;
+struct CellSumFunctor
+{
+  const CellArrays * cells; double * cell_sum; double * total;
+  ONIKA_HOST_DEVICE_FUNC inline void operator () ( size_t c ) const
+  {
+    const double * __restrict__ e = cells[c][particle_e];
+    const size_t n = cells[c].size();
+    double s = 0.0;
+    if( ONIKA_CU_THREAD_IDX == 0 ) { for(size_t p=0;p<n;p++) s += e[p]; cell_sum[c] = s; ONIKA_CU_ATOMIC_ADD( *total , s ); }   // particle order
+  }
+};
+namespace onika { namespace parallel { template<> struct BlockParallelForFunctorTraits<CellSumFunctor> { static inline constexpr bool CudaCompatible = true; }; } }
+
+// prolog / epilog protocol + element list
+struct ScaleListedFunctor
+{
+  double * __restrict__ data; double s; int * prolog_calls; int * epilog_calls;
+  ONIKA_HOST_DEVICE_FUNC inline void operator () ( ssize_t i ) const { if( ONIKA_CU_THREAD_IDX == 0 ) data[i] *= s; }
+  inline void operator () ( block_parallel_for_gpu_prolog_t ) const { ++ *prolog_calls; }
+  inline void operator () ( block_parallel_for_gpu_epilog_t ) const { ++ *epilog_calls; }
+};
+namespace onika { namespace parallel { template<> struct BlockParallelForFunctorTraits<ScaleListedFunctor> { static inline constexpr bool CudaCompatible = true; }; } }
+
+// ---------------------------------------------------------------- scenarios
+static int scenario_axpy(Out& out, size_t n)
+{
+  CudaMMVector<double> x(n), y(n);
+  fill(x,1,-1,1); fill(y,2,-1,1);
+  AxpyFunctor f{ y.data(), x.data(), 0.5 };
+  parallel_for( n , f , parallel_execution_context("axpy") );     // synchronous: the temporary wrapper dies here
+  out.doubles( y.data() , n );
+  // parallel_memset on a second buffer
+  CudaMMVector<double> z(n, -1.0);
+  parallel_memset( z.data() , n , 3.25 , parallel_execution_context("memset") );
+  out.doubles( z.data() , n );
+  return 0;
+}
+
+static int scenario_value_add(Out& out, size_t rows, size_t cols)
+{
+  extras::Array2D a; a.resize(rows,cols);
+  fill(a.m_data,7,1e-3,1.0);
+  extras::BlockParallelValueAddFunctor<true> f = { a , 1.1 };
+  block_parallel_for( rows , f , parallel_execution_context("vadd","1d") );
+  out.doubles( a.data() , rows*cols );
+  const ParallelExecutionSpace<2> r2 = { {0,0} , { ssize_t(rows) , ssize_t(cols) } };
+  block_parallel_for( r2 , f , parallel_execution_context("vadd","2d") );
+  out.doubles( a.data() , rows*cols );
+  // work-stealing grid (fixed_gpu_grid_size), 1D
+  BlockParallelForOptions o; o.fixed_gpu_grid_size = true;
+  block_parallel_for( rows , f , parallel_execution_context("vadd","ws") , o );
+  out.doubles( a.data() , rows*cols );
+  return 0;
+}
+
+// tests/parallel_queue_lane.cu run_test(): kernel1 on the GPU, kernel2 declared host-only (hybrid), 4 queue modes
+static int scenario_lanes(Out& out, const std::string& mode, size_t rows, size_t cols, bool kernel_1d)
+{
+  extras::Array2D array1, array2;
+  array1.resize(rows,cols); array2.resize(rows,cols);
+  fill(array1.m_data,8,1e-3,1.0); fill(array2.m_data,9,1e-3,1.0);
+  const ParallelExecutionSpace<2> range2d = { {0,0} , { ssize_t(rows) , ssize_t(cols) } };
+  extras::BlockParallelValueAddFunctor<true>  array1_kernel1 = { array1 , 1.1 };
+  extras::BlockParallelValueAddFunctor<false> array1_kernel2 = { array1 , 1.2 };
+  extras::BlockParallelValueAddFunctor<true>  array2_kernel1 = { array2 , 1.3 };
+  extras::BlockParallelValueAddFunctor<false> array2_kernel2 = { array2 , 1.4 };
+  auto & pq = ParallelExecutionQueue::default_queue();
+  auto op11 = kernel_1d ? block_parallel_for( rows , array1_kernel1 , parallel_execution_context("Array1","Kernel1") )
+                        : block_parallel_for( range2d , array1_kernel1 , parallel_execution_context("Array1","Kernel1") );
+  auto op12 = kernel_1d ? block_parallel_for( rows , array1_kernel2 , parallel_execution_context("Array1","Kernel2") )
+                        : block_parallel_for( range2d , array1_kernel2 , parallel_execution_context("Array1","Kernel2") );
+  auto op21 = kernel_1d ? block_parallel_for( rows , array2_kernel1 , parallel_execution_context("Array2","Kernel1") )
+                        : block_parallel_for( range2d , array2_kernel1 , parallel_execution_context("Array2","Kernel1") );
+  auto op22 = kernel_1d ? block_parallel_for( rows , array2_kernel2 , parallel_execution_context("Array2","Kernel2") )
+                        : block_parallel_for( range2d , array2_kernel2 , parallel_execution_context("Array2","Kernel2") );
+  std::shared_ptr<std::mutex> start_sync;
+  if( mode == "hybrid-delayed-lane" )
+  {
+    ParallelExecutionQueueBase qa, qb;
+    qa << set_lane(0) << std::move(op11) << set_lane(1) << std::move(op21);
+    qb << set_lane(0) << std::move(op12) << set_lane(1) << std::move(op22);
+    pq << std::move(qa) << std::move(qb);
+  }
+  else if( mode == "hybrid-lane" )
+  {
+    pq << set_lane(0) << std::move(op11) << set_lane(1) << std::move(op21)
+       << set_lane(0) << std::move(op12) << set_lane(1) << std::move(op22);
+  }
+  else if( mode == "hybrid-sequence" )
+  {
+    pq << std::move(op11) << std::move(op12) << std::move(op21) << std::move(op22);
+  }
+  else if( mode == "singletask-dependency" )
+  {
+    const auto a1_loc = local_access( array1.m_data.data() , 2 , AccessStencilElement::RW , "a1_loc" );
+    const auto a1_nbh = access_cross_2d( array1.m_data.data() , AccessStencilElement::RW , AccessStencilElement::RO , "a1_nbh" );
+    const ParallelExecutionSpace<2> single_task_space = { {64,64} , {980,980} };
+    start_sync = std::make_shared<std::mutex>();
+    start_sync->lock();
+    auto single_task = make_single_task_block_parallel_functor( [start_sync]() { start_sync->lock(); start_sync->unlock(); } );
+    pq << any_lane() << a1_loc << block_parallel_for( single_task_space , single_task , parallel_execution_context("Array1","UnlockTask1") )
+       << any_lane() << a1_nbh << std::move(op11)
+       << any_lane() << a1_nbh << std::move(op12);
+    // array2 operations run synchronously afterwards (their wrappers die at the end of this function otherwise)
+  }
+  else { std::fprintf(stderr,"unknown test mode %s\n",mode.c_str()); return 2; }
+  if( start_sync != nullptr ) start_sync->unlock();
+  pq << flush;
+  const bool idle_probe = pq.query_status();   // may be true or false; must not deadlock
+  (void) idle_probe;
+  pq << synchronize;
+  if( mode == "singletask-dependency" ) { { auto w = std::move(op21); } { auto w = std::move(op22); } }
+  out.doubles( array1.data() , rows*cols );
+  out.doubles( array2.data() , rows*cols );
+  return pq.empty() ? 0 : 3;
+}
+
+static int scenario_grid3d(Out& out)
+{
+  {
+    const ssize_t N = 4;
+    CudaMMVector<double> m( N*N*N , 0.0 );
+    Grid3DFunctor f = { m.data() , N };
+    ParallelExecutionSpace<3> r = { {0,0,0} , {N,N,N} };
+    block_parallel_for( r , f , parallel_execution_context("grid3d","block") );
+    out.doubles( m.data() , m.size() );
+  }
+  {
+    const ssize_t N = 16;
+    CudaMMVector<double> m( N*N*N , 0.0 );
+    Grid3DFunctor f = { m.data() , N };
+    ParallelExecutionSpace<3> r = { {2,3,3} , {N-1,N-3,N-3} };
+    parallel_for( r , f , parallel_execution_context("grid3d","pfor") );
+    out.doubles( m.data() , m.size() );
+  }
+  return 0;
+}
+
+static int scenario_reduce(Out& out, size_t rows, size_t cols)
+{
+  CudaMMVector<double> d( rows*cols );
+  fill(d,17,-1.0,1.0);
+  ReduceResult res = { DBL_MAX , -DBL_MAX , 0.0 , 0ull };        // initial value travels to the device, result travels back
+  auto* pec = parallel_execution_context("reduce");
+  pec->init_device_scratch();                                     // the functor needs the device return-data pointer
+  RowReduceFunctor f = { d.data() , cols , (ReduceResult*) pec->get_device_return_data_ptr() };
+  BlockParallelForOptions o; o.return_data = &res; o.return_data_size = sizeof(res);
+  int cb_fired = 0;
+  o.user_cb = { [](void* p){ ++ *static_cast<int*>(p); } , &cb_fired };
+  block_parallel_for( rows , f , pec , o );
+  const double r[5] = { res.vmin , res.vmax , res.vsum , double(res.count) , double(cb_fired) };
+  out.doubles( r , 5 );
+  return 0;
+}
+
+static int scenario_cells(Out& out, size_t ncells)
+{
+  // sizes: deterministic pseudo-Poisson-ish in [0,64]
+  std::vector<uint32_t> counts(ncells);
+  size_t total = 0;
+  for(size_t c=0;c<ncells;c++) { counts[c] = uint32_t( lcg(c,42,0.0,33.0) ); if( c % 97 == 0 ) counts[c] = 64; if( c % 89 == 5 ) counts[c] = 0; total += counts[c]; }
+  onika::memory::CudaMMArray<CellArrays> cells; cells.resize(ncells);
+  for(size_t c=0;c<ncells;c++) new( &cells[c] ) CellArrays();
+  size_t k = 0, bytes = 0;
+  for(size_t c=0;c<ncells;c++)
+  {
+    cells[c].resize( counts[c] );
+    for(size_t p=0;p<counts[c];p++,k++) cells[c][particle_e][p] = lcg(k,40,-1.0,1.0);
+    bytes += cells[c].storage_size();
+  }
+  CudaMMVector<double> sums( ncells , 0.0 );
+  CudaMMVector<double> tot( 1 , 0.0 );
+  CellSumFunctor f = { cells.m_data_pointer , sums.data() , tot.data() };
+  block_parallel_for( ncells , f , parallel_execution_context("cells") );
+  out.u64( ncells ); out.u64( total ); out.u64( bytes );
+  std::vector<double> cnt( counts.begin() , counts.end() );
+  out.doubles( cnt.data() , ncells );
+  out.doubles( sums.data() , ncells );
+  out.doubles( tot.data() , 1 );
+  for(size_t c=0;c<ncells;c++) cells[c].clear();
+  return 0;
+}
+
+static int scenario_listed(Out& out)
+{
+  const size_t n = 1000;
+  CudaMMVector<double> d(n); fill(d,3,1e-3,1.0);
+  CudaMMVector<ssize_t> idx; for(size_t i=0;i<n;i+=3) idx.push_back( ssize_t(i) );
+  int prolog = 0, epilog = 0;
+  ScaleListedFunctor f = { d.data() , 2.0 , &prolog , &epilog };
+  ParallelExecutionSpace<1,1> space = { {0} , { ssize_t(idx.size()) } , std::span<const ssize_t>( idx.data() , idx.size() ) };
+  block_parallel_for( space , f , parallel_execution_context("listed") );
+  out.doubles( d.data() , n );
+  const double pe[2] = { double(prolog) , double(epilog) };
+  out.doubles( pe , 2 );
+  return 0;
+}
+
+// SOATL: layout, resize policy, tuple access, serialisation, device parallel_apply_simd
+static int scenario_soatl(Out& out, size_t n)
+{
+  using namespace onika::soatl;
+  // --- tests/soatupletest.cpp style static checks ---
+  static_assert( find_index_of_id<_tag_particle_rx,_tag_particle_rx,_tag_particle_ry>::index == 0 );
+  static_assert( find_index_of_id<_tag_particle_ry,_tag_particle_rx,_tag_particle_ry>::index == 1 );
+  static_assert( find_index_of_id<_tag_particle_e,_tag_particle_rx,_tag_particle_ry>::index == bad_field_index );
+  // --- layout probe: <64,16,rx,ry,rz,atype,e,mid>, resize sequence ---
+  {
+    auto fa = make_hybrid_field_arrays( cst::align<64>() , cst::chunk<16>() , particle_rx , particle_ry , particle_rz , particle_atype , particle_e , particle_mid );
+    const size_t seq[] = { 17 , 33 , 10 , 0 , 100 , 40 };
+    for(size_t s : seq)
+    {
+      fa.resize(s);
+      out.u64( fa.capacity() ); out.u64( fa.storage_size() );
+      const uint8_t* base = (const uint8_t*) fa.storage_ptr();
+      const uint8_t* p[6] = { (uint8_t*) fa[particle_rx] , (uint8_t*) fa[particle_ry] , (uint8_t*) fa[particle_rz] , (uint8_t*) fa[particle_atype] , (uint8_t*) fa[particle_e] , (uint8_t*) fa[particle_mid] };
+      for(int k=0;k<6;k++) out.u64( base ? uint64_t( p[k] - base ) : 0 );
+    }
+    fa.clear();
+    if( fa.storage_ptr() != nullptr || fa.capacity() != 0 ) return 4;
+  }
+  // --- tuple access, growth keeps contents ---
+  {
+    auto fa = make_hybrid_field_arrays( cst::align<64>() , cst::chunk<8>() , particle_e , particle_atype , particle_rx , particle_mid , particle_ry , particle_rz );
+    for(size_t i=0;i<n;i++) fa.push_back( fa.make_tuple( lcg(i,30,1e-3,1), (unsigned char)( lcg(i,34,0,50) ), lcg(i,31,1e-3,1), int32_t( lcg(i,35,0,500) ), lcg(i,32,1e-3,1), lcg(i,33,1e-3,1) ) );
+    if( fa.size() != n ) return 5;
+    auto t = fa[ n/2 ];
+    if( t[particle_rx] != lcg(n/2,31,1e-3,1) || t[particle_mid] != int32_t( lcg(n/2,35,0,500) ) ) return 6;
+    // serialise into the <1,1> wire layout (tests/soatlserializetest.cpp:86-104)
+    auto wire = make_hybrid_field_arrays( cst::align<1>() , cst::chunk<1>() , particle_e , particle_atype , particle_rx , particle_mid , particle_ry , particle_rz );
+    wire.resize(n);
+    copy( wire , fa , 0 , n/2 );
+    copy( wire , fa , n/2 , n - n/2 , particle_rx , particle_ry );
+    copy( wire , fa , particle_rz , particle_e , particle_atype , particle_mid );
+    copy( wire , fa );
+    out.u64( wire.storage_size() );
+    out.bytes( wire.storage_ptr() , wire.storage_size() );
+    wire.clear(); fa.clear();
+  }
+  // --- tests/benchmark.cpp kernel through parallel_apply_simd with a device lambda ---
+  {
+    auto arrays = make_hybrid_field_arrays( cst::align<64>() , cst::chunk<16>() , particle_rx , particle_ry , particle_rz , particle_e );
+    arrays.resize(n);
+    for(size_t i=0;i<arrays.capacity();i++) { arrays[particle_rx][i]=2.0; arrays[particle_ry][i]=3.0; arrays[particle_rz][i]=4.0; arrays[particle_e][i]=0.0; }
+    for(size_t i=0;i<n;i++) { arrays[particle_rx][i]=lcg(i,10,0,1); arrays[particle_ry][i]=lcg(i,11,0,1); arrays[particle_rz][i]=lcg(i,12,0,1); }
+    const double ax = arrays[particle_rx][0], ay = arrays[particle_ry][0], az = arrays[particle_rz][0];
+    parallel_apply_simd( [ax,ay,az] ONIKA_HOST_DEVICE_FUNC (double& d, double x, double y, double z)
+      {
+        x = x - ax; y = y - ay; z = z - az;
+        d = sqrt( x*x + y*y + z*z );
+        x /= d; y /= d; z /= d;
+        d += x/(y*z);
+      } , arrays , particle_e , particle_rx , particle_ry , particle_rz );
+    out.doubles( arrays[particle_e] , n );
+    arrays.clear();
+  }
+  return 0;
+}
+
+int main(int argc, char* argv[])
+{
+  if( argc < 3 ) { std::fprintf(stderr,"usage: %s <scenario> <output> [args]\n",argv[0]); return 2; }
+  const std::string sc = argv[1];
+  Out out( argv[2] );
+  auto arg = [&](int i, long def) { return ( argc > i ) ? std::atol(argv[i]) : def; };
+  if( onika::cuda::CudaContext::default_cuda_ctx() == nullptr ) return 9;
+  int rc = 2;
+  if( sc == "axpy" ) rc = scenario_axpy( out , arg(3,100003) );
+  else if( sc == "value_add" ) rc = scenario_value_add( out , arg(3,257) , arg(4,129) );
+  else if( sc == "lanes" ) rc = scenario_lanes( out , argc>3 ? argv[3] : "hybrid-lane" , arg(4,1024) , arg(5,1024) , arg(6,1) != 0 );
+  else if( sc == "grid3d" ) rc = scenario_grid3d( out );
+  else if( sc == "reduce" ) rc = scenario_reduce( out , arg(3,777) , arg(4,1001) );
+  else if( sc == "cells" ) rc = scenario_cells( out , arg(3,4096) );
+  else if( sc == "listed" ) rc = scenario_listed( out );
+  else if( sc == "soatl" ) rc = scenario_soatl( out , arg(3,53) );
+  ParallelExecutionQueue::default_queue() << flush << synchronize;
+  return rc;
+}

@@ -1,0 +1,141 @@
+"""GPU (-m gpu): programs written against the reference's C++ API (tests/cxx/frontend_test.cu: the scenarios of the
+onikaParallelTutorial plugins, tests/parallel_queue_lane.cu, tests/benchmark.cpp, tests/soatlserializetest.cpp) compiled
+against THIS repo's include/onika front end + libonika_b200.so, run on the GPU, outputs checked against the oracle and
+the golden vectors.  The generic functor path (user functors through block_parallel_for / parallel_for) is what is
+exercised here; the typed fast paths are covered by test_gpu_parity.py."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests._inputs import lcg_uniform, unhx
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")
+SUM_RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def prog():
+    from onika_b200 import cxx
+    return cxx.build_all()[0]
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(GOLD) as f:
+        return json.load(f)
+
+
+def run(prog, tmp_path, scenario, *args, expect_rc=0):
+    out = os.path.join(tmp_path, scenario + ".bin")
+    r = subprocess.run([prog, scenario, out, *map(str, args)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == expect_rc, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+    return np.fromfile(out, dtype=np.uint8)
+
+
+def test_parallel_for_axpy_and_memset(prog, tmp_path, orc):
+    for n in (1, 100003, 1_000_001):
+        d = run(prog, tmp_path, "axpy", n).view(np.float64)
+        x, y = lcg_uniform(n, 1, -1, 1), lcg_uniform(n, 2, -1, 1)
+        orc.axpy(y, x, 0.5)
+        assert np.array_equal(d[:n], y)
+        assert np.array_equal(d[n:], np.full(n, 3.25))
+
+
+def test_block_parallel_for_value_add_1d_2d_workstealing(prog, tmp_path, orc):
+    rows, cols = 257, 129
+    d = run(prog, tmp_path, "value_add", rows, cols).view(np.float64).reshape(3, rows, cols)
+    a = lcg_uniform(rows * cols, 7).reshape(rows, cols)
+    for k in range(3):
+        orc.value_add(a, 1.1)
+        assert np.array_equal(d[k], a), k
+
+
+@pytest.mark.parametrize("mode", ["hybrid-lane", "hybrid-delayed-lane", "hybrid-sequence", "singletask-dependency"])
+@pytest.mark.parametrize("kernel_1d", [1, 0])
+def test_parallel_queue_lane_scenarios(prog, tmp_path, orc, mode, kernel_1d):
+    rows, cols = (1024, 1024) if kernel_1d else (256, 192)
+    if mode == "singletask-dependency" and not kernel_1d:
+        pytest.skip("single-task space {64..980}^2 is written for the 1024^2 arrays")
+    d = run(prog, tmp_path, "lanes", mode, rows, cols, kernel_1d).view(np.float64).reshape(2, rows, cols)
+    a1, a2 = lcg_uniform(rows * cols, 8).reshape(rows, cols), lcg_uniform(rows * cols, 9).reshape(rows, cols)
+    orc.lane_sequence(a1, a2, 1.1, 1.2, 1.3, 1.4)      # GPU kernel then host-only kernel in each lane, in order
+    assert np.array_equal(d[0], a1) and np.array_equal(d[1], a2)
+
+
+def test_3d_spaces(prog, tmp_path, orc, gold):
+    d = run(prog, tmp_path, "grid3d").view(np.float64)
+    assert np.array_equal(d[:64], np.ones(64))          # block_parallel_for over {0..4}^3: every cell once
+    m = np.zeros(16 ** 3)
+    orc.parallel_for_3d(m, 16, (2, 3, 3), (15, 13, 13))
+    assert np.array_equal(d[64:], m)
+    assert [int(i) for i in np.nonzero(d[64:])[0]] == gold["parallel_for_3d"]["nonzero"]
+
+
+def test_return_data_reduction_and_callback(prog, tmp_path, orc):
+    rows, cols = 777, 1001
+    r = run(prog, tmp_path, "reduce", rows, cols).view(np.float64)
+    d = lcg_uniform(rows * cols, 17, -1.0, 1.0)
+    assert r[0] == orc.reduce_min(d) and r[1] == orc.reduce_max(d)
+    assert abs(r[2] - orc.reduce_sum_ld(d)) <= SUM_RTOL * np.abs(d).sum()
+    assert r[3] == rows * cols and r[4] == 1.0
+
+
+def test_cell_grid_of_field_arrays_generic_path(prog, tmp_path, orc):
+    ncells = 4096
+    raw = run(prog, tmp_path, "cells", ncells)
+    hdr = raw[:24].view(np.uint64)
+    body = raw[24:].view(np.float64)
+    counts = body[:ncells].astype(np.uint32)
+    sums, total = body[ncells:2 * ncells], body[2 * ncells]
+    assert hdr[0] == ncells and hdr[1] == counts.sum()
+    nbytes, cap, off = orc.cell_grid_layout(counts, 64, 16, [8, 8, 8, 8], 64)
+    assert hdr[2] == nbytes                               # same bytes as one reference FieldArrays per cell
+    e = lcg_uniform(int(counts.sum()), 40, -1, 1)
+    starts = np.concatenate([[0], np.cumsum(counts.astype(np.int64))[:-1]])
+    want = np.array([np.add.reduce(e[s:s + c]) if c else 0.0 for s, c in zip(starts, counts)])
+    seq = np.zeros(ncells)
+    for c in range(ncells):                               # strict particle order, like the functor
+        s = 0.0
+        for v in e[starts[c]:starts[c] + counts[c]]:
+            s += v
+        seq[c] = s
+    assert np.array_equal(sums, seq)
+    assert abs(total - seq.sum()) <= SUM_RTOL * np.abs(e).sum()
+    assert np.allclose(want, seq)
+
+
+def test_element_list_space_prolog_epilog(prog, tmp_path):
+    r = run(prog, tmp_path, "listed").view(np.float64)
+    d = lcg_uniform(1000, 3)
+    d[::3] *= 2.0
+    assert np.array_equal(r[:1000], d)
+    assert r[1000] == 1.0 and r[1001] == 1.0
+
+
+def test_soatl_container_layout_serialize_and_device_apply(prog, tmp_path, orc, gold):
+    n = 13
+    raw = run(prog, tmp_path, "soatl", n)
+    u = raw[: 6 * 8 * 8].view(np.uint64).reshape(6, 8)
+    case = [c for c in gold["soatl_layout"] if c["cfg"] == 3 and c["sizes"] == [17, 33, 10, 0, 100, 40]][0]
+    for k in range(6):
+        assert u[k, 0] == case["capacity"][k] and u[k, 1] == case["storage_bytes"][k]
+        assert list(u[k, 2:]) == case["offsets"][k]
+    pos = 6 * 8 * 8
+    wire_size = int(raw[pos:pos + 8].view(np.uint64)[0])
+    pos += 8
+    g = gold["soatl_serialize"]
+    assert raw[pos:pos + wire_size].tobytes().hex() == g["packed_hex"]      # byte-identical to the reference's wire format
+    pos += wire_size
+    e = raw[pos:].view(np.float64)
+    want = orc.soatl_dist(lcg_uniform(n, 10, 0, 1), lcg_uniform(n, 11, 0, 1), lcg_uniform(n, 12, 0, 1))
+    assert np.isnan(e[0]) and np.array_equal(e, want, equal_nan=True)
+    # a larger sweep of the device lambda
+    n = 100_003
+    raw = run(prog, tmp_path, "soatl", n)
+    e = raw[-8 * n:].view(np.float64)
+    want = orc.soatl_dist(lcg_uniform(n, 10, 0, 1), lcg_uniform(n, 11, 0, 1), lcg_uniform(n, 12, 0, 1))
+    assert np.array_equal(e, want, equal_nan=True)
