@@ -29,8 +29,9 @@ namespace onika { namespace extras {
       double * __restrict__ row = m_array[i];
       ONIKA_CU_BLOCK_SIMD_FOR(size_t, j, 0, cols) { row[j] += m_value_to_add; }
     }
-    // one element per item of a 2D space
-    ONIKA_HOST_DEVICE_FUNC inline void operator () (const onikaInt3_t& c) const { m_array[c.x][c.y] += m_value_to_add; }
+    // one element per item of a 2D space.  The whole block is called for the item: exactly one thread updates it, so the
+    // device result equals the host (one thread per block) result instead of depending on a write race
+    ONIKA_HOST_DEVICE_FUNC inline void operator () (const onikaInt3_t& c) const { if( ONIKA_CU_THREAD_IDX == 0 ) m_array[c.x][c.y] += m_value_to_add; }
   };
 
   template<bool AllowGpuExec = true>
@@ -52,7 +53,7 @@ namespace onika { namespace extras {
       double * __restrict__ row = m_array[i];
       ONIKA_CU_BLOCK_SIMD_FOR(size_t, j, 0, cols) { row[j] = chain( row[j] ); }
     }
-    ONIKA_HOST_DEVICE_FUNC inline void operator () (const onikaInt3_t& c) const { m_array[c.x][c.y] = chain( m_array[c.x][c.y] ); }
+    ONIKA_HOST_DEVICE_FUNC inline void operator () (const onikaInt3_t& c) const { if( ONIKA_CU_THREAD_IDX == 0 ) m_array[c.x][c.y] = chain( m_array[c.x][c.y] ); }
   };
 
 } 

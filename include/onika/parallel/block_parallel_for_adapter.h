@@ -32,8 +32,9 @@ namespace onika { namespace parallel {
       }
     }
 
+    // 2D/3D blocks follow ParallelExecutionContext::gpu_block_dims() (8x8x4 = 256 threads by default): no 128-thread bound here
     template<class FuncT>
-    __global__ void __launch_bounds__(ONIKA_CU_MAX_THREADS_PER_BLOCK)
+    __global__ void
     bpf_box_kernel( __grid_constant__ const FuncT func , const onikaInt3_t start , const unsigned int ex , const unsigned int ey , const unsigned long long n )
     {
       for(unsigned long long i = blockIdx.x; i < n; i += gridDim.x)

@@ -74,7 +74,20 @@ struct Grid3DFunctor   // plugins/onikaParallelTutorial/parallel_for_3d_benchmar
     ONIKA_CU_ATOMIC_ADD( m_array[ (k*N+j)*N+i ] , 1.0 );
   }
 };
+// block-level variant: the whole block is called once per cell, one thread counts the visit (on the host a block is one
+// thread, so both targets count 1 per cell; the unguarded tutorial functor counts blockDim per cell on any GPU)
+struct Grid3DBlockFunctor
+{
+  double * const __restrict__ m_array = nullptr;
+  const long m_size = 0;
+  ONIKA_HOST_DEVICE_FUNC inline void operator () ( onikaInt3_t c ) const
+  {
+    const unsigned long N = m_size, i = c.x, j = c.y, k = c.z;
+    if( ONIKA_CU_THREAD_IDX == 0 ) ONIKA_CU_ATOMIC_ADD( m_array[ (k*N+j)*N+i ] , 1.0 );
+  }
+};
 namespace onika { namespace parallel {
+  template<> struct BlockParallelForFunctorTraits<Grid3DBlockFunctor> { static inline constexpr bool CudaCompatible = true; };
   template<> struct BlockParallelForFunctorTraits<Grid3DFunctor> { static inline constexpr bool CudaCompatible = true; };
   template<> struct ParallelForFunctorTraits<Grid3DFunctor> { static inline constexpr bool CudaCompatible = true; };
 } }
@@ -233,7 +246,7 @@ static int scenario_grid3d(Out& out)
   {
     const ssize_t N = 4;
     CudaMMVector<double> m( N*N*N , 0.0 );
-    Grid3DFunctor f = { m.data() , N };
+    Grid3DBlockFunctor f = { m.data() , N };
     ParallelExecutionSpace<3> r = { {0,0,0} , {N,N,N} };
     block_parallel_for( r , f , parallel_execution_context("grid3d","block") );
     out.doubles( m.data() , m.size() );
