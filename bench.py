@@ -218,7 +218,7 @@ def run_ours(args) -> int:
     import torch
     import torch.distributed as dist
     import onika_b200 as ob
-    from onika_b200 import parallel as P
+    from onika_b200 import parallel as P, distributed as D
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -242,7 +242,7 @@ def run_ours(args) -> int:
     def step():
         functor.launch(n, 0)                  # one pass of the hot path over this rank's 2 GiB shard
         if world > 1:
-            dist.all_reduce(result, op=dist.ReduceOp.MIN)   # the path's only exchange: one fp64 partial per rank
+            D.combine_across_ranks(ob.OP_MIN, result)       # the path's only exchange: one fp64 partial per rank (NCCL all-reduce MIN)
 
     K, W = max(1, args.steps), max(3, args.warmup)
     for _ in range(W):
