@@ -167,13 +167,15 @@ def secondary_kernels(ob, torch):
         e1.synchronize()
         return e0.elapsed_time(e1) / reps * 1e-3
 
-    # the working sets of C1 and C4 fit in the 126 MB L2; a 512 MB scratch is rewritten between reps to flush it
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    # the working sets of C1 and C4 fit in the 126 MB L2; 1 GiB of other data is READ between reps to flush it (clean
+    # lines: a write-flush would leave dirty lines whose eviction is billed to the next kernel)
+    flush = torch.ones(1 << 27, dtype=torch.float64, device="cuda")
+    flush_out = torch.empty(1, dtype=torch.float64, device="cuda")
 
     def flushed(fn, reps=8):
         ts = []
         for _ in range(reps + 2):
-            flush.fill_(1)
+            P.ReduceFunctor(ob.OP_MIN, flush, flush_out).launch(flush.numel(), 0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record(); e1.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e-3)

@@ -10,22 +10,26 @@
 //   * HBM layout: all cells packed back to back in ONE arena (each block keeps the exact SOATL column layout
 //     FieldArrays<A,C,...> would give it), with three small tables: byte offset, size, capacity per cell;
 //   * a warp takes 32 consecutive cells per step: one coalesced load per table, then the variable-length columns
-//     are STAGED THROUGH SHARED MEMORY 16 particles at a time: a half-warp fetches one cell's 16 x 8 B = one
-//     128-byte line per load instruction (fully coalesced, CELL_ILP cells in flight per half-warp) into a padded
-//     32 x 17 tile; then lane l folds row l (its own cell) in particle order with conflict-free LDS.64;
+//     are STAGED THROUGH SHARED MEMORY 16 particles at a time: FOUR lanes fetch one cell's 16 x 8 B = 128-byte line
+//     with one 256-bit load each, so a single LDG.E.256 instruction brings in the lines of 8 cells (1 KiB) and the 4
+//     instructions that cover the warp's 32 cells are all in flight together; data lands in a padded 32 x 18 tile with
+//     conflict-free 128-bit shared stores; then lane l folds row l (its own cell) in particle order with 128-bit
+//     shared loads.  ~190 warp instructions per 32 cells instead of ~610 for a half-warp-per-cell 8-byte version
+//     (profiles/r1_stream_cell_kernels_full.csv), which was issue/latency bound at 52 % of DRAM peak;
+//   * cells whose column is not 32-byte aligned or whose capacity is not a multiple of 4 take a scalar load path;
 //   * in-cell sums are therefore sequential in particle order, bit-identical to the reference's host loop, and the
 //     per-cell results leave as one coalesced 256-byte store per warp;
 //   * the grid-wide total uses per-thread partials, a block reduction and the same ticketed two-pass finish as
 //     onk_reduce.cu (fixed order, no atomics on data);
 //   * persistent grid: CELL_CTAS_PER_SM x 148 CTAs, warps walk groups of 32 cells grid-stride.
 #include "onk_internal.cuh"
+#include <cstdlib>
 
 namespace onk
 {
-  constexpr unsigned CELL_CTAS_PER_SM = 6;
+  constexpr unsigned CELL_CTAS_PER_SM = 4;
   constexpr int CELL_MAX_FIELDS = 16;
-  constexpr int CELL_ILP = 4;                       // cells in flight per half-warp
-  constexpr int CELL_ROW = 17;                      // padded row length (doubles) of the staging tile
+  constexpr int CELL_ROW = 18;                      // padded row length (doubles) of the staging tile: 144 B, 16-byte aligned
   struct CellFieldParams { uint32_t pre_bytes[CELL_MAX_FIELDS]; int npre; uint32_t align_mask; };
 
   __device__ __forceinline__ uint64_t cell_field_offset(uint32_t cap, const CellFieldParams& fp)
@@ -35,59 +39,19 @@ namespace onk
     return off;
   }
 
-  __global__ void __launch_bounds__(THREADS, CELL_CTAS_PER_SM)
-  cell_sum_f64_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restrict__ cell_off, const uint32_t* __restrict__ cell_size,
-                      const uint32_t* __restrict__ cell_cap, uint64_t ncells, const __grid_constant__ CellFieldParams fp,
-                      double* __restrict__ cell_sum, double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ total)
+  __device__ __forceinline__ void sts128(double* p, double a, double b)
   {
-    __shared__ double stage[THREADS / 32][32 * CELL_ROW];
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned hl = lane & 15u;            // lane within the half-warp
-    const unsigned half = lane >> 4;           // which half-warp
-    double* tile = stage[threadIdx.x >> 5];
-    const uint64_t warp_global = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * THREADS) >> 5;
-    double thread_total = 0.0;
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" :: "r"((unsigned)__cvta_generic_to_shared(p)), "d"(a), "d"(b) : "memory");
+  }
+  __device__ __forceinline__ void lds128(const double* p, double& a, double& b)
+  {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+  }
 
-    // a warp takes 32 consecutive cells per step: lane l owns cell c0+l (tables, in-order fold, result)
-    for (uint64_t c0 = warp_global * 32; c0 < ncells; c0 += nwarps * 32)
-    {
-      const uint64_t cmine = c0 + lane;
-      uint64_t off = 0; uint32_t sz = 0, cap = 0;
-      if (cmine < ncells) { off = __ldg(cell_off + cmine); sz = __ldg(cell_size + cmine); cap = __ldg(cell_cap + cmine); }
-      const uint64_t addr = off + cell_field_offset(cap, fp);
-      uint32_t nmax = sz;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
 
-      double s = 0.0;
-      for (uint32_t p0 = 0; p0 < nmax; p0 += 16)
-      {
-        // stage particles [p0, p0+16) of all 32 cells: half-warp `half` fetches cells half*16 + j
-#pragma unroll
-        for (int j0 = 0; j0 < 16; j0 += CELL_ILP)
-        {
-          double v[CELL_ILP];
-#pragma unroll
-          for (int q = 0; q < CELL_ILP; q++)
-          {
-            const int src = half * 16 + j0 + q;
-            const uint64_t a = __shfl_sync(0xffffffffu, addr, src);
-            const uint32_t n = __shfl_sync(0xffffffffu, sz, src);
-            v[q] = (p0 + hl < n) ? ld_stream_ro1((const double*)(arena + a) + p0 + hl) : 0.0;
-          }
-#pragma unroll
-          for (int q = 0; q < CELL_ILP; q++) tile[(half * 16 + j0 + q) * CELL_ROW + hl] = v[q];
-        }
-        __syncwarp();
-        // particle order: s = ((s + e[p0]) + e[p0+1]) + ...   (+0.0 beyond the cell's size leaves s unchanged)
-#pragma unroll
-        for (int i = 0; i < 16; i++) s = __dadd_rn(s, tile[lane * CELL_ROW + i]);
-        __syncwarp();
-      }
-      if (cmine < ncells) { cell_sum[cmine] = s; thread_total = __dadd_rn(thread_total, s); }
-    }
-
+  // grid-wide total: per-thread partials -> block reduction -> ticketed two-pass finish (fixed order)
+  __device__ __forceinline__ void cell_total_finish(double thread_total, double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ total)
+  {
     if (total == nullptr) return;
     const double blk = block_reduce<ONK_OP_SUM, THREADS>(thread_total);
     __shared__ bool is_last;
@@ -106,6 +70,248 @@ namespace onk
       r = block_reduce<ONK_OP_SUM, THREADS>(r);
       if (threadIdx.x == 0) { *total = r; *ticket = 0u; }
     }
+  }
+
+  constexpr uint32_t CELL_SCALAR_FLAG = 0x80000000u;
+
+  __global__ void __launch_bounds__(THREADS, CELL_CTAS_PER_SM)
+  cell_sum_f64_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restrict__ cell_off, const uint32_t* __restrict__ cell_size,
+                      const uint32_t* __restrict__ cell_cap, uint64_t ncells, const __grid_constant__ CellFieldParams fp,
+                      double* __restrict__ cell_sum, double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ total)
+  {
+    __shared__ __align__(16) double stage[THREADS / 32][32 * CELL_ROW];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned q = lane & 3u;              // which 32-byte quarter of a cell's 128-byte line this lane fetches
+    const unsigned c8 = lane >> 2;             // cell within the group of 8 served by one load instruction
+    double* tile = stage[threadIdx.x >> 5];
+    const uint64_t warp_global = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * THREADS) >> 5;
+    double thread_total = 0.0;
+
+    // Software pipeline over the warp's steps (32 consecutive cells each; lane l owns cell c0+l):
+    //   tables of step s+2 are loaded into registers, the data lines of step s+1 are prefetched into L2
+    //   (prefetch.global.L2, one or two fire-and-forget requests per lane), step s is processed meanwhile.
+    //   (Measured: a two-step prefetch distance is slower, 110 us vs 92 us on 128^3 cells -- with 4736 resident warps it
+    //   keeps ~90 MB of speculative lines in the 126 MB L2 and thrashes it.)
+    // This removes the two serialized DRAM round trips (tables, then data) from every step.
+    const uint64_t stride = nwarps * 32;
+    auto load_tables = [&](uint64_t c, uint64_t& off, uint32_t& sz, uint32_t& cap)
+    {
+      off = 0; sz = 0; cap = 0;
+      if (c < ncells) { off = __ldg(cell_off + c); sz = __ldg(cell_size + c); cap = __ldg(cell_cap + c); }
+    };
+    auto prefetch_lines = [&](uint64_t off, uint32_t sz, uint32_t cap)
+    {
+      const uint8_t* pcol = arena + off + cell_field_offset(cap, fp);
+      if (sz > 0)  asm volatile("prefetch.global.L2 [%0];" :: "l"(pcol));
+      if (sz > 16) asm volatile("prefetch.global.L2 [%0];" :: "l"(pcol + 128));
+    };
+    uint64_t off0, off1, off2; uint32_t sz0, sz1, sz2, cap0, cap1, cap2;
+    const uint64_t cfirst = warp_global * 32 + lane;
+    load_tables(cfirst, off0, sz0, cap0);
+    load_tables(cfirst + stride, off1, sz1, cap1);
+    for (uint64_t c0 = warp_global * 32; c0 < ncells; c0 += stride)
+    {
+      const uint64_t cmine = c0 + lane;
+      load_tables(cmine + 2 * stride, off2, sz2, cap2);
+      prefetch_lines(off1, sz1, cap1);
+      const uint64_t off = off0; const uint32_t sz = sz0, cap = cap0;
+      const uint8_t* col = arena + off + cell_field_offset(cap, fp);
+      // size with a flag in the top bit: this cell's column cannot be read with aligned 256-bit loads
+      const uint32_t szf = sz | ((((uintptr_t)col & 31u) != 0 || (cap & 3u) != 0) ? CELL_SCALAR_FLAG : 0u);
+      uint32_t nmax = sz;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+
+      double s = 0.0;
+      for (uint32_t p0 = 0; p0 < nmax; p0 += 16)
+      {
+        // stage particles [p0, p0+16) of all 32 cells: load instruction `it` serves cells it*8 .. it*8+7
+        d4 v[4];
+#pragma unroll
+        for (int it = 0; it < 4; it++)
+        {
+          const int src = it * 8 + (int)c8;
+          const uint8_t* a = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)col, src);
+          const uint32_t nf = __shfl_sync(0xffffffffu, szf, src);
+          const uint32_t n = nf & ~CELL_SCALAR_FLAG;
+          const uint32_t e0 = p0 + 4u * q;                       // first of the 4 particles this lane fetches
+          const double* src_ptr = (const double*)a + e0;
+          v[it] = d4{0.0, 0.0, 0.0, 0.0};
+          if (e0 < n)
+          {
+            if (!(nf & CELL_SCALAR_FLAG)) v[it] = ld_stream_ro(src_ptr);   // capacity is a multiple of 4 => the whole vector is inside the column
+            else
+            {
+              v[it].a = ld_stream_ro1(src_ptr);
+              if (e0 + 1 < n) v[it].b = ld_stream_ro1(src_ptr + 1);
+              if (e0 + 2 < n) v[it].c = ld_stream_ro1(src_ptr + 2);
+              if (e0 + 3 < n) v[it].d = ld_stream_ro1(src_ptr + 3);
+            }
+            // particles beyond the cell's size (padding up to the capacity) count as +0.0
+            if (e0 + 1 >= n) v[it].b = 0.0;
+            if (e0 + 2 >= n) v[it].c = 0.0;
+            if (e0 + 3 >= n) v[it].d = 0.0;
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 4; it++)
+        {
+          double* row = tile + (it * 8 + (int)c8) * CELL_ROW + 4 * q;
+          sts128(row, v[it].a, v[it].b);
+          sts128(row + 2, v[it].c, v[it].d);
+        }
+        __syncwarp();
+        // particle order: s = ((s + e[p0]) + e[p0+1]) + ...   (+0.0 beyond the cell's size leaves s unchanged)
+        const double* mine = tile + lane * CELL_ROW;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2)
+        {
+          double x0, x1;
+          lds128(mine + i, x0, x1);
+          s = __dadd_rn(s, x0);
+          s = __dadd_rn(s, x1);
+        }
+        __syncwarp();
+      }
+      if (cmine < ncells) { cell_sum[cmine] = s; thread_total = __dadd_rn(thread_total, s); }
+      // rotate the pipeline
+      off0 = off1; sz0 = sz1; cap0 = cap1;
+      off1 = off2; sz1 = sz2; cap1 = cap2;
+    }
+
+    cell_total_finish(thread_total, partials, ticket, total);
+  }
+
+  // ------------------------------------------------------------------------------------------------------------
+  // Asynchronously staged variant (default).  The cell columns go global -> shared with cp.async (LDGSTS.128, L1
+  // bypass) into a per-warp ring of ASY_STAGES stages of 32 rows: 8 lanes move one cell's 128-byte line as eight
+  // 16-byte pieces, the src-size operand zero-fills whatever lies beyond the cell's size (ragged tails, empty cells),
+  // so nothing is held in registers and ASY_STAGES steps of 32 cells are in flight per warp: the
+  // table -> address -> data latency chain of one step overlaps the in-order folds of the previous ones.
+  // (A variant with one TMA bulk copy per cell -- cp.async.bulk, variable byte count per lane -- was measured at
+  // 146 us on 128^3 cells against 105 us for the register-staged kernel above: ~20 cycles per small bulk request and
+  // SM, the request rate and not the bandwidth being the limit at 128-256 B per copy.)
+  // Particles beyond ASY_RCAP, columns that are not 16-byte aligned: summed straight from global memory by their lane.
+  constexpr int ASY_STAGES = 3;
+  constexpr int ASY_RCAP = 32;                       // particles staged per cell (two 128-byte lines)
+  constexpr int ASY_ROW = ASY_RCAP + 2;              // doubles per row: 272 B (16-byte multiple, staggers banks)
+  constexpr unsigned ASY_CTAS_PER_SM = 1;
+  constexpr size_t ASY_SMEM = (size_t)(THREADS / 32) * ASY_STAGES * 32 * ASY_ROW * sizeof(double);
+
+  __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+  __device__ __forceinline__ void cp_async16_zfill(unsigned dst, const void* src, unsigned src_bytes)
+  {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  }
+
+  __global__ void __launch_bounds__(THREADS, ASY_CTAS_PER_SM)
+  cell_sum_f64_async_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restrict__ cell_off, const uint32_t* __restrict__ cell_size,
+                            const uint32_t* __restrict__ cell_cap, uint64_t ncells, const __grid_constant__ CellFieldParams fp,
+                            double* __restrict__ cell_sum, double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ total)
+  {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const unsigned piece = lane & 7u;          // which 16-byte piece of a 128-byte line this lane moves
+    const unsigned g4 = lane >> 3;             // cell within the group of 4 served by one cp.async instruction
+    double* ring = reinterpret_cast<double*>(dyn_smem) + (size_t)w * ASY_STAGES * 32 * ASY_ROW;
+
+    const uint64_t warp_global = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * THREADS) >> 5;
+    const uint64_t nsteps_total = (ncells + 31) / 32;
+    const uint64_t my_steps = (warp_global < nsteps_total) ? (nsteps_total - warp_global + nwarps - 1) / nwarps : 0;
+    double thread_total = 0.0;
+
+    // per-stage bookkeeping in registers (stage index is a compile-time constant after unrolling)
+    const uint8_t* col_s[ASY_STAGES]; uint32_t sz_s[ASY_STAGES]; uint32_t staged_s[ASY_STAGES];
+
+    // tables of the NEXT step to be issued, loaded one issue ahead so that their DRAM latency is never on the critical path
+    uint64_t nx_off = 0; uint32_t nx_sz = 0, nx_cap = 0;
+    auto load_next_tables = [&](uint64_t step)
+    {
+      const uint64_t c = (warp_global + step * nwarps) * 32 + lane;
+      nx_off = 0; nx_sz = 0; nx_cap = 0;
+      if (step < my_steps && c < ncells) { nx_off = __ldg(cell_off + c); nx_sz = __ldg(cell_size + c); nx_cap = __ldg(cell_cap + c); }
+    };
+    load_next_tables(0);
+
+    auto issue = [&](int stage, uint64_t step)
+    {
+      const uint64_t off = nx_off; const uint32_t sz = nx_sz, cap = nx_cap;
+      load_next_tables(step + 1);                        // steps are issued in order: the next call is for step+1
+      const uint8_t* col = arena + off + cell_field_offset(cap, fp);
+      uint32_t n_st = sz < (uint32_t)ASY_RCAP ? sz : (uint32_t)ASY_RCAP;
+      if ((((uintptr_t)col) & 15u) != 0) n_st = 0;                 // unaligned column: this lane reads global memory itself
+      col_s[stage] = col; sz_s[stage] = sz; staged_s[stage] = n_st;
+      double* tile = ring + (size_t)stage * 32 * ASY_ROW;
+#pragma unroll
+      for (int it = 0; it < 8; it++)
+      {
+        const int src_lane = it * 4 + (int)g4;
+        const uint8_t* a = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)col, src_lane);
+        const uint32_t nb = __shfl_sync(0xffffffffu, n_st, src_lane) * 8u;      // staged bytes of that cell
+        const unsigned dst = smem_u32(tile + (size_t)src_lane * ASY_ROW) + piece * 16u;
+        // first line: always written (zero-filled beyond the cell's size, also for empty cells)
+        {
+          const uint32_t o = piece * 16u;
+          const uint32_t valid = (nb > o) ? ((nb - o < 16u) ? nb - o : 16u) : 0u;
+          cp_async16_zfill(dst, a + o, valid);
+        }
+        // second line: only when some cell of this instruction is longer than 16 particles
+        if (__any_sync(0xffffffffu, nb > 128u))
+        {
+          const uint32_t o = 128u + piece * 16u;
+          const uint32_t valid = (nb > o) ? ((nb - o < 16u) ? nb - o : 16u) : 0u;
+          cp_async16_zfill(dst + 128u, a + o, valid);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // prologue: fill the ring (empty groups are committed too so that group counting stays uniform)
+#pragma unroll
+    for (int sgi = 0; sgi < ASY_STAGES; sgi++)
+    {
+      if ((uint64_t)sgi < my_steps) issue(sgi, (uint64_t)sgi);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
+    for (uint64_t k0 = 0; k0 < my_steps; k0 += ASY_STAGES)
+    {
+#pragma unroll
+      for (int sgi = 0; sgi < ASY_STAGES; sgi++)
+      {
+        const uint64_t k = k0 + sgi;
+        if (k < my_steps)                                  // warp-uniform
+        {
+          asm volatile("cp.async.wait_group %0;" :: "n"(ASY_STAGES - 1) : "memory");   // the oldest group (this stage) has landed
+          __syncwarp();
+          const double* row = ring + ((size_t)sgi * 32 + lane) * ASY_ROW;
+          const uint32_t n_st = staged_s[sgi], sz = sz_s[sgi];
+          double s = 0.0;
+          // particle order; zero-filled slots add +0.0, which leaves s unchanged
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) { double x0, x1; lds128(row + i, x0, x1); s = __dadd_rn(s, x0); s = __dadd_rn(s, x1); }
+          if (n_st > 16u)
+          {
+#pragma unroll
+            for (int i = 16; i < 32; i += 2) { double x0, x1; lds128(row + i, x0, x1); s = __dadd_rn(s, x0); s = __dadd_rn(s, x1); }
+          }
+          if (sz > n_st)                                   // long or unaligned cells: the rest straight from global memory
+          {
+            const double* e = reinterpret_cast<const double*>(col_s[sgi]);
+            for (uint32_t i = n_st; i < sz; i++) s = __dadd_rn(s, ld_stream_ro1(e + i));
+          }
+          const uint64_t c = (warp_global + k * nwarps) * 32 + lane;
+          if (c < ncells) { cell_sum[c] = s; thread_total = __dadd_rn(thread_total, s); }
+          __syncwarp();                                    // every lane is done reading this stage
+          if (k + ASY_STAGES < my_steps) issue(sgi, k + ASY_STAGES);
+          else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    cell_total_finish(thread_total, partials, ticket, total);
   }
 }
 
@@ -153,8 +359,18 @@ int onk_cell_sum_f64(const void* arena_dev, const uint64_t* cell_off_dev, const 
   const unsigned cells_per_cta = (THREADS / 32) * 32;
   unsigned grid = grid_for(ncells, cells_per_cta, CELL_CTAS_PER_SM);
   if (grid > (unsigned)MAX_PARTIALS) grid = MAX_PARTIALS;
-  cell_sum_f64_kernel<<<grid, THREADS, 0, L->stream>>>((const uint8_t*)arena_dev, cell_off_dev, cell_size_dev, cell_cap_dev, ncells, fp,
-                                                       cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev);
+  static const int variant = []{ const char* e = getenv("ONK_CELL_KERNEL"); return (e && e[0] == 'l') ? 0 : 1; }();   // "ldg" | "async" (default)
+  if (variant == 1)
+  {
+    static bool configured = false;
+    if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_f64_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ASY_SMEM)); configured = true; }
+    grid = grid_for(ncells, cells_per_cta, ASY_CTAS_PER_SM);
+    cell_sum_f64_async_kernel<<<grid, THREADS, ASY_SMEM, L->stream>>>((const uint8_t*)arena_dev, cell_off_dev, cell_size_dev, cell_cap_dev, ncells, fp,
+                                                                    cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev);
+  }
+  else
+    cell_sum_f64_kernel<<<grid, THREADS, 0, L->stream>>>((const uint8_t*)arena_dev, cell_off_dev, cell_size_dev, cell_cap_dev, ncells, fp,
+                                                         cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev);
   ONK_CHECK_LAUNCH(); count_launch();
   return ONK_OK;
 }

@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""Launch every typed kernel a few times at the BASELINE config sizes (for ncu captures and quick device timings).
+
+  python tools/profile_kernels.py [--reps 5] [--only cells,axpy,...]
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
+    import numpy as np
+    import torch
+    import onika_b200 as ob
+    from onika_b200 import parallel as P, soatl, cellgrid
+    from tests._inputs import poisson_counts
+    ob.init(0)
+    ob.bind_lane_to_torch_stream(0)
+    # L2 flush by READING 1 GiB (clean lines): a write-flush would leave 126 MB of dirty lines whose eviction gets billed
+    # to the next kernel
+    flush = torch.ones(1 << 27, dtype=torch.float64, device="cuda")
+    flush_out = torch.empty(1, dtype=torch.float64, device="cuda")
+
+    def timed(name, fn, nbytes, flush_l2=False):
+        if only and name not in only:
+            return
+        ts = []
+        for _ in range(args.reps + 2):
+            if flush_l2:
+                P.ReduceFunctor(ob.OP_MIN, flush, flush_out).launch(flush.numel(), 0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        ts = sorted(ts[2:])
+        t = ts[len(ts) // 2]
+        print(f"{name:28s} {t * 1e6:10.1f} us   {nbytes / t / 1e9:8.1f} GB/s  (min {nbytes / ts[-1] / 1e9:.0f} max {nbytes / ts[0] / 1e9:.0f})", flush=True)
+
+    n = 10_000_000
+    x = torch.rand(n, dtype=torch.float64, device="cuda"); y = torch.rand(n, dtype=torch.float64, device="cuda")
+    timed("axpy", lambda: P.AxpyFunctor(y, x, 0.5).launch(n, 0), 24 * n, True)
+    n = 1 << 28
+    big = torch.rand(n, dtype=torch.float64, device="cuda")
+    o = torch.empty(1, dtype=torch.float64, device="cuda")
+    timed("reduce_min", lambda: P.ReduceFunctor(ob.OP_MIN, big, o).launch(n, 0), 8 * n)
+    timed("reduce_sum", lambda: P.ReduceFunctor(ob.OP_SUM, big, o).launch(n, 0), 8 * n)
+    timed("axpy_big", lambda: P.AxpyFunctor(big[: n // 2], big[n // 2:], 0.5).launch(n // 2, 0), 24 * (n // 2))
+    timed("value_add", lambda: P.BlockParallelValueAddFunctor(big.view(1 << 14, 1 << 14), 1.1).launch(1 << 14, 0), 16 * n)
+    timed("memset", lambda: P.MemSetFunctor(big, 1.5).launch(n, 0), 8 * n)
+    del big
+    fa = soatl.make_hybrid_field_arrays(256, 16, [(f"f{k}", "f8") for k in range(8)])
+    n = 64 << 20
+    fa.resize(n)
+    fa.storage.view(torch.float64).uniform_(0, 1)
+    c = [0.125 * (k + 1) for k in range(8)]
+    timed("soatl_rmw", lambda: fa.parallel_apply_rmw(1.0000001, c), 128 * n)
+    fa.clear()
+    fb = soatl.make_hybrid_field_arrays(64, 16, [("rx", "f8"), ("ry", "f8"), ("rz", "f8"), ("e", "f8")])
+    n = 64 << 20
+    fb.resize(n)
+    fb.storage.view(torch.float64).uniform_(0.1, 1)
+    timed("soatl_dist", lambda: fb.parallel_apply_dist("e", "rx", "ry", "rz", 0.05, 0.06, 0.07), 32 * n)
+    fb.clear()
+    counts = poisson_counts(128 ** 3)
+    cg = cellgrid.CellGrid(counts, 64, 16, (8, 8, 8, 8), 64)
+    cg.arena.view(torch.float64).uniform_(-1, 1)
+    alg = 8 * int(counts.sum()) + cg.ncells * 24
+    timed("cells", lambda: cg.cell_sum(3), alg, True)
+    timed("cells_f0", lambda: cg.cell_sum(0), alg, True)
+    # raw back-to-back launches through the C ABI with preallocated outputs (the arena is 1.5 GB >> L2)
+    import ctypes as C
+    from onika_b200 import _capi
+    from onika_b200.runtime import ptr
+    sums = torch.empty(cg.ncells, dtype=torch.float64, device="cuda")
+    tot = torch.zeros(1, dtype=torch.float64, device="cuda")
+    fb_ = (C.c_uint32 * 4)(8, 8, 8, 8)
+    def raw(field):
+        _capi.check(_capi.lib().onk_cell_sum_f64(ptr(cg.arena), ptr(cg.cell_off), ptr(cg.cell_size), ptr(cg.cell_cap), cg.ncells, 64, fb_, 4, field,
+                                                 ptr(sums), ptr(tot), 0))
+    if not only or "cells_raw" in only:
+        for field in (3, 0):
+            for _ in range(3):
+                raw(field)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                raw(field)
+            e1.record(); e1.synchronize()
+            t = e0.elapsed_time(e1) / 20 * 1e-3
+            print(f"cells_raw field {field}            {t * 1e6:10.1f} us   {alg / t / 1e9:8.1f} GB/s", flush=True)
+    torch.cuda.synchronize()
+
+
+if __name__ == "__main__":
+    main()
