@@ -7,6 +7,8 @@
 #include <onika/cuda/cuda_context.h>
 #include <onika/extras/array2d.h>
 #include <onika/parallel/block_parallel_for_functor.h>
+#include <onika/parallel/block_parallel_for_adapter.h>
+#include <onika_b200.h>
 
 namespace onika { namespace extras {
 
@@ -60,6 +62,23 @@ namespace onika { namespace extras {
 
 namespace parallel
 {
+  // rows [start,end) of a dense row-major Array2D (and full-width 2D boxes) are ONE contiguous stream of doubles:
+  // onk_value_add_f64 (256-bit vectorised, persistent grid) does the whole operation
+  template<unsigned int ND>
+  struct B200TypedFastPath< extras::BlockParallelValueAddFunctor<true,false> , ND , 0 >
+  {
+    static inline constexpr bool available = ( ND <= 2 );
+    template<class SpaceT> static inline bool launch( const extras::BlockParallelValueAddFunctor<true,false>& f , const SpaceT& sp , int lane )
+    {
+      const ssize_t r0 = sp.m_start[0] , r1 = sp.m_end[0];
+      if( r0 < 0 || r1 > ssize_t(f.m_array.rows()) ) return false;
+      if constexpr ( ND == 2 ) { if( sp.m_start[1] != 0 || sp.m_end[1] != ssize_t(f.m_array.columns()) ) return false; }
+      if( r1 <= r0 ) return true;
+      ONIKA_B200_CHECK( onk_value_add_f64( f.m_array[r0] , uint64_t(r1-r0) , f.m_array.columns() , f.m_value_to_add , lane ) );
+      return true;
+    }
+  };
+
   template<bool GpuEnable, bool SingleTaskMode>
   struct BlockParallelForFunctorTraits< extras::BlockParallelValueAddFunctor<GpuEnable,SingleTaskMode> > { static constexpr bool CudaCompatible = GpuEnable && !SingleTaskMode; };
   template<bool GpuEnable>

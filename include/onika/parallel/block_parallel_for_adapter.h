@@ -16,6 +16,19 @@
 
 namespace onika { namespace parallel {
 
+  // ========================== typed fast paths ==========================
+  // Customisation point: a functor type whose whole operation is one of the typed sm_100a kernels of libonika_b200
+  // (include/onika_b200.h) specialises this; the adapter then issues that kernel on the operation's lane instead of the
+  // generic functor kernel.  launch() returns false when this particular call cannot use it (e.g. a sub-box that is not
+  // one contiguous stream), in which case the generic path runs.  Results are identical by construction (same
+  // arithmetic, parity-tested against the same oracle).
+  template<class FuncT, unsigned int ND, unsigned int ElemND>
+  struct B200TypedFastPath
+  {
+    static inline constexpr bool available = false;
+    template<class SpaceT> static inline bool launch( const FuncT& , const SpaceT& , int /*lane*/ ) { return false; }
+  };
+
   // ========================== device kernels ==========================
 #if defined(__CUDACC__)
   namespace b200
@@ -147,6 +160,14 @@ namespace onika { namespace parallel {
         const unsigned long long nitems = m_parallel_space.number_of_items();
         if( nitems == 0 ) return;
         const unsigned int threads = pec->m_block_size.x * pec->m_block_size.y * pec->m_block_size.z;
+#       ifndef ONIKA_B200_DISABLE_TYPED_FAST_PATHS
+        if constexpr ( B200TypedFastPath<FuncT,ND,ElemND>::available )
+#       else
+        if constexpr ( false )
+#       endif
+        {
+          if( pec->m_grid_size.x == 0 && B200TypedFastPath<FuncT,ND,ElemND>::launch( m_func , m_parallel_space , pec->m_lane ) ) return;
+        }
         if constexpr ( ND == 1 )
         {
           ssize_t start = m_parallel_space.m_start[0];

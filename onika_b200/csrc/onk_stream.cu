@@ -49,7 +49,9 @@ namespace onk
   // ---------------------------------------------------------------- a[i] = a[i] + v   (1R + 1W)   value-add
   // ---------------------------------------------------------------- a[i] = a[i]*s + c (1R + 1W)   SOATL column sweep
   // One kernel for both: `ncols` columns of `len` doubles, column k at base + k*col_stride (doubles).
-  constexpr int RMW_UNROLL = 4;
+  // tools/tune.cu sweep (profiles/r1_tune_sweep_width_rmw_axpy.log): a read+write mix is fastest with ~32 KB of loads in
+  // flight per SM (6.39 TB/s); deeper unrolling (128 KB/SM) costs 4 % -- the opposite of the read-only kernels
+  constexpr int RMW_UNROLL = 1;
   constexpr int RMW_MAX_COLS = 16;
   struct RmwParams { double s; double c[RMW_MAX_COLS]; };
 
@@ -243,6 +245,26 @@ int onk_parallel_memset(void* data_dev, uint64_t n, uint64_t pattern, int elem_b
   else if (elem_bytes == 4) { p64 &= 0xffffffffu; p64 |= p64 << 32; }
   const uint64_t total = n * (uint64_t)elem_bytes;
   uint8_t* p = (uint8_t*)data_dev;
+  // Patterns that repeat every 32 bits (0.0, integers, bytes, ...) go to the device's fill engine: measured 7.3 TB/s
+  // against ~6.3 TB/s for ANY SM-issued store shape, TMA bulk stores included (profiles/r1_tune_sweep_memset.log).
+  // General 64-bit values (most doubles) need the kernel below.
+  if ((uint32_t)p64 == (uint32_t)(p64 >> 32) && ((uintptr_t)p & 3) == 0 && (total & 3) == 0)
+  {
+    typedef int (*memset32_t)(unsigned long long, unsigned int, size_t, void*);
+    static memset32_t fill32 = nullptr;
+    if (!fill32)
+    {
+      void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+      ONK_CUDA(cudaGetDriverEntryPoint("cuMemsetD32Async", &fn, cudaEnableDefault, &q));
+      fill32 = (memset32_t)fn;
+    }
+    if (fill32)
+    {
+      const int r = fill32((unsigned long long)(uintptr_t)p, (unsigned int)p64, total / 4, (void*)L->stream);
+      if (r != 0) { set_error("onk_parallel_memset: cuMemsetD32Async failed with CUresult %d", r); return ONK_ERR_CUDA; }
+      return ONK_OK;
+    }
+  }
   uint64_t head = ((32 - ((uintptr_t)p & 31)) & 31);
   if (head > total) head = total;
   const uint64_t body = (total - head) / 8;          // 64-bit words starting at a 32-byte boundary

@@ -15,7 +15,7 @@ PLUGIN_FLAGS = [
     "-std=c++20", "--extended-lambda", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O2",
     "--fmad=false", "-Xcompiler", "-fopenmp", "-Xcompiler", "-Wno-deprecated-declarations", "-I" + INCLUDE,
 ]
-PROGRAMS = {"frontend_test": ["frontend_test.cu"]}
+PROGRAMS = {"frontend_test": (["frontend_test.cu"], []), "frontend_test_generic": (["frontend_test.cu"], ["-DONIKA_B200_DISABLE_TYPED_FAST_PATHS"])}
 
 
 def compile_program(sources, output, extra_flags=(), verbose=False):
@@ -49,9 +49,9 @@ def needs_build(name: str) -> bool:
 
 def build_all(force: bool = False, verbose: bool = False):
     outs = []
-    for name, srcs in PROGRAMS.items():
+    for name, (srcs, flags) in PROGRAMS.items():
         if force or needs_build(name):
-            compile_program([os.path.join(CXX_TESTS, s) for s in srcs], program_path(name), verbose=verbose)
+            compile_program([os.path.join(CXX_TESTS, s) for s in srcs], program_path(name), extra_flags=flags, verbose=verbose)
         outs.append(program_path(name))
     return outs
 

@@ -383,6 +383,47 @@ static int scenario_soatl(Out& out, size_t n)
   return 0;
 }
 
+// device-timed throughput of the generic functor path and of the typed fast paths, through the public API
+static int scenario_perf(Out&, size_t n)
+{
+  void* stream = nullptr;
+  ONIKA_B200_CHECK( onk_lane_stream( 0 , &stream ) );
+  cudaEvent_t e0, e1;
+  ONIKA_CU_CHECK_ERRORS( cudaEventCreate(&e0) ); ONIKA_CU_CHECK_ERRORS( cudaEventCreate(&e1) );
+  auto & pq = ParallelExecutionQueue::default_queue();
+  auto bench = [&](const char* name, double bytes, auto make_op)
+  {
+    const int reps = 10;
+    for(int i=0;i<3;i++) { pq << set_lane(0) << make_op(); } pq << flush << synchronize;
+    ONIKA_CU_CHECK_ERRORS( cudaEventRecord( e0 , (cudaStream_t) stream ) );
+    for(int i=0;i<reps;i++) { pq << set_lane(0) << make_op(); }
+    pq << flush;
+    ONIKA_CU_CHECK_ERRORS( cudaEventRecord( e1 , (cudaStream_t) stream ) );
+    pq << synchronize;
+    float ms = 0; ONIKA_CU_CHECK_ERRORS( cudaEventElapsedTime( &ms , e0 , e1 ) );
+    std::printf("%-44s %9.1f us/op  %8.1f GB/s\n", name , ms*1e3/reps , bytes*reps/(ms*1e-3)/1e9 );
+  };
+  {
+    void *px = nullptr, *py = nullptr;                       // device memory: no managed-memory migration in the timings
+    ONIKA_B200_CHECK( onk_alloc( n*8 , 256 , ONK_MEM_DEVICE , &px ) ); ONIKA_B200_CHECK( onk_alloc( n*8 , 256 , ONK_MEM_DEVICE , &py ) );
+    ONIKA_B200_CHECK( onk_memset_bytes( px , 0 , n*8 , 0 ) ); ONIKA_B200_CHECK( onk_memset_bytes( py , 0 , n*8 , 0 ) );
+    AxpyFunctor f{ (double*)py , (const double*)px , 0.5 };
+    bench( "parallel_for axpy (generic functor path)" , 24.0*n , [&]{ return parallel_for( n , f , parallel_execution_context("axpy") ); } );
+    bench( "parallel_memset (typed or generic)" , 8.0*n , [&]{ return parallel_memset( (double*)py , n , 1.5 , parallel_execution_context("memset") ); } );
+    ONIKA_B200_CHECK( onk_free( px , n*8 ) ); ONIKA_B200_CHECK( onk_free( py , n*8 ) );
+  }
+  {
+    const size_t rows = 8192, cols = n / 8192;
+    extras::Array2D a; a.resize( rows , cols );
+    ONIKA_CU_CHECK_ERRORS( cudaMemPrefetchAsync( a.data() , rows*cols*8 , 0 , (cudaStream_t) stream ) );
+    extras::BlockParallelValueAddFunctor<true> f = { a , 1.1 };
+    bench( "block_parallel_for value-add rows" , 16.0*rows*cols , [&]{ return block_parallel_for( rows , f , parallel_execution_context("vadd") ); } );
+    BlockParallelForOptions ws; ws.fixed_gpu_grid_size = true;
+    bench( "block_parallel_for value-add rows, work-stealing (generic)" , 16.0*rows*cols , [&]{ return block_parallel_for( rows , f , parallel_execution_context("vadd") , ws ); } );
+  }
+  return 0;
+}
+
 int main(int argc, char* argv[])
 {
   if( argc < 3 ) { std::fprintf(stderr,"usage: %s <scenario> <output> [args]\n",argv[0]); return 2; }
@@ -399,6 +440,7 @@ int main(int argc, char* argv[])
   else if( sc == "cells" ) rc = scenario_cells( out , arg(3,4096) );
   else if( sc == "listed" ) rc = scenario_listed( out );
   else if( sc == "soatl" ) rc = scenario_soatl( out , arg(3,53) );
+  else if( sc == "perf" ) rc = scenario_perf( out , arg(3,1<<27) );
   ParallelExecutionQueue::default_queue() << flush << synchronize;
   return rc;
 }

@@ -159,6 +159,93 @@ __global__ void __launch_bounds__(T, C) k_rmw_chunked(double* __restrict__ a, ui
   }
 }
 
+// width sweep: W doubles per access (1 = 8 B scalar, 2 = 16 B, 4 = 32 B), EPT independent accesses per thread per tile
+template<int W> struct vec_t;
+template<> struct vec_t<1> { double v[1]; };
+template<> struct alignas(16) vec_t<2> { double v[2]; };
+template<> struct alignas(32) vec_t<4> { double v[4]; };
+template<int W> __device__ __forceinline__ vec_t<W> ldw(const double* p)
+{
+  vec_t<W> r;
+  if constexpr (W==1) asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(r.v[0]) : "l"(p) : "memory");
+  else if constexpr (W==2) asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.v[0]),"=d"(r.v[1]) : "l"(p) : "memory");
+  else asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[0]),"=d"(r.v[1]),"=d"(r.v[2]),"=d"(r.v[3]) : "l"(p) : "memory");
+  return r;
+}
+template<int W> __device__ __forceinline__ void stw(double* p, const vec_t<W>& r)
+{
+  if constexpr (W==1) asm volatile("st.global.f64 [%0], %1;" :: "l"(p),"d"(r.v[0]) : "memory");
+  else if constexpr (W==2) asm volatile("st.global.v2.f64 [%0], {%1,%2};" :: "l"(p),"d"(r.v[0]),"d"(r.v[1]) : "memory");
+  else asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p),"d"(r.v[0]),"d"(r.v[1]),"d"(r.v[2]),"d"(r.v[3]) : "memory");
+}
+template<int T, int W, int EPT, int C>
+__global__ void __launch_bounds__(T, C) k_rmw_w(double* __restrict__ a, uint64_t ntiles, double s, double c)
+{
+  constexpr unsigned TILE = T*W*EPT;
+  for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+  {
+    double* p = a + t*TILE + threadIdx.x*W;
+    vec_t<W> v[EPT];
+#pragma unroll
+    for (int e=0;e<EPT;e++) v[e] = ldw<W>(p + e*(T*W));
+#pragma unroll
+    for (int e=0;e<EPT;e++) { for (int k=0;k<W;k++) v[e].v[k] = v[e].v[k]*s+c; stw<W>(p + e*(T*W), v[e]); }
+  }
+}
+template<int T, int W, int EPT, int C>
+__global__ void __launch_bounds__(T, C) k_axpy_w(double* __restrict__ y, const double* __restrict__ x, uint64_t ntiles, double a)
+{
+  constexpr unsigned TILE = T*W*EPT;
+  for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+  {
+    const uint64_t o = t*TILE + threadIdx.x*W;
+    vec_t<W> vx[EPT], vy[EPT];
+#pragma unroll
+    for (int e=0;e<EPT;e++) { vx[e] = ldw<W>(x + o + e*(T*W)); vy[e] = ldw<W>(y + o + e*(T*W)); }
+#pragma unroll
+    for (int e=0;e<EPT;e++) { for (int k=0;k<W;k++) vy[e].v[k] = vy[e].v[k] + a*vx[e].v[k]; stw<W>(y + o + e*(T*W), vy[e]); }
+  }
+}
+
+template<int T, int W, int EPT, int C, int HS>
+__global__ void __launch_bounds__(T, C) k_set_w(double* __restrict__ a, uint64_t ntiles, double v)
+{
+  constexpr unsigned TILE = T*W*EPT;
+  vec_t<W> r; for (int k=0;k<W;k++) r.v[k] = v;
+  for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+  {
+    double* p = a + t*TILE + threadIdx.x*W;
+#pragma unroll
+    for (int e=0;e<EPT;e++)
+    {
+      if constexpr (HS==0) stw<W>(p + e*(T*W), r);
+      else { static_assert(W==4 || HS==0); d4 q{v,v,v,v}; st<HS-1>(p + e*(T*W), q); }
+    }
+  }
+}
+
+// memset through TMA bulk stores: the tile is written to shared memory once, then one thread per CTA streams it out
+template<int T, int TILE_BYTES, int C, int DEPTH>
+__global__ void __launch_bounds__(T, C) k_set_tma(double* __restrict__ a, uint64_t ntiles, double v)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
+  double* tile = reinterpret_cast<double*>(smem);
+  for (int i = threadIdx.x; i < TILE_BYTES/8; i += T) tile[i] = v;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    int pending = 0;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+    {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(a + t*(TILE_BYTES/8)), "r"((unsigned)__cvta_generic_to_shared(tile)), "r"(TILE_BYTES) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (++pending >= DEPTH) { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(DEPTH-1) : "memory"); pending = DEPTH-1; }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+
 static cudaEvent_t e0, e1;
 template<class F> double timeit(F f, int reps = 20)
 {
@@ -197,6 +284,18 @@ int main()
 
 #define CPY(T,U,C) { const uint64_t nt = n/(T*U*4); double t = timeit([&]{ k_copy<T,U,C><<<sms*C,T>>>(b,a,nt); }, 10); printf("copy T=%d U=%d C=%d : %8.1f GB/s (r+w)\n",T,U,C, 2*n*8/t/1e9); }
   CPY(256,4,4) CPY(256,2,8) CPY(256,8,2) CPY(512,4,2) CPY(256,4,8)
+
+#define RW(T,W,EPT,C) { const uint64_t nt = n/(T*W*EPT); double t = timeit([&]{ k_rmw_w<T,W,EPT,C><<<sms*C,T>>>(a,nt,1.0,0.0); }, 10); printf("rmw_w T=%d W=%d EPT=%d C=%d : %8.1f GB/s\n",T,W,EPT,C, 2*n*8/t/1e9); }
+  RW(128,1,4,8) RW(128,4,4,4) RW(128,1,4,8) RW(128,4,4,4) RW(128,1,4,8) RW(256,4,4,4) RW(128,1,4,6) RW(128,1,4,10) RW(128,1,4,7) RW(128,1,4,9) RW(64,1,4,16) RW(64,1,8,16) RW(128,1,6,8) RW(128,1,3,8) RW(128,1,5,8) RW(128,2,2,8) RW(128,2,4,8) RW(128,2,4,4) RW(128,4,1,8) RW(128,4,2,8) RW(128,4,2,6) RW(128,4,4,8) RW(256,1,2,8) RW(256,1,4,4)
+#define SET(T,W,EPT,C,HS) { const uint64_t nt = n/(T*W*EPT); double t = timeit([&]{ k_set_w<T,W,EPT,C,HS><<<sms*C,T>>>(a,nt,1.5); }, 10); printf("set_w T=%d W=%d EPT=%d C=%d HS=%d : %8.1f GB/s\n",T,W,EPT,C,HS, n*8/t/1e9); }
+  SET(256,4,4,4,0) SET(256,4,4,4,1) SET(256,4,4,4,2) SET(256,4,4,4,3) SET(256,4,4,4,4) SET(256,4,1,4,0) SET(256,4,1,8,0) SET(256,4,2,4,0) SET(128,4,1,8,0) SET(128,1,4,8,0) SET(128,2,4,8,0) SET(256,4,8,2,0) SET(256,4,4,8,0) SET(512,4,4,2,0) SET(128,4,4,16,0) SET(256,4,1,2,0) SET(256,4,16,1,0)
+#define SETT(T,TB,C,D) { const uint64_t nt = (n*8)/TB; CK(cudaFuncSetAttribute(k_set_tma<T,TB,C,D>, cudaFuncAttributeMaxDynamicSharedMemorySize, TB)); double t = timeit([&]{ k_set_tma<T,TB,C,D><<<sms*C,T,TB>>>(a,nt,1.5); }, 10); printf("set_tma T=%d tile=%d C=%d depth=%d : %8.1f GB/s\n",T,TB,C,D, n*8/t/1e9); }
+  SETT(128,16384,2,4) SETT(128,32768,2,4) SETT(128,65536,1,4) SETT(128,8192,4,8) SETT(128,16384,4,8) SETT(128,32768,1,2) SETT(128,4096,8,8) SETT(128,16384,1,16) SETT(32,16384,4,8)
+  { double t = timeit([&]{ CK(cudaMemsetAsync(a, 0x3c, n*8)); }, 10); printf("cudaMemset(0x3c) : %8.1f GB/s\n", n*8/t/1e9); }
+  { double t = timeit([&]{ CK(cudaMemsetAsync(a, 0, n*8)); }, 10); printf("cudaMemset : %8.1f GB/s\n", n*8/t/1e9); }
+
+#define AX(T,W,EPT,C) { const uint64_t nh = n/2; const uint64_t nt = nh/(T*W*EPT); double t = timeit([&]{ k_axpy_w<T,W,EPT,C><<<sms*C,T>>>(a,a+nh,nt,0.5); }, 10); printf("axpy_w T=%d W=%d EPT=%d C=%d : %8.1f GB/s\n",T,W,EPT,C, 3*nh*8/t/1e9); }
+  AX(128,1,4,16) AX(128,1,4,8) AX(128,1,8,8) AX(256,1,4,8) AX(128,2,4,8) AX(128,2,2,12) AX(256,2,4,4) AX(256,4,2,4) AX(256,4,1,8) AX(128,4,2,8) AX(512,1,4,4) AX(1024,1,2,2)
 
 #define STR(STRIDE,USEFUL) { const uint64_t nl = (n*8)/STRIDE; double t = timeit([&]{ k_strided<256,4><<<sms*4,256>>>(a,nl,STRIDE/8,USEFUL/32,out); }, 10); printf("strided useful=%d of stride=%d : %8.1f GB/s useful (%.1f us for %llu lines)\n",USEFUL,STRIDE, nl*(double)USEFUL/t/1e9, t*1e6, (unsigned long long)nl); }
   STR(128,128) STR(256,128) STR(512,128) STR(1024,128) STR(512,256) STR(1024,256) STR(512,64) STR(2048,128)
