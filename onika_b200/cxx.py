@@ -47,8 +47,27 @@ def needs_build(name: str) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+REFERENCE_TUTORIAL = "/root/reference/plugins/onikaParallelTutorial"
+REFPLUGIN_BIN = os.path.join(CXX_TESTS, "_refplugins", "run_reference_tutorial")
+
+
+def build_reference_plugins(force: bool = False, verbose: bool = False):
+    """Compile the reference's OWN tutorial plugin sources, unchanged and from where they lie (never copied), against
+    this repo's include/onika + the operator runner.  Only possible where /root/reference exists; the binary lands in the
+    git-ignored tests/cxx/_refplugins/ and travels to the GPU box like oracle/_ref."""
+    if not os.path.isdir(REFERENCE_TUTORIAL):
+        return None
+    srcs = [os.path.join(REFERENCE_TUTORIAL, f) for f in sorted(os.listdir(REFERENCE_TUTORIAL)) if f.endswith(".cu")]
+    newest = max(os.path.getmtime(p) for p in srcs + [os.path.join(CXX_TESTS, "run_operator.cu"), _build.LIB])
+    if not force and os.path.exists(REFPLUGIN_BIN) and os.path.getmtime(REFPLUGIN_BIN) > newest and not needs_build("frontend_test"):
+        return REFPLUGIN_BIN
+    os.makedirs(os.path.dirname(REFPLUGIN_BIN), exist_ok=True)
+    return compile_program([os.path.join(CXX_TESTS, "run_operator.cu")] + srcs, REFPLUGIN_BIN, verbose=verbose)
+
+
 def build_all(force: bool = False, verbose: bool = False):
     outs = []
+    build_reference_plugins(force, verbose)
     for name, (srcs, flags) in PROGRAMS.items():
         if force or needs_build(name):
             compile_program([os.path.join(CXX_TESTS, s) for s in srcs], program_path(name), extra_flags=flags, verbose=verbose)

@@ -139,3 +139,67 @@ def test_soatl_container_layout_serialize_and_device_apply(prog, tmp_path, orc, 
     e = raw[-8 * n:].view(np.float64)
     want = orc.soatl_dist(lcg_uniform(n, 10, 0, 1), lcg_uniform(n, 11, 0, 1), lcg_uniform(n, 12, 0, 1))
     assert np.array_equal(e, want, equal_nan=True)
+
+
+# ---------------------------------------------------------------- the reference's own tutorial plugins, compiled unchanged
+def _refplugins():
+    from onika_b200 import cxx
+    if not os.path.exists(cxx.REFPLUGIN_BIN):
+        pytest.skip("tests/cxx/_refplugins/run_reference_tutorial not built (needs /root/reference at build time)")
+    return cxx.REFPLUGIN_BIN
+
+
+def _run_op(tmp_path, op, *args):
+    exe = _refplugins()
+    out = os.path.join(tmp_path, op + ".bin")
+    dump = [a.replace("@OUT", out) for a in args]
+    r = subprocess.run([exe, op, *dump], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stdout[-1500:], r.stderr[-1500:])
+    return out, r.stdout
+
+
+def _load_array(path):
+    raw = np.fromfile(path, dtype=np.uint8)
+    rows, cols = (int(v) for v in raw[:16].view(np.uint64))
+    return raw[16:].view(np.float64).reshape(rows, cols)
+
+
+def _chain(x, v, iters):
+    """BlockParallelIterativeValueAddFunctor (extras/block_parallel_value_add_functor.h:60-93) in numpy"""
+    y = np.power(x, np.sin(x))
+    for _ in range(iters):
+        x = x + y + v
+        y = np.power(x, np.sin(x))
+    return x * y
+
+
+def test_reference_plugin_synchronous_and_async_block_parallel(tmp_path):
+    """plugins/onikaParallelTutorial/{synchronous,async}_block_parallel.cu, unchanged sources"""
+    a = lcg_uniform(300 * 200, 8).reshape(300, 200)
+    for op in ("synchronous_block_parallel", "async_block_parallel"):
+        out, _ = _run_op(tmp_path, op, "fill:my_array=300x200", "my_value=1.1", "dump:my_array=@OUT")
+        assert np.array_equal(_load_array(out), a + 1.1)
+
+
+@pytest.mark.parametrize("op", ["concurrent_block_parallel", "hybrid_async_block_parallel", "automatic_concurrent_parallel"])
+def test_reference_plugin_lane_operators(tmp_path, op):
+    """two arrays x (iterative kernel, then value-add kernel) on lanes 0/1; the hybrid variant runs kernel 2 on the host"""
+    a = lcg_uniform(128 * 96, 8).reshape(128, 96)
+    v, iters = 0.25, 3
+    out, stdout = _run_op(tmp_path, op, "fill:array1=128x96", "fill:array2=128x96", f"value={v}", f"iter_count={iters}",
+                          "dump:array1=@OUT")
+    want = _chain(a, v, iters) + v
+    got = _load_array(out)
+    # pow/sin come from libm on the host and from libdevice on the GPU: last-ulp differences (SURVEY 8c), not bit parity
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+    assert "All operations have terminated" in stdout
+
+
+def test_reference_plugin_parallel_for_benchmarks(tmp_path):
+    _, out = _run_op(tmp_path, "parallel_for_benchmark", "samples=4096", "iterations=8")
+    assert "Benchmark passed" in out
+    _, out = _run_op(tmp_path, "parallel_for_3d_benchmark", "pfor3d_side=16", "pfor3d_block_side=4")
+    # the tutorial prints the 16^3 coverage mask of parallel_for over {2,3,3}..{15,13,13}: 13*10*10 ones
+    body = out.split("parallel_for 3D test")[-1]
+    ones = sum(line.split(":")[1].split().count("1") for line in body.splitlines() if " J=" in line)
+    assert ones == 13 * 10 * 10
