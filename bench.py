@@ -195,7 +195,29 @@ def secondary_kernels(ob, torch):
     outd = torch.empty(1, dtype=torch.float64, device="cuda")
     t = timed(lambda: P.ReduceFunctor(ob.OP_SUM, big, outd).launch(n, 0))
     out["reduce_sum_2^28"] = {"GB/s": round(8 * n / t / 1e9, 1), "ms": round(t * 1e3, 4), "bytes_per_elem": 8}
-    del big
+    # C5: tests/parallel_queue_lane.cu sequence at 16384^2 -- two arrays, (kernel1 -> kernel2 -> min -> sum) per array on
+    # lanes 4/5, captured once as a CUDA graph and replayed on lane 0
+    import ctypes as C
+    from onika_b200 import _capi
+    L = _capi.lib()
+    big2 = torch.rand(n, dtype=torch.float64, device="cuda")
+    res = torch.empty(4, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    others = (C.c_int * 1)(5)
+    _capi.check(L.onk_graph_begin(4, others, 1))
+    for lane, arr, v1, v2, r0 in ((4, big, 1.1, 1.2, 0), (5, big2, 1.3, 1.4, 2)):
+        _capi.check(L.onk_value_add_f64(arr.data_ptr(), 1 << 14, 1 << 14, v1, lane))
+        _capi.check(L.onk_value_add_f64(arr.data_ptr(), 1 << 14, 1 << 14, v2, lane))
+        _capi.check(L.onk_reduce_f64(ob.OP_MIN, arr.data_ptr(), n, res[r0:].data_ptr(), lane))
+        _capi.check(L.onk_reduce_f64(ob.OP_SUM, arr.data_ptr(), n, res[r0 + 1:].data_ptr(), lane))
+    gph = C.c_void_p()
+    _capi.check(L.onk_graph_end(C.byref(gph)))
+    t = timed(lambda: _capi.check(L.onk_graph_launch(gph, 0)), reps=5, warm=2)
+    c5_bytes = 2 * (2 * 16 * n + 2 * 8 * n)
+    out["C5_lane_sequence_2x16384^2_graph"] = {"GB/s": round(c5_bytes / t / 1e9, 1), "ms": round(t * 1e3, 4), "kernels_per_replay": 8,
+                                               "algorithmic_bytes": c5_bytes, "lanes": 2}
+    _capi.check(L.onk_graph_destroy(gph))
+    del big, big2
     fa = soatl.make_hybrid_field_arrays(256, 16, [(f"f{k}", "f8") for k in range(8)])
     n = 64 << 20
     fa.resize(n)

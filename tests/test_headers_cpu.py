@@ -1,0 +1,88 @@
+"""CPU: the boundary compiles where a maintainer would use it -- include/onika_b200.h as plain C11 and as C++, a C
+program linked against libonika_b200.so, and the C++ front end (include/onika/**) in a host-only g++ translation unit."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INC = os.path.join(ROOT, "include")
+
+
+def _env():
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    return env
+
+
+def test_c_abi_header_is_valid_c11_and_cxx(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include <onika_b200.h>\nint main(void){ return onk_abi_version() == ONK_ABI_VERSION ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", f"-I{INC}", str(src)], env=_env())
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", f"-I{INC}", str(src)], env=_env())
+
+
+def test_plain_c_program_links_and_calls_the_library(tmp_path):
+    from onika_b200 import _build
+    lib = _build.build()
+    src = tmp_path / "link.c"
+    src.write_text(r'''
+#include <onika_b200.h>
+#include <stdio.h>
+int main(void)
+{
+  const uint32_t fb[6] = {8,8,8,1,8,4};
+  uint64_t off[6];
+  const uint64_t cap = onk_soatl_update_capacity(17, 0, 16);
+  const uint64_t total = onk_soatl_layout(64, fb, 6, cap, off);
+  printf("%d %llu %llu %llu %llu\n", onk_abi_version(), (unsigned long long)cap, (unsigned long long)total,
+         (unsigned long long)off[3], (unsigned long long)off[5]);
+  int n = -1;
+  const int rc = onk_device_count(&n);            /* no GPU here: a clean error code, not a crash */
+  printf("rc=%d err=%s\n", rc, rc ? onk_last_error() : "none");
+  return 0;
+}
+''')
+    exe = tmp_path / "link"
+    subprocess.check_call(["gcc", "-std=c11", f"-I{INC}", str(src), "-o", str(exe), f"-L{os.path.dirname(lib)}", "-lonika_b200",
+                           f"-Wl,-rpath,{os.path.dirname(lib)}"], env=_env())
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    assert out.splitlines()[0] == "1 32 1216 768 1088"          # SURVEY 8a row a23 layout probe
+
+
+def test_cxx_front_end_compiles_in_a_host_only_translation_unit(tmp_path):
+    """plugins also contain host-only .cpp files that include the onika headers (no nvcc): they must parse with g++"""
+    src = tmp_path / "host_tu.cpp"
+    src.write_text(r'''
+#include <onika/parallel/block_parallel_for.h>
+#include <onika/parallel/parallel_for.h>
+#include <onika/parallel/memset.h>
+#include <onika/parallel/parallel_execution_context_allocator.h>
+#include <onika/parallel/parallel_execution_queue.h>
+#include <onika/parallel/parallel_execution_operators.h>
+#include <onika/extras/array2d.h>
+#include <onika/extras/block_parallel_value_add_functor.h>
+#include <onika/cuda/cuda_reduction.h>
+#include <onika/cuda/memcpy.h>
+#include <onika/soatl/field_arrays.h>
+#include <onika/soatl/compute.h>
+#include <onika/scg/operator.h>
+struct tag_x {}; struct tag_i {};
+namespace onika { namespace soatl {
+  template<> struct FieldId<tag_x> { using value_type = double; using Id = tag_x; static const char* name() { return "x"; } };
+  template<> struct FieldId<tag_i> { using value_type = int; using Id = tag_i; static const char* name() { return "i"; } };
+} }
+using namespace onika;
+static_assert( sizeof(parallel::ParallelDataAccess) == 64 );
+static_assert( sizeof(parallel::HostKernelExecutionScratch) == 1024 && sizeof(parallel::GPUKernelExecutionScratch) == 1024 );
+static_assert( ! parallel::functor_gpu_support_v< extras::BlockParallelValueAddFunctor<true> > , "host-only TU: no device target" );
+static_assert( soatl::find_index_of_id_v<tag_i,tag_x,tag_i> == 1 );
+int layout_probe()
+{
+  // pure layout arithmetic of FieldArrays<64,16,x,i>: column offsets for a capacity (host only, no allocation)
+  return int( soatl::pfa_pointer_offset<64,16,tag_i,tag_x,tag_i>( 32 ) );    // 32*8 = 256
+}
+''')
+    subprocess.check_call(["g++", "-std=c++20", "-fopenmp", "-Wall", "-c", f"-I{INC}", str(src), "-o", str(tmp_path / "host_tu.o")], env=_env())
