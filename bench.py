@@ -98,6 +98,12 @@ def cpu_reduce_min_baseline(min_seconds: float, steps: int | None = None, warmup
     import numpy as np
     import oracle
     orc = oracle.orc
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    orc.set_num_threads(ncpu)
     n = CPU_SAMPLE_ELEMS
     d = np.empty(n, dtype=np.float64)
     orc.fill_lcg(d, SEED)                     # parallel first touch, like cpu_init (tests/gpu_reduce_min_fp64.cu:30-44)
@@ -144,7 +150,7 @@ def run_reference_arm(args) -> int:
         "e2e": {"value": round(gbs, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "elements_per_s": round(gbs * 1e9 / 8, 1),
     }
-    print(json.dumps(line))
+    emit_json(line)
     return 0
 
 
@@ -248,7 +254,7 @@ def run_ours(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: the onika_b200 hot path has no CPU fallback"}))
+        emit_json({"error": "no CUDA device: the onika_b200 hot path has no CPU fallback"})
         return 2
     torch.cuda.set_device(local)
     ob.init(local)
@@ -393,14 +399,45 @@ def run_ours(args) -> int:
         }
         if kernels is not None:
             line["kernels"] = kernels
-        print(json.dumps(line))
+        emit_json(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+class _OnlyJsonOnStdout:
+    """Libraries (NCCL's version banner, for one) write to fd 1.  The contract is ONE JSON line on stdout: fd 1 is pointed
+    at stderr for the whole run and the line is written to the saved descriptor at the end."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text: str) -> None:
+        os.write(self.saved, (text.rstrip("\n") + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+_STDOUT = None
+
+
+def emit_json(obj) -> None:
+    if _STDOUT is not None:
+        _STDOUT.emit(json.dumps(obj))
+    else:
+        print(json.dumps(obj))
+
+
 def main() -> int:
+    global _STDOUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -410,9 +447,14 @@ def main() -> int:
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary per-config kernel timings")
     ap.add_argument("--profile-mode", action="store_true", help="timed region + roofline only (for ncu runs): no e2e, no CPU baseline, no extras")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference_arm(args)
-    return run_ours(args)
+    with _OnlyJsonOnStdout() as guard:
+        _STDOUT = guard
+        try:
+            if args.impl == "reference":
+                return run_reference_arm(args)
+            return run_ours(args)
+        finally:
+            _STDOUT = None
 
 
 if __name__ == "__main__":

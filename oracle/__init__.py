@@ -69,6 +69,7 @@ class _Oracle:
                 build(ref=False)
             L = C.CDLL(ORACLE_SO)
             L.orc_num_threads.restype = C.c_int
+            L.orc_set_num_threads.argtypes = [C.c_int]
             L.orc_fill_lcg_f64.argtypes = [_dp, C.c_uint64, C.c_uint64, C.c_double, C.c_double]
             for name in ("orc_reduce_min_f64", "orc_reduce_max_f64", "orc_reduce_sum_f64_ld"):
                 f = getattr(L, name)
@@ -98,6 +99,10 @@ class _Oracle:
 
     def num_threads(self) -> int:
         return self.lib.orc_num_threads()
+
+    def set_num_threads(self, n: int) -> None:
+        """process-wide OpenMP thread count (shared libgomp: also applies to oracle/_ref)"""
+        self.lib.orc_set_num_threads(int(n))
 
     def fill_lcg(self, d: np.ndarray, seed: int, lo: float = 1e-3, hi: float = 1.0) -> None:
         assert d.dtype == np.float64

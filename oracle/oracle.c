@@ -15,6 +15,7 @@
 #include <omp.h>
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
+void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 void orc_fill_lcg_f64(double* d, uint64_t n, uint64_t seed, double lo, double hi)
 {

@@ -19,6 +19,8 @@ extern "C" {
 #endif
 
 int orc_num_threads(void);
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the CPU baseline asks for the cores it is allowed to use */
+void orc_set_num_threads(int n);
 
 /* deterministic hashed inputs in [lo,hi), filled with the same static OpenMP partition the reductions use, so pages are
  * first-touched by the thread that will read them (what cpu_init does: tests/gpu_reduce_min_fp64.cu:30-44).
