@@ -269,10 +269,17 @@ def run_ours(args) -> int:
     result = torch.empty(1, dtype=torch.float64, device="cuda")
     functor = P.ReduceFunctor(ob.OP_MIN, data, result)
 
+    # N > 1: the path's only exchange is one fp64 partial per rank.  Default: fused into the reduction kernel over NVLink
+    # peer memory (onk_reduce_xchg_f64).  --exchange nccl: separate NCCL all-reduce(MIN) after the kernel.
+    xchg = D.PeerExchange() if (world > 1 and args.exchange == "fused") else None
+
     def step():
-        functor.launch(n, 0)                  # one pass of the hot path over this rank's 2 GiB shard
-        if world > 1:
-            D.combine_across_ranks(ob.OP_MIN, result)       # the path's only exchange: one fp64 partial per rank (NCCL all-reduce MIN)
+        if xchg is not None:
+            xchg.reduce(ob.OP_MIN, data, n=n, out=result, lane=0)   # ONE kernel: local reduce + cross-GPU combine
+        else:
+            functor.launch(n, 0)              # one pass of the hot path over this rank's 2 GiB shard
+            if world > 1:
+                D.combine_across_ranks(ob.OP_MIN, result)
 
     K, W = max(1, args.steps), max(3, args.warmup)
     for _ in range(W):
@@ -390,7 +397,7 @@ def run_ours(args) -> int:
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "elements_per_gpu": n, "bytes_per_gpu": n * 8, "sharding": f"element range x{world}, all-reduce(min) of one fp64 partial per step" if world > 1 else "single GPU",
+            "config": {"workload": WORKLOAD, "elements_per_gpu": n, "bytes_per_gpu": n * 8, "sharding": (f"element range x{world}; one fp64 partial per rank and step, combined " + ("inside the reduction kernel over NVLink peer memory (rank order)" if xchg is not None else "by an NCCL all-reduce(min)")) if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (2 GiB per pass vs 126 MB)", "timing": "CUDA events on the launching stream, max over ranks"},
             "elements_per_s": round(value * 1e9 / 8, 1),
             "frac_of_nominal_8TBs_per_gpu": round(value / world / 8000.0, 4),
@@ -444,6 +451,7 @@ def main() -> int:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=6.0, help="wall budget per CPU-baseline variant")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="N>1: cross-GPU combine inside the kernel (NVLink peer stores) or a separate NCCL all-reduce")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary per-config kernel timings")
     ap.add_argument("--profile-mode", action="store_true", help="timed region + roofline only (for ncu runs): no e2e, no CPU baseline, no extras")
     args = ap.parse_args()

@@ -141,6 +141,24 @@ int onk_reduce_f64(int op, const double* in_dev, uint64_t n, double* out_dev, in
  * mpi::all_reduce_multi, include/onika/mpi/all_reduce_multi.h:30-37) */
 int onk_combine_f64(int op, const double* partials_dev, uint32_t count, double* out_dev, int lane);
 
+/* ---- fused reduction + cross-GPU combine over NVLink peer memory ----
+ * The counterpart of "reduce locally, then mpi::all_reduce_multi" (include/onika/mpi/all_reduce_multi.h:30-37) as ONE
+ * kernel per rank: the last CTA of the local reduction stores its partial into every peer's exchange buffer (peer
+ * stores over NVLink/NVSwitch), publishes it with a release flag, waits for the peers' flags and folds the `world`
+ * partials in RANK ORDER -- every rank gets the same bits, sums are reproducible, no collective library call.
+ * Exchange buffers are ONK_XCHG_BYTES of device memory per rank (onk_xchg_create), shared between the processes of one
+ * node through CUDA IPC: export the local handle, all-gather the handles with any host-side transport, open the peers.
+ * All ranks must call onk_reduce_xchg_f64 the same number of times (the call count is the flag epoch). */
+#define ONK_XCHG_BYTES      1024
+#define ONK_XCHG_MAX_WORLD    16
+#define ONK_IPC_HANDLE_BYTES  64
+typedef struct onk_xchg onk_xchg;
+int onk_xchg_create(int rank, int world, onk_xchg** x);
+int onk_xchg_export(onk_xchg* x, unsigned char handle[ONK_IPC_HANDLE_BYTES]);
+int onk_xchg_connect(onk_xchg* x, const unsigned char* handles /* world x ONK_IPC_HANDLE_BYTES, rank order */);
+int onk_xchg_destroy(onk_xchg* x);
+int onk_reduce_xchg_f64(int op, const double* in_dev, uint64_t n, double* out_dev, onk_xchg* x, int lane);
+
 /* parallel_for(N, y[i] += a*x[i])   include/onika/parallel/parallel_for.h:91-112 (config C1) */
 int onk_axpy_f64(double* y_dev, const double* x_dev, double a, uint64_t n, int lane);
 /* parallel_memset<T>                include/onika/parallel/memset.h:30-51 ; elem_bytes in {1,2,4,8}, value = low bytes of pattern */

@@ -17,6 +17,7 @@ OK, ERR_NO_DEVICE, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4, 
 LANE_DEFAULT, LANE_ALL, MAX_LANES = -1, -2, 256
 MEM_DEVICE, MEM_MANAGED, MEM_PINNED = 0, 1, 2
 OP_MIN, OP_MAX, OP_SUM = 0, 1, 2
+ONK_IPC_HANDLE_BYTES, ONK_XCHG_MAX_WORLD = 64, 16
 
 vp, u64, u32, i32, dbl, sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_double, C.c_size_t
 P = C.POINTER
@@ -56,6 +57,11 @@ PROTOTYPES = {
     "onk_graph_destroy": (i32, [vp]),
     "onk_reduce_f64": (i32, [i32, vp, u64, vp, i32]),
     "onk_combine_f64": (i32, [i32, vp, u32, vp, i32]),
+    "onk_xchg_create": (i32, [i32, i32, P(vp)]),
+    "onk_xchg_export": (i32, [vp, C.c_char_p]),
+    "onk_xchg_connect": (i32, [vp, C.c_char_p]),
+    "onk_xchg_destroy": (i32, [vp]),
+    "onk_reduce_xchg_f64": (i32, [i32, vp, u64, vp, vp, i32]),
     "onk_axpy_f64": (i32, [vp, vp, dbl, u64, i32]),
     "onk_parallel_memset": (i32, [vp, u64, u64, i32, i32]),
     "onk_value_add_f64": (i32, [vp, u64, u64, dbl, i32]),

@@ -20,10 +20,67 @@ namespace onk
   constexpr unsigned RED_TILE = THREADS * RED_UNROLL * 4;        // doubles per tile (4096 = 32 KiB)
   constexpr unsigned RED_CTAS_PER_SM = 4;
 
+  // ---- cross-GPU exchange (fused into the finish of the reduction kernel) ----
+  // one buffer per rank, mapped into every peer process: [parity][rank] values and epoch flags
+  struct XchgBuffer
+  {
+    double             val[2][ONK_XCHG_MAX_WORLD];
+    unsigned long long flag[2][ONK_XCHG_MAX_WORLD];
+    unsigned long long error;                      // set when a peer did not show up in time
+  };
+  static_assert(sizeof(XchgBuffer) <= ONK_XCHG_BYTES, "exchange buffer layout");
+  struct XchgParams
+  {
+    XchgBuffer* peer[ONK_XCHG_MAX_WORLD];          // peer[r] = rank r's buffer as seen from this device (peer[rank] is local)
+    int rank, world;
+    unsigned long long epoch;                      // strictly increasing, identical on all ranks for matching calls
+  };
+
+  __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+  { asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+  __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+  { unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+
+  // called by the last CTA with the rank-local result in thread 0; returns the global result in thread 0
   template<int OP>
+  __device__ __forceinline__ double xchg_combine(double local, const XchgParams& xp)
+  {
+    using R = Red<OP>;
+    __shared__ double s_local;
+    __shared__ double s_vals[ONK_XCHG_MAX_WORLD];
+    if (threadIdx.x == 0) s_local = local;
+    __syncthreads();
+    const int par = (int)(xp.epoch & 1ull);
+    if ((int)threadIdx.x < xp.world)
+    {
+      const int peer = (int)threadIdx.x;
+      // publish: value first, then the flag with release semantics at system scope (peer stores travel over NVLink)
+      XchgBuffer* pb = xp.peer[peer];
+      *reinterpret_cast<volatile double*>(&pb->val[par][xp.rank]) = s_local;
+      st_release_sys(&pb->flag[par][xp.rank], xp.epoch);
+      // gather: wait for rank `peer`'s flag in MY buffer
+      XchgBuffer* mine = xp.peer[xp.rank];
+      const long long t0 = clock64();
+      bool ok = true;
+      while (ld_acquire_sys(&mine->flag[par][peer]) < xp.epoch)
+      {
+        if (clock64() - t0 > 20000000000ll) { ok = false; break; }        // ~10 s: a peer is missing; do not hang the device
+        __nanosleep(64);
+      }
+      s_vals[peer] = ok ? *reinterpret_cast<volatile double*>(&mine->val[par][peer]) : __longlong_as_double(0x7ff8000000000000ll);
+      if (!ok) mine->error = xp.epoch;
+    }
+    __syncthreads();
+    double r = R::identity();
+    if (threadIdx.x == 0) for (int i = 0; i < xp.world; i++) r = R::apply(r, s_vals[i]);     // rank order
+    return r;
+  }
+
+  template<int OP, bool XCHG>
   __global__ void __launch_bounds__(THREADS, RED_CTAS_PER_SM)
   reduce_f64_kernel(const double* __restrict__ in, uint64_t n, uint64_t head, uint64_t ntiles,
-                    double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ out)
+                    double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ out,
+                    const __grid_constant__ XchgParams xp)
   {
     using R = Red<OP>;
     double acc[RED_UNROLL * 4];
@@ -82,6 +139,7 @@ namespace onk
       double r = R::identity();
       for (unsigned i = threadIdx.x; i < gridDim.x; i += THREADS) r = R::apply(r, __ldcg(partials + i));
       r = block_reduce<OP, THREADS>(r);
+      if constexpr (XCHG) r = xchg_combine<OP>(r, xp);
       if (threadIdx.x == 0) { *out = r; *ticket = 0u; }
     }
   }
@@ -101,7 +159,7 @@ namespace onk
   }
 
   template<int OP>
-  static int launch_reduce(const double* in, uint64_t n, double* out, Lane* L)
+  static int launch_reduce(const double* in, uint64_t n, double* out, Lane* L, const XchgParams* xp = nullptr)
   {
     // 32-byte alignment of the vector body; a pointer that is not even 8-byte aligned is rejected by the caller
     uint64_t head = ((32 - ((uintptr_t)in & 31)) & 31) / 8;
@@ -111,7 +169,10 @@ namespace onk
     unsigned grid = grid_for(ntiles, 1, RED_CTAS_PER_SM);
     if (ntiles == 0) grid = (unsigned)((edge + THREADS - 1) / THREADS ? (edge + THREADS - 1) / THREADS : 1);
     if (grid > (unsigned)MAX_PARTIALS) grid = MAX_PARTIALS;
-    reduce_f64_kernel<OP><<<grid, THREADS, 0, L->stream>>>(in, n, head, ntiles, L->ws.partials, L->ws.ticket, out);
+    if (xp != nullptr && xp->world > 1)
+      reduce_f64_kernel<OP, true><<<grid, THREADS, 0, L->stream>>>(in, n, head, ntiles, L->ws.partials, L->ws.ticket, out, *xp);
+    else
+      reduce_f64_kernel<OP, false><<<grid, THREADS, 0, L->stream>>>(in, n, head, ntiles, L->ws.partials, L->ws.ticket, out, XchgParams{});
     ONK_CHECK_LAUNCH();
     count_launch();
     return ONK_OK;
@@ -120,7 +181,84 @@ namespace onk
 
 using namespace onk;
 
+struct onk_xchg
+{
+  XchgBuffer* local = nullptr;
+  XchgParams  params{};
+  bool        connected = false;
+  void*       opened[ONK_XCHG_MAX_WORLD] = {};
+};
+
 extern "C" {
+
+int onk_xchg_create(int rank, int world, onk_xchg** x)
+{
+  ONK_REQUIRE(x != nullptr, "onk_xchg_create: null argument");
+  ONK_REQUIRE(world >= 1 && world <= ONK_XCHG_MAX_WORLD && rank >= 0 && rank < world, "onk_xchg_create: bad rank/world %d/%d", rank, world);
+  if (int rc = require_init()) return rc;
+  onk_xchg* h = new onk_xchg();
+  cudaError_t e = cudaMalloc((void**)&h->local, ONK_XCHG_BYTES);      // plain cudaMalloc: exportable through CUDA IPC
+  if (e == cudaSuccess) e = cudaMemset(h->local, 0, ONK_XCHG_BYTES);
+  if (e != cudaSuccess) { delete h; ONK_CUDA(e); }
+  h->params.rank = rank; h->params.world = world; h->params.epoch = 0;
+  h->params.peer[rank] = h->local;
+  h->connected = (world == 1);
+  *x = h;
+  return ONK_OK;
+}
+
+int onk_xchg_export(onk_xchg* x, unsigned char handle[ONK_IPC_HANDLE_BYTES])
+{
+  ONK_REQUIRE(x != nullptr && handle != nullptr, "onk_xchg_export: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == ONK_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+  cudaIpcMemHandle_t h;
+  ONK_CUDA(cudaIpcGetMemHandle(&h, x->local));
+  memcpy(handle, &h, sizeof(h));
+  return ONK_OK;
+}
+
+int onk_xchg_connect(onk_xchg* x, const unsigned char* handles)
+{
+  ONK_REQUIRE(x != nullptr && handles != nullptr, "onk_xchg_connect: null argument");
+  for (int r = 0; r < x->params.world; r++)
+  {
+    if (r == x->params.rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * ONK_IPC_HANDLE_BYTES, sizeof(h));
+    void* p = nullptr;
+    ONK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    x->opened[r] = p;
+    x->params.peer[r] = (XchgBuffer*)p;
+  }
+  x->connected = true;
+  return ONK_OK;
+}
+
+int onk_xchg_destroy(onk_xchg* x)
+{
+  if (!x) return ONK_OK;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < ONK_XCHG_MAX_WORLD; r++) if (x->opened[r]) cudaIpcCloseMemHandle(x->opened[r]);
+  if (x->local) cudaFree(x->local);
+  delete x;
+  return ONK_OK;
+}
+
+int onk_reduce_xchg_f64(int op, const double* in_dev, uint64_t n, double* out_dev, onk_xchg* x, int lane)
+{
+  ONK_REQUIRE(x != nullptr && x->connected, "onk_reduce_xchg_f64: exchange is not connected");
+  ONK_REQUIRE(out_dev != nullptr && (n == 0 || in_dev != nullptr), "onk_reduce_xchg_f64: null pointer");
+  ONK_REQUIRE(((uintptr_t)in_dev & 7) == 0, "onk_reduce_xchg_f64: input is not 8-byte aligned");
+  ONK_REQUIRE(op == ONK_OP_MIN || op == ONK_OP_MAX || op == ONK_OP_SUM, "onk_reduce_xchg_f64: unknown op %d", op);
+  Lane* L; if (int rc = lane_get(lane, &L)) return rc;
+  x->params.epoch += 1;
+  switch (op)
+  {
+    case ONK_OP_MIN: return launch_reduce<ONK_OP_MIN>(in_dev, n, out_dev, L, &x->params);
+    case ONK_OP_MAX: return launch_reduce<ONK_OP_MAX>(in_dev, n, out_dev, L, &x->params);
+    default:         return launch_reduce<ONK_OP_SUM>(in_dev, n, out_dev, L, &x->params);
+  }
+}
 
 int onk_reduce_f64(int op, const double* in_dev, uint64_t n, double* out_dev, int lane)
 {

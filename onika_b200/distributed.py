@@ -59,3 +59,45 @@ def combine_across_ranks(op: int, partial, group=None):
         return parallel.combine(OP_SUM, gathered, out=partial)
     partial[0] = fold_partials(OP_SUM, [float(v) for v in gathered])
     return partial
+
+
+class PeerExchange:
+    """Fused reduction + cross-GPU combine over NVLink peer memory (onk_reduce_xchg_f64).
+
+    One exchange buffer per rank in device memory, shared between the processes of the node through CUDA IPC: the
+    handles travel once through torch.distributed (host-side plumbing); afterwards every reduction is ONE kernel per
+    rank -- its last CTA stores the rank's partial into every peer's buffer, publishes a release flag, waits for the
+    peers' flags and folds the partials in rank order.  No NCCL call on the data path.  All ranks must issue the same
+    sequence of reduce() calls."""
+
+    def __init__(self, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from ._capi import check, lib, ONK_IPC_HANDLE_BYTES
+        self._C, self._check, self._lib = C, check, lib()
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.handle = C.c_void_p()
+        check(self._lib.onk_xchg_create(self.rank, self.world, C.byref(self.handle)))
+        if self.world > 1:
+            mine = C.create_string_buffer(ONK_IPC_HANDLE_BYTES)
+            check(self._lib.onk_xchg_export(self.handle, mine))
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, bytes(mine.raw), group=group)
+            check(self._lib.onk_xchg_connect(self.handle, b"".join(gathered)))
+            dist.barrier(group=group)          # every rank has mapped every buffer before the first kernel uses them
+
+    def reduce(self, op: int, data, n=None, out=None, lane: int = -1):
+        import torch
+        from .runtime import ptr
+        if n is None:
+            n = data.numel()
+        if out is None:
+            out = torch.empty(1, dtype=torch.float64, device=data.device)
+        self._check(self._lib.onk_reduce_xchg_f64(op, ptr(data), n, ptr(out), self.handle, lane))
+        return out
+
+    def close(self):
+        if self.handle:
+            self._check(self._lib.onk_xchg_destroy(self.handle))
+            self.handle = None

@@ -1,0 +1,73 @@
+"""GPU, needs >= 2 devices (skipped on a 1-GPU box): the fused reduction + cross-GPU combine over NVLink peer memory
+(onk_reduce_xchg_f64) against the oracle on the unsharded data, one process per GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import onika_b200 as ob
+    from onika_b200 import distributed as D, _capi
+    from tests._inputs import lcg_uniform
+    ob.init(rank)
+    ob.bind_lane_to_torch_stream(0)
+    d = lcg_uniform(n, 7, -1.0, 1.0)
+    b, e = D.shard_range(n, rank, world)
+    shard = torch.from_numpy(d[b:e]).cuda()
+    x = D.PeerExchange()
+    res = {}
+    for rep in range(3):                      # repeated calls exercise the epoch / parity protocol
+        for name, op in (("min", _capi.OP_MIN), ("max", _capi.OP_MAX), ("sum", _capi.OP_SUM)):
+            out = x.reduce(op, shard)
+            torch.cuda.synchronize()
+            res[(name, rep)] = float(out.item())
+    # same answer as the NCCL path
+    part = ob.parallel.reduce_min(shard)
+    nccl = float(D.combine_across_ranks(_capi.OP_MIN, part).item())
+    q.put((rank, res, nccl))
+    dist.barrier()
+    x.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [4_000_003, 17])
+def test_fused_reduce_exchange_two_gpus(n, orc):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted((q.get(timeout=180) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    from tests._inputs import lcg_uniform
+    d = lcg_uniform(n, 7, -1.0, 1.0)
+    for rank, res, nccl in got:
+        for rep in range(3):
+            assert res[("min", rep)] == orc.reduce_min(d) and res[("max", rep)] == orc.reduce_max(d)
+            assert abs(res[("sum", rep)] - orc.reduce_sum_ld(d)) <= 1e-12 * np.abs(d).sum()
+        assert nccl == orc.reduce_min(d)
+    assert got[0][1] == got[1][1]             # identical bits on both ranks, every repetition
