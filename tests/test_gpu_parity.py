@@ -473,3 +473,68 @@ def test_errors_and_memory_api(ob):
     info = ob.device_info()
     assert info["sm_count"] > 0 and "B200" in info["name"]
     assert ob.launch_count() > 0
+
+
+# ---------------------------------------------------------------- full-size properties for C3 and C5
+def test_soatl_rmw_config_c3_full_size_properties(ob):
+    """config C3: FieldArrays<256,16,f0..f7>, 64 Mi elements (4 GiB): sampled elements bit-exact against the unfused host
+    formula, the padding sweep stops at ceil(n/16)*16, the rest of the allocation is untouched, column sums follow
+    sum(f*s+c) = s*sum(f) + n*c within the summation tolerance."""
+    import torch
+    from onika_b200 import soatl, parallel as P
+    n = (64 << 20) - 5                                    # ragged: 11 padding elements are swept, none beyond
+    fa = soatl.make_hybrid_field_arrays(256, 16, [(f"f{k}", "f8") for k in range(8)])
+    fa.resize(n)
+    cap = fa.capacity()
+    assert cap % 16 == 0 and cap >= n
+    g = torch.Generator(device="cuda").manual_seed(0)
+    fa.storage.view(torch.float64).copy_(torch.rand(fa.storage.numel() // 8, dtype=torch.float64, device="cuda", generator=g))
+    s, c = 1.0000001, [0.125 * (k + 1) for k in range(8)]
+    rng = np.random.default_rng(5)
+    idx = np.unique(np.concatenate([rng.integers(0, n, 4096), [0, 1, n - 1, n, (n + 15) // 16 * 16 - 1]]))   # [n, ceil16(n)): swept padding
+    tidx = torch.from_numpy(idx).cuda()
+    before = [host(fa[f"f{k}"][tidx]) for k in range(8)]
+    sums0 = [float(P.reduce_sum(fa[f"f{k}"][:n]).item()) for k in range(8)]
+    n_pad = (n + 15) // 16 * 16
+    beyond0 = [host(fa[f"f{k}"][n_pad:cap]) for k in range(8)] if cap > n_pad else None
+    fa.parallel_apply_rmw(s, c)
+    ob.lane_sync()
+    for k in range(8):
+        got = host(fa[f"f{k}"][tidx])
+        want = before[k] * s + c[k]                        # numpy: rounded multiply, then rounded add
+        assert np.array_equal(got, want), k
+        s1 = float(P.reduce_sum(fa[f"f{k}"][:n]).item())
+        assert abs(s1 - (s * sums0[k] + n * c[k])) <= 1e-9 * abs(s1)
+        if beyond0 is not None:
+            assert np.array_equal(host(fa[f"f{k}"][n_pad:cap]), beyond0[k])
+    fa.clear()
+
+
+def test_lane_sequence_config_c5_full_size_properties(ob):
+    """config C5 shape: two 16384 x 16384 fp64 arrays (2 GiB each), kernel1 -> kernel2 per array on lanes 1/2, then min
+    and sum of each array: sampled elements bit-exact, min exact, sums within tolerance and reproducible."""
+    import torch
+    from onika_b200 import parallel as P
+    rows = cols = 1 << 14
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a1 = torch.rand(rows, cols, dtype=torch.float64, device="cuda", generator=g)
+    a2 = torch.rand(rows, cols, dtype=torch.float64, device="cuda", generator=g)
+    rng = np.random.default_rng(9)
+    ii, jj = torch.from_numpy(rng.integers(0, rows, 4096)).cuda(), torch.from_numpy(rng.integers(0, cols, 4096)).cuda()
+    b1, b2 = host(a1[ii, jj]), host(a2[ii, jj])
+    m1_0, m2_0 = float(a1.min().item()), float(a2.min().item())
+    torch.cuda.synchronize()
+    q = P.ParallelExecutionQueue()
+    q << P.set_lane(1) << P.block_parallel_for(rows, P.BlockParallelValueAddFunctor(a1, 1.1)) \
+      << P.set_lane(2) << P.block_parallel_for(rows, P.BlockParallelValueAddFunctor(a2, 1.3)) \
+      << P.set_lane(1) << P.block_parallel_for(rows, P.BlockParallelValueAddFunctor(a1, 1.2)) \
+      << P.set_lane(2) << P.block_parallel_for(rows, P.BlockParallelValueAddFunctor(a2, 1.4)) << P.flush
+    r = [P.reduce_min(a1, lane=1), P.reduce_sum(a1, lane=1), P.reduce_min(a2, lane=2), P.reduce_sum(a2, lane=2)]
+    q << P.synchronize
+    ob.lane_sync()
+    assert np.array_equal(host(a1[ii, jj]), (b1 + 1.1) + 1.2) and np.array_equal(host(a2[ii, jj]), (b2 + 1.3) + 1.4)
+    assert float(r[0].item()) == (m1_0 + 1.1) + 1.2 and float(r[2].item()) == (m2_0 + 1.3) + 1.4   # x -> (x+a)+b is monotone
+    for arr, sm in ((a1, r[1]), (a2, r[3])):
+        ref = float(arr.sum().item())
+        assert abs(float(sm.item()) - ref) <= SUM_RTOL * ref
+        assert float(P.reduce_sum(arr).item()) == float(sm.item())
