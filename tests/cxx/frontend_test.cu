@@ -16,6 +16,10 @@
 #include <onika/soatl/compute.h>
 #include <onika/soatl/copy.h>
 #include <onika/memory/allocator.h>
+#include <onika/cuda/memcpy.h>
+#include <onika/cuda/input_array_span.h>
+#include <onika/cuda/ro_shallow_copy.h>
+#include <onika/cuda/cuda_math.h>
 #include "declare_fields.h"
 
 #include <cfloat>
@@ -146,6 +150,46 @@ struct ScaleListedFunctor
   inline void operator () ( block_parallel_for_gpu_epilog_t ) const { ++ *epilog_calls; }
 };
 namespace onika { namespace parallel { template<> struct BlockParallelForFunctorTraits<ScaleListedFunctor> { static inline constexpr bool CudaCompatible = true; }; } }
+
+// helpers of include/onika/cuda: cu_block_memcpy / cu_block_memmove, InputArraySpan (small array inside the functor),
+// VectorShallowCopy, cuda_math
+struct HelpersFunctor
+{
+  const uint8_t* src; uint8_t* dst; uint8_t* mv; size_t row_bytes;
+  onika::cuda::InputArraySpan<double,8> coeffs;            // <= 8 elements: travels inside the kernel parameters
+  onika::cuda::VectorShallowCopy<double> table;
+  double* out;
+  ONIKA_HOST_DEVICE_FUNC inline void operator () ( size_t row ) const
+  {
+    // misaligned byte ranges on purpose: row r starts at r*row_bytes + (r % 7)
+    onika::cuda::cu_block_memcpy( dst + row*row_bytes + (row%7) , src + row*row_bytes + (row%5) , row_bytes - 8 );
+    // overlapping move inside mv: shift the row's payload by 3 bytes to the right
+    onika::cuda::cu_block_memmove( mv + row*row_bytes + 3 , mv + row*row_bytes , row_bytes - 8 );
+    if( ONIKA_CU_THREAD_IDX == 0 )
+    {
+      double acc = 0.0;
+      for(size_t k=0;k<coeffs.size();k++) acc += coeffs[k] * table[ ( row + k ) % table.size() ];
+      out[row] = onika::cuda::clamp( acc , -1.0 , 1.0 ) + onika::cuda::pow_ce_dint( 2.0 , double(row % 5) );
+    }
+  }
+};
+namespace onika { namespace parallel { template<> struct BlockParallelForFunctorTraits<HelpersFunctor> { static inline constexpr bool CudaCompatible = true; }; } }
+
+static int scenario_helpers(Out& out, size_t rows)
+{
+  const size_t row_bytes = 1000;
+  CudaMMVector<uint8_t> src( rows*row_bytes ), dst( rows*row_bytes , uint8_t(0xEE) ), mv( rows*row_bytes );
+  for(size_t i=0;i<src.size();i++) { src[i] = uint8_t( ( i * 131u + 7u ) >> 3 ); mv[i] = uint8_t( ( i * 29u + 1u ) >> 2 ); }
+  std::vector<double> c = { 0.5 , -0.25 , 0.125 , 1.5 , -2.0 };
+  CudaMMVector<double> table( 64 ); fill( table , 4 , -1.0 , 1.0 );
+  CudaMMVector<double> res( rows , 0.0 );
+  HelpersFunctor f = { src.data() , dst.data() , mv.data() , row_bytes , onika::cuda::InputArraySpan<double,8>( c ) , onika::cuda::VectorShallowCopy<double>( table ) , res.data() };
+  block_parallel_for( rows , f , parallel_execution_context("helpers") );
+  out.bytes( dst.data() , dst.size() );
+  out.bytes( mv.data() , mv.size() );
+  out.doubles( res.data() , rows );
+  return 0;
+}
 
 // ---------------------------------------------------------------- scenarios
 static int scenario_axpy(Out& out, size_t n)
@@ -441,6 +485,7 @@ int main(int argc, char* argv[])
   else if( sc == "listed" ) rc = scenario_listed( out );
   else if( sc == "soatl" ) rc = scenario_soatl( out , arg(3,53) );
   else if( sc == "perf" ) rc = scenario_perf( out , arg(3,1<<27) );
+  else if( sc == "helpers" ) rc = scenario_helpers( out , arg(3,333) );
   ParallelExecutionQueue::default_queue() << flush << synchronize;
   return rc;
 }

@@ -116,6 +116,31 @@ def test_element_list_space_prolog_epilog(prog, tmp_path):
     assert r[1000] == 1.0 and r[1001] == 1.0
 
 
+def test_cuda_helper_headers_memcpy_memmove_spans_math(prog, tmp_path):
+    rows, rb = 333, 1000
+    raw = run(prog, tmp_path, "helpers", rows)
+    n = rows * rb
+    dst, mv, res = raw[:n], raw[n:2 * n], raw[2 * n:].view(np.float64)
+    i = np.arange(n, dtype=np.uint64)
+    src = ((i * 131 + 7) >> 3).astype(np.uint8)
+    mv0 = ((i * 29 + 1) >> 2).astype(np.uint8)
+    want_dst = np.full(n, 0xEE, np.uint8)
+    want_mv = mv0.copy()
+    for r in range(rows):
+        want_dst[r * rb + r % 7: r * rb + r % 7 + rb - 8] = src[r * rb + r % 5: r * rb + r % 5 + rb - 8]
+        want_mv[r * rb + 3: r * rb + 3 + rb - 8] = mv0[r * rb: r * rb + rb - 8]
+    assert np.array_equal(dst, want_dst) and np.array_equal(mv, want_mv)
+    c = [0.5, -0.25, 0.125, 1.5, -2.0]
+    table = lcg_uniform(64, 4, -1.0, 1.0)
+    want = np.zeros(rows)
+    for r in range(rows):
+        acc = 0.0
+        for k, ck in enumerate(c):
+            acc += ck * table[(r + k) % 64]
+        want[r] = min(max(acc, -1.0), 1.0) + 2.0 ** (r % 5)
+    assert np.array_equal(res, want)
+
+
 def test_soatl_container_layout_serialize_and_device_apply(prog, tmp_path, orc, gold):
     n = 13
     raw = run(prog, tmp_path, "soatl", n)
