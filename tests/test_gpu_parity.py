@@ -538,3 +538,86 @@ def test_lane_sequence_config_c5_full_size_properties(ob):
         ref = float(arr.sum().item())
         assert abs(float(sm.item()) - ref) <= SUM_RTOL * ref
         assert float(P.reduce_sum(arr).item()) == float(sm.item())
+
+
+# ---------------------------------------------------------------- runtime hardening
+def test_many_lanes_cross_lane_wait_and_query(ob, orc):
+    """64 lanes each run their own kernel chain concurrently; lane 0 then waits on all of them on the device
+    (onk_lane_wait_lane) and reduces; nothing is synchronised on the host until the end."""
+    import torch
+    from tests._inputs import lcg_uniform
+    from onika_b200 import _capi
+    L = _capi.lib()
+    nl, n = 64, 200_003
+    h = lcg_uniform(nl * n, 21, -1, 1).reshape(nl, n)
+    t = dev(h)
+    outs = torch.empty(nl, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    for lane in range(1, nl + 1):
+        row = t[lane - 1]
+        _capi.check(L.onk_value_add_f64(row.data_ptr(), 1, n, 0.5, lane))
+        _capi.check(L.onk_axpy_f64(row.data_ptr(), row.data_ptr(), 1.0, n, lane))      # y += 1*y  (x aliases y: same thread reads both)
+        _capi.check(L.onk_reduce_f64(_capi.OP_MAX, row.data_ptr(), n, outs[lane - 1:].data_ptr(), lane))
+    for lane in range(1, nl + 1):
+        _capi.check(L.onk_lane_wait_lane(100, lane))
+    final = torch.empty(1, dtype=torch.float64, device="cuda")
+    _capi.check(L.onk_reduce_f64(_capi.OP_MAX, outs.data_ptr(), nl, final.data_ptr(), 100))
+    idle = C.c_int(-1)
+    _capi.check(L.onk_lane_query(_capi.LANE_ALL, C.byref(idle)))
+    assert idle.value in (0, 1)
+    _capi.check(L.onk_lane_sync(100))
+    want = (h + 0.5) + (h + 0.5)
+    assert float(final.item()) == want.max()
+    ob.lane_sync()
+    assert np.array_equal(host(t), want)
+    _capi.check(L.onk_lane_query(_capi.LANE_ALL, C.byref(idle)))
+    assert idle.value == 1
+
+
+def test_managed_memory_prefetch_and_memcpy(ob, orc):
+    from tests._inputs import lcg_uniform
+    from onika_b200 import _capi
+    L = _capi.lib()
+    n = 1_000_003
+    p = C.c_void_p()
+    _capi.check(L.onk_alloc(n * 8, 256, _capi.MEM_MANAGED, C.byref(p)))
+    yes = C.c_int()
+    _capi.check(L.onk_is_gpu_addressable(p, C.byref(yes)))
+    assert yes.value == 1
+    a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n,))      # host-dereferenceable, as plugins expect
+    d = lcg_uniform(n, 31, -1, 1)
+    a[:] = d
+    _capi.check(L.onk_prefetch(p, n * 8, 1, 3))
+    _capi.check(L.onk_value_add_f64(p, 1, n, 2.0, 3))
+    out = C.c_void_p()
+    _capi.check(L.onk_alloc(8, 8, _capi.MEM_PINNED, C.byref(out)))               # pinned host result slot, written by the kernel
+    _capi.check(L.onk_reduce_f64(_capi.OP_MIN, p, n, out, 3))
+    back = np.zeros(n)
+    _capi.check(L.onk_memcpy(back.ctypes.data, p, n * 8, 3))
+    _capi.check(L.onk_lane_sync(3))
+    assert np.array_equal(back, d + 2.0) and np.array_equal(a, d + 2.0)
+    assert C.cast(out, C.POINTER(C.c_double))[0] == (d + 2.0).min()
+    _capi.check(L.onk_free(p, n * 8))
+    _capi.check(L.onk_free(out, 8))
+
+
+def test_finalize_and_reinitialise(orc):
+    """onk_finalize tears lanes/scratch down; the next call re-creates them (runs in a subprocess: the other tests share one runtime)."""
+    import subprocess
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import onika_b200 as ob
+from onika_b200 import parallel as P
+for rnd in range(3):
+    ob.init(0)
+    t = torch.arange(100003, dtype=torch.float64, device="cuda") + 5.0
+    torch.cuda.synchronize()
+    assert P.reduce_min(t, lane=2).item() == 5.0
+    assert P.reduce_sum(t, lane=7).item() == float((np.arange(100003) + 5.0).sum())
+    ob.lane_sync()
+    ob.finalize()
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-1500:]
