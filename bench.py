@@ -271,7 +271,20 @@ def run_ours(args) -> int:
 
     # N > 1: the path's only exchange is one fp64 partial per rank.  Default: fused into the reduction kernel over NVLink
     # peer memory (onk_reduce_xchg_f64).  --exchange nccl: separate NCCL all-reduce(MIN) after the kernel.
-    xchg = D.PeerExchange() if (world > 1 and args.exchange == "fused") else None
+    xchg = None
+    if world > 1 and args.exchange == "fused":
+        try:
+            xchg = D.PeerExchange()
+            ok = 1
+        except Exception as ex:   # no peer access / CUDA IPC on this box: every rank must take the same path
+            print(f"[bench] rank {rank}: fused exchange unavailable ({str(ex)[:120]}); using NCCL", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if xchg is not None:
+                xchg.close()
+            xchg = None
 
     def step():
         if xchg is not None:

@@ -81,11 +81,16 @@ class PeerExchange:
         check(self._lib.onk_xchg_create(self.rank, self.world, C.byref(self.handle)))
         if self.world > 1:
             mine = C.create_string_buffer(ONK_IPC_HANDLE_BYTES)
-            check(self._lib.onk_xchg_export(self.handle, mine))
+            rc = self._lib.onk_xchg_export(self.handle, mine)
             gathered = [None] * self.world
-            dist.all_gather_object(gathered, bytes(mine.raw), group=group)
-            check(self._lib.onk_xchg_connect(self.handle, b"".join(gathered)))
-            dist.barrier(group=group)          # every rank has mapped every buffer before the first kernel uses them
+            dist.all_gather_object(gathered, bytes(mine.raw) if rc == 0 else None, group=group)   # collective: always reached
+            if rc != 0 or any(g is None for g in gathered):
+                raise RuntimeError("CUDA IPC export of the exchange buffer failed on some rank")
+            rc = self._lib.onk_xchg_connect(self.handle, b"".join(gathered))
+            oks = [None] * self.world
+            dist.all_gather_object(oks, rc == 0, group=group)          # every rank has mapped every buffer before first use
+            if not all(oks):
+                raise RuntimeError("CUDA IPC open of a peer exchange buffer failed on some rank (no peer access?)")
 
     def reduce(self, op: int, data, n=None, out=None, lane: int = -1):
         import torch
