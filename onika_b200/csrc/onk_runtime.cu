@@ -46,7 +46,8 @@ namespace onk
     if (lane < 0 || lane >= ONK_MAX_LANES) { set_error("invalid execution lane %d", lane); return ONK_ERR_ARG; }
     Runtime& r = rt();
     std::lock_guard<std::mutex> lk(r.mutex);
-    if ((size_t)lane >= r.lanes.size()) r.lanes.resize(lane + 1);
+    // the table is sized once (onk_init) and never reallocated: callers keep Lane* across further lane_get() calls
+    if (r.lanes.size() < (size_t)ONK_MAX_LANES) r.lanes.resize(ONK_MAX_LANES);
     Lane& L = r.lanes[lane];
     if (!L.created)
     {
@@ -98,6 +99,7 @@ int onk_init(int device)
   ONK_CUDA(cudaGetDeviceProperties(&r.prop, device));
   r.device = device;
   r.sm_count = r.prop.multiProcessorCount;
+  r.lanes.assign(ONK_MAX_LANES, Lane{});        // fixed size: Lane* handed out by lane_get() stay valid
   r.initialised = true;
   return ONK_OK;
 }
@@ -162,7 +164,7 @@ int onk_lane_bind_stream(int lane, void* cuda_stream)
   {
     Runtime& r = rt();
     std::lock_guard<std::mutex> lk(r.mutex);
-    if ((size_t)lane >= r.lanes.size()) r.lanes.resize(lane + 1);
+    if (r.lanes.size() < (size_t)ONK_MAX_LANES) r.lanes.resize(ONK_MAX_LANES);
     Lane& L = r.lanes[lane];
     if (L.created && L.owned) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
     L.stream = (cudaStream_t)cuda_stream;

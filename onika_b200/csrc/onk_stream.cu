@@ -174,22 +174,46 @@ namespace onk
       const uint64_t nb = (prm.bytes[k] - b0 < PACK_CHUNK) ? prm.bytes[k] - b0 : PACK_CHUNK;
       const uint8_t* s = src + prm.src_off[k] + b0;
       uint8_t* d = dst + prm.dst_off[k] + b0;
-      if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0)
+      // 1. bytes up to the first 16-byte boundary of the DESTINATION
+      const unsigned dmis = (unsigned)((uintptr_t)d & 15u);
+      uint64_t head = dmis ? 16u - dmis : 0u;
+      if (head > nb) head = nb;
+      for (uint64_t i = threadIdx.x; i < head; i += THREADS) d[i] = s[i];
+      const uint8_t* s2 = s + head;
+      uint8_t* d2 = d + head;
+      const uint64_t rem = nb - head;
+      const unsigned sh = (unsigned)((uintptr_t)s2 & 15u);     // source misalignment relative to the (now aligned) destination
+      uint64_t done = 0;
+      if (sh == 0)
       {
-        const uint64_t nv = nb / 16;
-        for (uint64_t i = threadIdx.x; i < nv; i += THREADS) ((uint4*)d)[i] = __ldg((const uint4*)s + i);
-        for (uint64_t i = nv * 16 + threadIdx.x; i < nb; i += THREADS) d[i] = s[i];
-      }
-      else if ((((uintptr_t)s | (uintptr_t)d) & 3) == 0)
-      {
-        const uint64_t nv = nb / 4;
-        for (uint64_t i = threadIdx.x; i < nv; i += THREADS) ((uint32_t*)d)[i] = __ldg((const uint32_t*)s + i);
-        for (uint64_t i = nv * 4 + threadIdx.x; i < nb; i += THREADS) d[i] = s[i];
+        const uint64_t nv = rem / 16;
+        for (uint64_t i = threadIdx.x; i < nv; i += THREADS) ((uint4*)d2)[i] = __ldg((const uint4*)s2 + i);
+        done = nv * 16;
       }
       else
       {
-        for (uint64_t i = threadIdx.x; i < nb; i += THREADS) d[i] = s[i];
+        // 2. shifted copy: every 16-byte destination word is cut out of two ALIGNED 16-byte source words (the wire layout
+        //    <1,1,...> puts columns at arbitrary byte offsets).  The last word is left to the byte tail so that no read
+        //    goes past the end of the range.
+        uint64_t nv = rem / 16;
+        if (nv > 0) nv -= 1;
+        const uint4* S = (const uint4*)(s2 - sh);
+        const unsigned q = sh >> 3, r = (sh & 7u) * 8u;
+        for (uint64_t i = threadIdx.x; i < nv; i += THREADS)
+        {
+          const uint4 a = __ldg(S + i), b = __ldg(S + i + 1);
+          unsigned long long w[4] = { (unsigned long long)a.x | ((unsigned long long)a.y << 32), (unsigned long long)a.z | ((unsigned long long)a.w << 32),
+                                      (unsigned long long)b.x | ((unsigned long long)b.y << 32), (unsigned long long)b.z | ((unsigned long long)b.w << 32) };
+          const unsigned long long lo0 = q ? w[1] : w[0], lo1 = q ? w[2] : w[1], lo2 = q ? w[3] : w[2];
+          const unsigned long long o0 = r ? ((lo0 >> r) | (lo1 << (64u - r))) : lo0;
+          const unsigned long long o1 = r ? ((lo1 >> r) | (lo2 << (64u - r))) : lo1;
+          uint4 o; o.x = (unsigned)o0; o.y = (unsigned)(o0 >> 32); o.z = (unsigned)o1; o.w = (unsigned)(o1 >> 32);
+          ((uint4*)d2)[i] = o;
+        }
+        done = nv * 16;
       }
+      // 3. tail bytes
+      for (uint64_t i = done + threadIdx.x; i < rem; i += THREADS) d2[i] = s2[i];
     }
   }
 

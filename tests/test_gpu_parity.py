@@ -621,3 +621,33 @@ print("ok")
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-1500:]
+
+
+@pytest.mark.parametrize("n", [1, 2, 13, 15, 16, 17, 999, 4097, 100_003, 262_145])
+def test_soatl_repack_any_alignment_vs_oracle(ob, orc, n):
+    """soatl::copy between <64,8,...> and the byte-packed <1,1,...> wire layout for sizes that put the wire columns at
+    every byte misalignment; both directions, whole allocations compared byte for byte with the oracle's repack."""
+    import torch
+    from onika_b200 import _capi
+    L = _capi.lib()
+    for fields in ([8, 1, 8, 4, 8, 8], [1, 2, 4, 8, 1, 8, 2], [4, 2, 1, 1, 8]):
+        fb = (C.c_uint32 * len(fields))(*fields)
+        cap_a = orc.update_capacity(n, 0, 8)
+        tot_a, offs_a = orc.layout(64, fields, cap_a)
+        tot_w, _ = orc.layout(1, fields, n)
+        rng = np.random.default_rng(n)
+        a = rng.integers(0, 256, tot_a, dtype=np.uint8)
+        w0 = rng.integers(0, 256, tot_w + 32, dtype=np.uint8)               # guard bytes after the wire buffer
+        ta, tw = dev(a), dev(w0)
+        _capi.check(L.onk_soatl_repack(tw.data_ptr(), 1, n, ta.data_ptr(), 64, cap_a, fb, len(fields), n, 0))
+        ob.lane_sync()
+        want_w = w0.copy()
+        orc.soatl_repack(want_w[:tot_w], 1, n, a, 64, cap_a, fields, n)
+        assert np.array_equal(host(tw), want_w), (n, fields)                # guard bytes untouched
+        b0 = rng.integers(0, 256, tot_a, dtype=np.uint8)
+        tb = dev(b0)
+        _capi.check(L.onk_soatl_repack(tb.data_ptr(), 64, cap_a, tw.data_ptr(), 1, n, fb, len(fields), n, 0))
+        ob.lane_sync()
+        want_b = b0.copy()
+        orc.soatl_repack(want_b, 64, cap_a, want_w[:tot_w], 1, n, fields, n)
+        assert np.array_equal(host(tb), want_b), (n, fields)                # padding between columns untouched

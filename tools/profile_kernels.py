@@ -68,6 +68,19 @@ def main():
     fb.storage.view(torch.float64).uniform_(0.1, 1)
     timed("soatl_dist", lambda: fb.parallel_apply_dist("e", "rx", "ry", "rz", 0.05, 0.06, 0.07), 32 * n)
     fb.clear()
+    # SOATL serialisation: <64,8,e,atype,rx,mid,ry,rz> -> <1,1,...> wire layout and back (tests/soatlserializetest.cpp shape)
+    fields = [("e", "f8"), ("atype", "u1"), ("rx", "f8"), ("mid", "i4"), ("ry", "f8"), ("rz", "f8")]
+    n = (32 << 20) + int(os.environ.get("PACK_ODD", "0"))
+    src = soatl.make_hybrid_field_arrays(64, 8, fields); src.resize(n)
+    src.storage.random_(0, 255)
+    wire = soatl.make_hybrid_field_arrays(1, 1, fields); wire.resize(n)
+    back = soatl.make_hybrid_field_arrays(64, 8, fields); back.resize(n)
+    timed("soatl_pack", lambda: wire.copy_from(src), 2 * 37 * n)
+    timed("soatl_unpack", lambda: back.copy_from(wire), 2 * 37 * n)
+    if not only or "soatl_pack" in only:
+        torch.cuda.synchronize()
+        assert all(torch.equal(back[nm][:n].view(torch.uint8), src[nm][:n].view(torch.uint8)) for nm, _ in fields)
+    src.clear(); wire.clear(); back.clear()
     counts = poisson_counts(128 ** 3)
     cg = cellgrid.CellGrid(counts, 64, 16, (8, 8, 8, 8), 64)
     cg.arena.view(torch.float64).uniform_(-1, 1)
