@@ -63,16 +63,19 @@ namespace onika { namespace parallel {
     __global__ void __launch_bounds__(ONIKA_CU_MAX_THREADS_PER_BLOCK)
     bpf_worksteal_kernel( const unsigned long long n , GPUKernelExecutionScratch* scratch , const ElementListT idx , __grid_constant__ const FuncT func , const ssize_t start )
     {
-      __shared__ unsigned long long item;
-      for(;;)
+      // double-buffered ticket: thread 0 draws the NEXT item while the block works on the current one, so the atomic's
+      // round trip overlaps the functor and one barrier per item suffices (tickets drawn past n are harmless)
+      __shared__ unsigned long long item[2];
+      if( ONIKA_CU_THREAD_IDX == 0 ) item[0] = atomicAdd( & scratch->counters[GPUKernelExecutionScratch::WORKSTEALING_COUNTER] , 1ull );
+      __syncthreads();
+      for(unsigned int k=0;;k^=1u)
       {
-        if( ONIKA_CU_THREAD_IDX == 0 ) item = atomicAdd( & scratch->counters[GPUKernelExecutionScratch::WORKSTEALING_COUNTER] , 1ull );
-        __syncthreads();
-        const unsigned long long i = item;
-        __syncthreads();
+        const unsigned long long i = item[k];
         if( i >= n ) break;
+        if( ONIKA_CU_THREAD_IDX == 0 ) item[k^1u] = atomicAdd( & scratch->counters[GPUKernelExecutionScratch::WORKSTEALING_COUNTER] , 1ull );
         if constexpr ( ! Indexed ) func( start + ssize_t(i) );
         else func( idx[ start + ssize_t(i) ] );
+        __syncthreads();
       }
     }
 
@@ -80,9 +83,17 @@ namespace onika { namespace parallel {
     template<class KernelT>
     inline unsigned int persistent_grid( KernelT kernel , unsigned int block_threads , unsigned long long nitems , int sm_count )
     {
-      int per_sm = 0;
-      ONIKA_CU_CHECK_ERRORS( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm , kernel , int(block_threads) , 0 ) );
-      if( per_sm < 1 ) per_sm = 1;
+      // the occupancy query costs microseconds: remembered per (kernel, block size) and thread
+      static thread_local KernelT s_kernel = nullptr;
+      static thread_local unsigned int s_threads = 0;
+      static thread_local int s_per_sm = 0;
+      if( s_kernel != kernel || s_threads != block_threads )
+      {
+        ONIKA_CU_CHECK_ERRORS( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &s_per_sm , kernel , int(block_threads) , 0 ) );
+        if( s_per_sm < 1 ) s_per_sm = 1;
+        s_kernel = kernel; s_threads = block_threads;
+      }
+      const int per_sm = s_per_sm;
       const unsigned long long cap = (unsigned long long) per_sm * (unsigned long long) sm_count;
       return (unsigned int)( nitems < cap ? nitems : cap );
     }

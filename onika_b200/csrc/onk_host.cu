@@ -15,6 +15,9 @@ namespace onk
   constexpr size_t STAGE_BYTES = 64u << 20;       // per staging buffer
   constexpr int MAX_CHUNK_PARTIALS = MAX_PARTIALS;
 
+  // the staging buffers and the three internal lanes are shared: one host-buffer call at a time
+  static std::mutex g_host_path_mutex;
+
   static int ensure_staging(int nbuf)
   {
     Runtime& r = rt();
@@ -43,6 +46,7 @@ int onk_host_reduce_f64(int op, const double* in_host, uint64_t n, double* out_h
 {
   ONK_REQUIRE(out_host != nullptr && (n == 0 || in_host != nullptr), "onk_host_reduce_f64: null pointer");
   ONK_REQUIRE(op == ONK_OP_MIN || op == ONK_OP_MAX || op == ONK_OP_SUM, "onk_host_reduce_f64: unknown op %d", op);
+  std::lock_guard<std::mutex> guard(g_host_path_mutex);
   Lane *H, *K;
   if (int rc = lane_get(LANE_H2D, &H)) return rc;
   if (int rc = lane_get(LANE_COMPUTE, &K)) return rc;
@@ -75,6 +79,7 @@ int onk_host_reduce_f64(int op, const double* in_host, uint64_t n, double* out_h
 // shared driver of the in-place host updates: y (and optionally x) travel in, y travels back
 static int host_update(double* y_host, const double* x_host, uint64_t n, double a, bool is_axpy)
 {
+  std::lock_guard<std::mutex> guard(g_host_path_mutex);
   Lane *H, *K, *D;
   if (int rc = lane_get(LANE_H2D, &H)) return rc;
   if (int rc = lane_get(LANE_COMPUTE, &K)) return rc;
