@@ -136,6 +136,53 @@ def cpu_reduce_min_baseline(min_seconds: float, steps: int | None = None, warmup
     return gbs[best_kind], best_kind, cores, sample, med, len(ts)
 
 
+def cpu_secondary_baselines(budget_s: float = 2.0) -> dict:
+    """The reference's own OpenMP path (oracle/_ref; oracle port when _ref is absent) on bounded samples of the secondary
+    configs, median of a few passes each: context for the `kernels` object, same run, same box."""
+    import numpy as np
+    import oracle
+    orc = oracle.orc
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    orc.set_num_threads(ncpu)
+    use_ref = oracle.ref.available()
+    out = {"cores": ncpu, "impl": "reference (oracle/_ref)" if use_ref else "port (oracle/oracle.c)"}
+
+    def med(fn, nbytes):
+        fn()
+        ts = []
+        t_end = time.perf_counter() + budget_s
+        while time.perf_counter() < t_end and len(ts) < 15:
+            ts.append(fn())
+        ts.sort()
+        return round(nbytes / ts[len(ts) // 2] / 1e9, 1)
+
+    def wall(f):
+        t0 = time.perf_counter(); f(); return time.perf_counter() - t0
+
+    n = 10_000_000
+    x = np.empty(n); y = np.empty(n)
+    orc.fill_lcg(x, 1, -1.0, 1.0); orc.fill_lcg(y, 2, -1.0, 1.0)
+    out["C1_axpy_10M_GBps"] = med((lambda: oracle.ref.axpy(y, x, 0.5)) if use_ref else (lambda: wall(lambda: orc.axpy(y, x, 0.5))), 24 * n)
+    rows = cols = 4096
+    a = np.empty((rows, cols)); orc.fill_lcg(a.reshape(-1), 3)
+    out["C5_value_add_4096x4096_GBps"] = med((lambda: oracle.ref.value_add(a, 1.1)) if use_ref else (lambda: wall(lambda: orc.value_add(a, 1.1))), 16 * rows * cols)
+    if use_ref:
+        n = 8 << 20
+        colsv = [np.empty(n) for _ in range(8)]
+        for k, cv in enumerate(colsv):
+            orc.fill_lcg(cv, 20 + k, 0.0, 1.0)
+        out["C3_soatl_rmw_8x8Mi_GBps"] = med(lambda: oracle.ref.soatl_rmw8(colsv, 1.0000001, [0.125 * (k + 1) for k in range(8)], 64), 128 * n)
+        from tests._inputs import poisson_counts
+        counts = poisson_counts(64 ** 3)
+        e = np.empty(int(counts.sum())); orc.fill_lcg(e, 40, -1.0, 1.0)
+        alg = 8 * e.size + 24 * counts.size
+        out["C4_cell_sum_64^3_GBps"] = med(lambda: oracle.ref.cell_sum(counts, e)[3], alg)
+    return out
+
+
 def run_reference_arm(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -402,6 +449,8 @@ def run_ours(args) -> int:
         try:
             gbs, kind, cores, sample, _, _ = cpu_reduce_min_baseline(args.cpu_seconds)
             cpu_baseline = {"value": round(gbs, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+            if kernels is not None and "error" not in kernels:
+                kernels["cpu_reference_same_box"] = cpu_secondary_baselines()
         except Exception as ex:  # pragma: no cover
             cpu_baseline = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
 

@@ -6,6 +6,7 @@
 #include <onika/parallel/block_parallel_for.h>
 #include <onika/parallel/parallel_for.h>
 #include <onika/parallel/memset.h>
+#include <onika/parallel/reduction.h>
 #include <onika/parallel/parallel_execution_context_allocator.h>
 #include <onika/parallel/parallel_execution_queue.h>
 #include <onika/parallel/parallel_execution_operators.h>
@@ -427,6 +428,34 @@ static int scenario_soatl(Out& out, size_t n)
   return 0;
 }
 
+// reduction helpers queued on lanes together with the kernels that produce their input
+static int scenario_reduce_helpers(Out& out, size_t rows, size_t cols)
+{
+  extras::Array2D a1, a2;
+  a1.resize(rows,cols); a2.resize(rows,cols);
+  fill(a1.m_data,8,-1.0,1.0); fill(a2.m_data,9,-1.0,1.0);
+  extras::BlockParallelValueAddFunctor<true> k1 = { a1 , 1.1 } , k2 = { a2 , 1.3 };
+  double r[6] = { 0,0,0,0,0,0 };
+  auto & pq = ParallelExecutionQueue::default_queue();
+  pq << set_lane(0) << block_parallel_for( rows , k1 , parallel_execution_context("a1","add") )
+                    << parallel_reduce_min( a1.data() , rows*cols , &r[0] , parallel_execution_context("a1","min") )
+                    << parallel_reduce_max( a1.data() , rows*cols , &r[1] , parallel_execution_context("a1","max") )
+                    << parallel_reduce_sum( a1.data() , rows*cols , &r[2] , parallel_execution_context("a1","sum") )
+     << set_lane(1) << block_parallel_for( rows , k2 , parallel_execution_context("a2","add") )
+                    << parallel_reduce_min( a2.data() , rows*cols , &r[3] , parallel_execution_context("a2","min") )
+                    << parallel_reduce_max( a2.data() , rows*cols , &r[4] , parallel_execution_context("a2","max") )
+                    << parallel_reduce_sum( a2.data() , rows*cols , &r[5] , parallel_execution_context("a2","sum") )
+     << flush << synchronize;
+  out.doubles( r , 6 );
+  // synchronous form on an empty range: identities
+  double e[3] = { 1.0 , 1.0 , 1.0 };
+  parallel_reduce_min( a1.data() , 0 , &e[0] , parallel_execution_context("empty","min") );
+  parallel_reduce_max( a1.data() , 0 , &e[1] , parallel_execution_context("empty","max") );
+  parallel_reduce_sum( a1.data() , 0 , &e[2] , parallel_execution_context("empty","sum") );
+  out.doubles( e , 3 );
+  return 0;
+}
+
 // device-timed throughput of the generic functor path and of the typed fast paths, through the public API
 static int scenario_perf(Out&, size_t n)
 {
@@ -486,6 +515,7 @@ int main(int argc, char* argv[])
   else if( sc == "soatl" ) rc = scenario_soatl( out , arg(3,53) );
   else if( sc == "perf" ) rc = scenario_perf( out , arg(3,1<<27) );
   else if( sc == "helpers" ) rc = scenario_helpers( out , arg(3,333) );
+  else if( sc == "reduce_helpers" ) rc = scenario_reduce_helpers( out , arg(3,513) , arg(4,1027) );
   ParallelExecutionQueue::default_queue() << flush << synchronize;
   return rc;
 }

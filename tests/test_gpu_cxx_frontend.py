@@ -116,6 +116,25 @@ def test_element_list_space_prolog_epilog(prog, tmp_path):
     assert r[1000] == 1.0 and r[1001] == 1.0
 
 
+@pytest.mark.parametrize("which", ["typed", "generic"])
+def test_parallel_reduce_helpers_on_lanes(tmp_path, orc, which):
+    """onika/parallel/reduction.h: reductions queued behind the kernels producing their input, two lanes; typed kernel
+    (onk_reduce_f64) and, with the fast paths compiled out, the generic one-block functor body."""
+    import sys
+    from onika_b200 import cxx
+    exe = cxx.program_path("frontend_test" if which == "typed" else "frontend_test_generic")
+    if not os.path.exists(exe):
+        cxx.build_all()
+    rows, cols = 513, 1027
+    r = run(exe, tmp_path, "reduce_helpers", rows, cols).view(np.float64)
+    a1 = lcg_uniform(rows * cols, 8, -1.0, 1.0) + 1.1
+    a2 = lcg_uniform(rows * cols, 9, -1.0, 1.0) + 1.3
+    for k, a in ((0, a1), (3, a2)):
+        assert r[k] == orc.reduce_min(a) and r[k + 1] == orc.reduce_max(a)
+        assert abs(r[k + 2] - orc.reduce_sum_ld(a)) <= SUM_RTOL * np.abs(a).sum()
+    assert r[6] == sys.float_info.max and r[7] == -sys.float_info.max and r[8] == 0.0
+
+
 def test_cuda_helper_headers_memcpy_memmove_spans_math(prog, tmp_path):
     rows, rb = 333, 1000
     raw = run(prog, tmp_path, "helpers", rows)
