@@ -71,3 +71,66 @@ def test_fused_reduce_exchange_two_gpus(n, orc):
             assert abs(res[("sum", rep)] - orc.reduce_sum_ld(d)) <= 1e-12 * np.abs(d).sum()
         assert nccl == orc.reduce_min(d)
     assert got[0][1] == got[1][1]             # identical bits on both ranks, every repetition
+
+
+def _worker_c5(rank, world, port, rows, cols, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import onika_b200 as ob
+    from onika_b200 import distributed as D, parallel as P, _capi
+    from tests._inputs import lcg_uniform
+    ob.init(rank)
+    a1 = lcg_uniform(rows * cols, 8, -1, 1).reshape(rows, cols)
+    a2 = lcg_uniform(rows * cols, 9, -1, 1).reshape(rows, cols)
+    b, e = D.shard_range(rows, rank, world)                  # contiguous row shard of both arrays
+    t1, t2 = torch.from_numpy(a1[b:e].copy()).cuda(), torch.from_numpy(a2[b:e].copy()).cuda()
+    torch.cuda.synchronize()
+    x1, x2 = D.PeerExchange(), D.PeerExchange()              # one exchange per lane: calls on one exchange are ordered by its lane
+    q_ = P.ParallelExecutionQueue()
+    q_ << P.set_lane(1) << P.block_parallel_for(e - b, P.BlockParallelValueAddFunctor(t1, 1.1)) \
+       << P.set_lane(2) << P.block_parallel_for(e - b, P.BlockParallelValueAddFunctor(t2, 1.3)) \
+       << P.set_lane(1) << P.block_parallel_for(e - b, P.BlockParallelValueAddFunctor(t1, 1.2)) \
+       << P.set_lane(2) << P.block_parallel_for(e - b, P.BlockParallelValueAddFunctor(t2, 1.4)) << P.flush
+    r = [x1.reduce(_capi.OP_MIN, t1, lane=1), x1.reduce(_capi.OP_SUM, t1, lane=1),
+         x2.reduce(_capi.OP_MIN, t2, lane=2), x2.reduce(_capi.OP_SUM, t2, lane=2)]
+    q_ << P.synchronize
+    ob.lane_sync()
+    q.put((rank, b, e, t1.cpu().numpy(), t2.cpu().numpy(), [float(v.item()) for v in r]))
+    dist.barrier()
+    x1.close(); x2.close()
+    dist.destroy_process_group()
+
+
+def test_config_c5_lane_sequence_sharded_over_two_gpus(orc):
+    """BASELINE config C5 (scaled down): kernel1 -> kernel2 per array on lanes 1/2, rows sharded over 2 GPUs, min and sum
+    of each array combined across the GPUs inside the reduction kernels."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from tests._inputs import lcg_uniform
+    world, rows, cols = 2, 1025, 513
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_c5, args=(r, world, port, rows, cols, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted((q.get(timeout=180) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    a1 = lcg_uniform(rows * cols, 8, -1, 1).reshape(rows, cols)
+    a2 = lcg_uniform(rows * cols, 9, -1, 1).reshape(rows, cols)
+    orc.lane_sequence(a1, a2, 1.1, 1.2, 1.3, 1.4)
+    assert np.array_equal(np.concatenate([g[3] for g in got]), a1) and np.array_equal(np.concatenate([g[4] for g in got]), a2)
+    for g in got:
+        m1, s1, m2, s2 = g[5]
+        assert m1 == a1.min() and m2 == a2.min()
+        assert abs(s1 - orc.reduce_sum_ld(a1.ravel())) <= 1e-12 * np.abs(a1).sum()
+        assert abs(s2 - orc.reduce_sum_ld(a2.ravel())) <= 1e-12 * np.abs(a2).sum()
+    assert got[0][5] == got[1][5]
