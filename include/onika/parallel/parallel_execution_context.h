@@ -115,6 +115,10 @@ namespace onika { namespace parallel {
     double m_total_gpu_execution_time = 0.0;
     bool m_reset_counters = false;
     bool m_scheduled_on_gpu = false;
+    uint64_t m_wait_lanes[4] = { 0 , 0 , 0 , 0 };   // lanes (bit set) whose queued work this operation must follow (lane DAG edges)
+
+    inline void add_lane_dependency(int l) { if( l >= 0 && l < 256 ) m_wait_lanes[l>>6] |= ( uint64_t(1) << (l&63) ); }
+    inline bool depends_on_lane(int l) const { return l >= 0 && l < 256 && ( ( m_wait_lanes[l>>6] >> (l&63) ) & 1 ) != 0; }
 
     inline void initialize_stream_events()
     {
@@ -135,6 +139,7 @@ namespace onika { namespace parallel {
       m_grid_size = onikaDim3_t{ 0, 0, 0 };
       m_omp_sched = OMP_SCHED_DYNAMIC;
       m_reset_counters = false; m_scheduled_on_gpu = false;
+      for(auto& w : m_wait_lanes) w = 0;
       m_total_cpu_execution_time = 0.0; m_total_gpu_execution_time = 0.0;
       m_host_scratch.functor_data_size = 0;
     }

@@ -97,14 +97,26 @@ namespace onika { namespace parallel {
       m_queue_list = pec_list_append( m_queue_list , pec );
     }
 
-    // lane assignment of operations queued under any_lane(): those that cannot conflict by declaration (single tasks,
-    // or no declared data access) are spread round robin over the auto-lane cycle; operations that declare data
-    // accesses keep an undefined lane and are serialised on lane 0 by schedule() (safe default, as in the reference
-    // where conflict-driven splitting is not implemented: src/parallel/parallel_execution_queue.cpp:171-207)
-    inline void pre_process_queue( ParallelExecutionContext* head )
+    // Lane assignment of operations queued under any_lane() (their lane is UNDEFINED_EXECUTION_LANE).
+    //  * single tasks and operations without declared data access: round robin over the auto-lane cycle, as the reference
+    //    does (src/parallel/parallel_execution_queue.cpp:163-183);
+    //  * operations WITH declared accesses: the reference detects potential conflicts and prints them but leaves placement
+    //    unfinished (.cpp:185-207), i.e. they end up serialised.  Here the declarations drive a lane DAG: an operation
+    //    goes to the lane of the latest earlier operation it conflicts with (stream order gives the dependency for free),
+    //    gets a cross-lane edge (m_wait_lanes -> onk_lane_wait_lane at schedule time) for every other lane holding a
+    //    conflicting predecessor, and takes the least loaded lane of the cycle when it conflicts with nothing.
+    //    `in_flight` = operations already scheduled and not yet waited for; they count as predecessors too.
+    //  The outcome equals serial FIFO execution whenever the declared accesses are truthful.
+    inline void pre_process_queue( ParallelExecutionContext* head , ParallelExecutionContext* in_flight = nullptr )
     {
-      int cycle = 0;
       const int ncycle = ( m_auto_lane_cycle > 0 ) ? m_auto_lane_cycle : 1;
+      int lane_load[ONIKA_PARALLEL_QUEUE_MAX_LANES];
+      for(int l=0;l<int(ONIKA_PARALLEL_QUEUE_MAX_LANES);l++) lane_load[l] = 0;
+      auto count_load = [&](const ParallelExecutionContext* p) { if( p->m_lane >= 0 && p->m_lane < int(ONIKA_PARALLEL_QUEUE_MAX_LANES) ) ++ lane_load[p->m_lane]; };
+      for(auto* p=in_flight; p!=nullptr; p=p->m_next) count_load(p);
+
+      // phase 1 : operations that cannot be reasoned about keep the reference's placement
+      int cycle = 0;
       for(auto* pec=head; pec!=nullptr; pec=pec->m_next)
       {
         if( pec->m_lane == DEFAULT_EXECUTION_LANE ) pec->m_lane = 0;
@@ -113,6 +125,32 @@ namespace onika { namespace parallel {
           pec->m_lane = cycle;
           cycle = ( cycle + 1 ) % ncycle;
         }
+        if( pec->m_lane >= 0 ) count_load(pec);
+      }
+
+      // phase 2 : operations with declared accesses, in FIFO order
+      for(auto* pec=head; pec!=nullptr; pec=pec->m_next)
+      {
+        if( pec->m_lane != UNDEFINED_EXECUTION_LANE ) continue;
+        int last_conflict_lane = -1;
+        auto visit = [&](const ParallelExecutionContext* q)
+        {
+          if( q->m_lane < 0 || q->m_data_access.empty() ) return;
+          if( ! concurrent_data_access( q->m_data_access , pec->m_data_access ) ) return;
+          pec->add_lane_dependency( q->m_lane );
+          last_conflict_lane = q->m_lane;
+        };
+        for(auto* q=in_flight; q!=nullptr; q=q->m_next) visit(q);
+        for(auto* q=head; q!=nullptr && q!=pec; q=q->m_next) visit(q);
+        if( last_conflict_lane >= 0 ) pec->m_lane = last_conflict_lane;
+        else
+        {
+          int best = 0;
+          for(int l=1;l<ncycle;l++) if( lane_load[l] < lane_load[best] ) best = l;
+          pec->m_lane = best;
+        }
+        pec->m_wait_lanes[pec->m_lane>>6] &= ~( uint64_t(1) << (pec->m_lane&63) );   // same lane: ordered by the stream itself
+        count_load(pec);
       }
     }
   };
@@ -148,7 +186,7 @@ namespace onika { namespace parallel {
       // operations pushed under any_lane() carry an undefined lane: give them lanes before scheduling
       bool any_undefined = false;
       for(auto* p=m_queue_list; p!=nullptr; p=p->m_next) any_undefined = any_undefined || ( p->m_lane == UNDEFINED_EXECUTION_LANE );
-      if( any_undefined ) pre_process_queue( m_queue_list );
+      if( any_undefined ) pre_process_queue( m_queue_list , m_exec_list );
       ParallelExecutionContext *keep = nullptr, *scheduled = nullptr;
       auto* p = m_queue_list;
       while( p != nullptr )
@@ -184,6 +222,14 @@ namespace onika { namespace parallel {
       std::lock_guard lk_stream( exec_stream->m_mutex );
       pec->m_stream = exec_stream;
       const auto & func = get_block_parallel_functor( pec );
+
+      // lane DAG edges computed by pre_process_queue: operations are submitted in FIFO order, so everything this one
+      // depends on is already in its lane's stream -- one event edge per lane
+      for(int w=0;w<4;w++) for(uint64_t bits=pec->m_wait_lanes[w]; bits!=0; bits&=bits-1)
+      {
+        const int other = w*64 + __builtin_ctzll(bits);
+        if( other != lane ) ONIKA_B200_CHECK( onk_lane_wait_lane( lane , other ) );
+      }
 
       if( pec->m_execution_target == ParallelExecutionContext::EXECUTION_TARGET_CUDA )
       {

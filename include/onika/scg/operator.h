@@ -1,8 +1,10 @@
 // onika/scg/operator.h -- BOUNDARY SHIM of the operator (plugin) API, just enough for plugins whose execute() drives the
 // data-parallel hot path: OperatorNode with parallel_execution_context() / parallel_execution_queue(), typed slots with
 // default values (ADD_SLOT), the factory registry and run() = flush+synchronize, execute(), flush+synchronize.
-// The reference's graph machinery (YAML, batch control flow, slot connection, profiling, MPI) is out of scope
-// (SURVEY.md 2, rows 8-10); this shim only keeps plugin SOURCES compiling unchanged and runnable one operator at a time.
+// The reference's graph machinery (full YAML, batch control flow, profiling, MPI) is out of scope;
+// this shim keeps plugin SOURCES compiling unchanged and runnable, alone or as a flat batch (tests/cxx/run_operator.cu
+// reads the `name: { task_group, body: [ - op: {slot: value} ] }` subset of .msp files, connects same-named slots of the
+// same type in body order and lets a task_group batch share one queue among its operators).
 #pragma once
 #include <cassert>
 #include <functional>
@@ -33,7 +35,7 @@ namespace onika { namespace scg {
     static inline constexpr SlotDirection INPUT = ::onika::scg::INPUT;
     static inline constexpr SlotDirection OUTPUT = ::onika::scg::OUTPUT;
     static inline constexpr SlotDirection INPUT_OUTPUT = ::onika::scg::INPUT_OUTPUT;
-    static inline constexpr SlotDirection PRIVATE = ::onika::scg::PRIVATE;
+    struct PRIVATE_t {};   static inline constexpr PRIVATE_t PRIVATE = {};      // ADD_SLOT(T,name,PRIVATE): never connected to other operators
 
     virtual ~OperatorNode() { m_queue.schedule_all(); m_queue.wait(); }
     virtual void execute() = 0;
@@ -52,8 +54,14 @@ namespace onika { namespace scg {
       return m_peca.create( tag != nullptr ? tag : m_name.c_str() , sub_tag != nullptr ? sub_tag : "" , & parallel_execution_queue()
                           , m_gpu_enabled ? global_cuda_ctx() : nullptr );
     }
+    // operators below a task_group ancestor share that ancestor's queue (src/scg/operator.cpp:563-587)
+    inline void set_parent(OperatorNode* p) { m_parent = p; }
+    inline OperatorNode* parent() const { return m_parent; }
+    inline void set_task_group(bool b) { m_task_group = b; }
+    inline bool task_group() const { return m_task_group; }
     inline parallel::ParallelExecutionQueue& parallel_execution_queue()
     {
+      for(auto* p = m_parent; p != nullptr; p = p->m_parent) if( p->m_task_group ) return p->parallel_execution_queue();
       if( m_queue.m_stream_pool.m_func == nullptr )
       {
         m_stream_allocator.m_cuda_ctx = global_cuda_ctx();
@@ -79,6 +87,8 @@ namespace onika { namespace scg {
     parallel::ParallelExecutionStreamAutoAllocator m_stream_allocator;
     parallel::ParallelExecutionQueue m_queue;
     bool m_gpu_enabled = true;
+    bool m_task_group = false;
+    OperatorNode* m_parent = nullptr;
   };
 
 } }

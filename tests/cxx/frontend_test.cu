@@ -24,6 +24,7 @@
 #include "declare_fields.h"
 
 #include <cfloat>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -286,6 +287,93 @@ static int scenario_lanes(Out& out, const std::string& mode, size_t rows, size_t
   return pq.empty() ? 0 : 3;
 }
 
+// automatic lanes from declared data accesses (plugins/onikaParallelTutorial/automatic_concurrent_parallel.cu pattern,
+// extended with an operation that depends on two lanes): results must equal serial FIFO execution
+struct RepeatedAddFunctor   // a[i][j] += v, `iters` times, one rounding per add: slow on purpose, exact by construction
+{
+  extras::Array2DReference a; double v; int iters;
+  ONIKA_HOST_DEVICE_FUNC inline void operator () ( size_t i ) const
+  {
+    ONIKA_CU_BLOCK_SIMD_FOR(size_t, j, 0, a.columns()) { double x = a[i][j]; for(int k=0;k<iters;k++) x = x + v; a[i][j] = x; }
+  }
+};
+struct AddArrayFunctor      // b[i][j] += a[i][j]
+{
+  extras::Array2DReference a; extras::Array2DReference b;
+  ONIKA_HOST_DEVICE_FUNC inline void operator () ( size_t i ) const
+  {
+    ONIKA_CU_BLOCK_SIMD_FOR(size_t, j, 0, a.columns()) b[i][j] += a[i][j];
+  }
+};
+namespace onika { namespace parallel {
+  template<> struct BlockParallelForFunctorTraits<RepeatedAddFunctor> { static inline constexpr bool CudaCompatible = true; };
+  template<> struct BlockParallelForFunctorTraits<AddArrayFunctor> { static inline constexpr bool CudaCompatible = true; };
+} }
+
+static int scenario_autolanes(Out& out, size_t rows, size_t cols, int iters)
+{
+  extras::Array2D A, B, C;
+  A.resize(rows,cols); B.resize(rows,cols); C.resize(rows,cols);
+  fill(A.m_data,8,1e-3,1.0); fill(B.m_data,9,1e-3,1.0); fill(C.m_data,10,1e-3,1.0);
+  const auto a_rw = local_access( A.m_data.data() , 2 , AccessStencilElement::RW , "a_rw" );
+  const auto a_ro = local_access( A.m_data.data() , 2 , AccessStencilElement::RO , "a_ro" );
+  const auto b_rw = local_access( B.m_data.data() , 2 , AccessStencilElement::RW , "b_rw" );
+  const auto c_rw = local_access( C.m_data.data() , 2 , AccessStencilElement::RW , "c_rw" );
+  ParallelExecutionContext* pec[6] = { parallel_execution_context("A","add1") , parallel_execution_context("B","slow") , parallel_execution_context("A","add2")
+                                     , parallel_execution_context("B","+=A") , parallel_execution_context("A","add3") , parallel_execution_context("C","add") };
+  auto & pq = ParallelExecutionQueue::default_queue();
+  pq << any_lane(4)
+     << a_rw << block_parallel_for( rows , extras::BlockParallelValueAddFunctor<true>{ A , 1.1 } , pec[0] )
+     << b_rw << block_parallel_for( rows , RepeatedAddFunctor{ B , 1.3 , iters } , pec[1] )              // long: op 3 must wait for it across lanes
+     << a_rw << block_parallel_for( rows , extras::BlockParallelValueAddFunctor<true>{ A , 1.2 } , pec[2] )
+     << a_ro << b_rw << block_parallel_for( rows , AddArrayFunctor{ A , B } , pec[3] )                   // reads A (lane of 0,2), writes B (lane of 1)
+     << a_rw << block_parallel_for( rows , extras::BlockParallelValueAddFunctor<true>{ A , 1.4 } , pec[4] ) // write-after-read on A
+     << c_rw << block_parallel_for( rows , RepeatedAddFunctor{ C , 0.7 , 3 } , pec[5] );                  // independent of everything
+  pq << flush;
+  double lanes[6], waits[6];
+  for(int k=0;k<6;k++)
+  {
+    lanes[k] = pec[k]->m_lane;
+    int nw = 0; for(int l=0;l<256;l++) if( pec[k]->depends_on_lane(l) ) ++nw;
+    waits[k] = nw;
+  }
+  pq << synchronize;
+  out.doubles( A.data() , rows*cols ); out.doubles( B.data() , rows*cols ); out.doubles( C.data() , rows*cols );
+  out.doubles( lanes , 6 ); out.doubles( waits , 6 );
+  return pq.empty() ? 0 : 3;
+}
+
+// what the lane DAG buys: the tutorial pattern (2 arrays x 2 kernels, few blocks each) serialised on one lane, on two
+// explicit lanes, and under any_lane() with declared accesses.  Prints wall milliseconds of flush..synchronize.
+static int scenario_autolanes_perf(Out& out, size_t rows, size_t cols, int iters)
+{
+  extras::Array2D A, B;
+  A.resize(rows,cols); B.resize(rows,cols);
+  fill(A.m_data,8,1e-3,1.0); fill(B.m_data,9,1e-3,1.0);
+  const auto a_rw = local_access( A.m_data.data() , 2 , AccessStencilElement::RW , "a_rw" );
+  const auto b_rw = local_access( B.m_data.data() , 2 , AccessStencilElement::RW , "b_rw" );
+  auto & pq = ParallelExecutionQueue::default_queue();
+  double ms[3] = { 0 , 0 , 0 };
+  for(int rep=0; rep<3; rep++) for(int mode=0; mode<3; mode++)
+  {
+    auto a1 = block_parallel_for( rows , RepeatedAddFunctor{ A , 1.1 , iters } , parallel_execution_context("A","k1") );
+    auto a2 = block_parallel_for( rows , RepeatedAddFunctor{ A , 1.2 , iters } , parallel_execution_context("A","k2") );
+    auto b1 = block_parallel_for( rows , RepeatedAddFunctor{ B , 1.3 , iters } , parallel_execution_context("B","k1") );
+    auto b2 = block_parallel_for( rows , RepeatedAddFunctor{ B , 1.4 , iters } , parallel_execution_context("B","k2") );
+    if( mode == 0 )      pq << set_lane(0) << std::move(a1) << std::move(a2) << std::move(b1) << std::move(b2);
+    else if( mode == 1 ) pq << set_lane(0) << std::move(a1) << set_lane(1) << std::move(b1) << set_lane(0) << std::move(a2) << set_lane(1) << std::move(b2);
+    else                 pq << any_lane() << a_rw << std::move(a1) << a_rw << std::move(a2) << b_rw << std::move(b1) << b_rw << std::move(b2);
+    const auto t0 = std::chrono::steady_clock::now();
+    pq << flush << synchronize;
+    const double t = std::chrono::duration<double,std::milli>( std::chrono::steady_clock::now() - t0 ).count();
+    if( rep == 0 || t < ms[mode] ) ms[mode] = t;      // best of 3 (first round also warms up the managed arrays)
+  }
+  std::printf("autolanes_perf rows=%zu cols=%zu iters=%d : one_lane %.3f ms , explicit_lanes %.3f ms , any_lane+accesses %.3f ms\n", rows, cols, iters, ms[0], ms[1], ms[2]);
+  out.doubles( ms , 3 );
+  out.doubles( A.data() , rows*cols ); out.doubles( B.data() , rows*cols );
+  return pq.empty() ? 0 : 3;
+}
+
 static int scenario_grid3d(Out& out)
 {
   {
@@ -508,6 +596,8 @@ int main(int argc, char* argv[])
   if( sc == "axpy" ) rc = scenario_axpy( out , arg(3,100003) );
   else if( sc == "value_add" ) rc = scenario_value_add( out , arg(3,257) , arg(4,129) );
   else if( sc == "lanes" ) rc = scenario_lanes( out , argc>3 ? argv[3] : "hybrid-lane" , arg(4,1024) , arg(5,1024) , arg(6,1) != 0 );
+  else if( sc == "autolanes" ) rc = scenario_autolanes( out , arg(3,64) , arg(4,4096) , int(arg(5,2000)) );
+  else if( sc == "autolanes_perf" ) rc = scenario_autolanes_perf( out , arg(3,4) , arg(4,8192) , int(arg(5,20000)) );
   else if( sc == "grid3d" ) rc = scenario_grid3d( out );
   else if( sc == "reduce" ) rc = scenario_reduce( out , arg(3,777) , arg(4,1001) );
   else if( sc == "cells" ) rc = scenario_cells( out , arg(3,4096) );

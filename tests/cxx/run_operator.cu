@@ -1,26 +1,214 @@
-// tests/cxx/run_operator.cu -- minimal host for operator plugins: instantiates a registered operator by name, sets slot
-// values given as name=value, runs it once (run() = sync, execute(), sync) and dumps any Array2D slot to a file.
+// tests/cxx/run_operator.cu -- minimal host for operator plugins.
+//   run_operator <operator> [slot=value ...] [fill:<array2d slot>=<rows>x<cols>] [dump:<array2d slot>=<file>]
+//       instantiates a registered operator by name, sets slot values, runs it once (run() = sync, execute(), sync)
+//   run_operator --msp <file.msp> [batch name] [dump:<slot>=<file> ...]
+//       reads the flat-batch subset of the reference's .msp (YAML) files, e.g. data/exemples/concurrent_block_parallel.msp:
+//           <batch>:
+//             name: <string>            (optional)
+//             task_group: true|false    (optional: operators of the body share one parallel execution queue)
+//             body:
+//               - <operator>: { <slot>: <value> , ... }
+//               - <operator>
+//       operators run in body order; a consuming slot without a value in the file aliases the latest earlier producing
+//       slot of the same name (INPUT_OUTPUT / OUTPUT), which is how `my_array` travels from one operator to the next
 // Linked together with UNMODIFIED plugin sources (e.g. the reference's plugins/onikaParallelTutorial/*.cu compiled from
 // where they lie) it shows that plugin code runs on this runtime unchanged.
 #include <onika/scg/operator.h>
 #include <onika/extras/array2d.h>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <string>
 
 using namespace onika;
 using namespace onika::scg;
 
+namespace
+{
+  using SlotValues = std::vector< std::pair<std::string,std::string> >;
+  struct BodyItem { std::string op; SlotValues values; };
+  struct BatchSpec { std::string key, name; bool task_group = false; std::vector<BodyItem> body; };
+
+  std::string trim(std::string s)
+  {
+    const char* ws = " \t\r\n";
+    const auto b = s.find_first_not_of(ws);
+    if( b == std::string::npos ) return {};
+    s = s.substr( b , s.find_last_not_of(ws) - b + 1 );
+    if( s.size() >= 2 && ( s.front() == '"' || s.front() == '\'' ) && s.back() == s.front() ) s = s.substr(1,s.size()-2);
+    return s;
+  }
+
+  // "{ a: 1 , b: x }" -> [(a,1),(b,x)]
+  bool parse_flow_map(const std::string& text, SlotValues& out)
+  {
+    const auto lb = text.find('{'), rb = text.rfind('}');
+    if( lb == std::string::npos || rb == std::string::npos || rb < lb ) return false;
+    std::string inner = text.substr(lb+1,rb-lb-1);
+    size_t pos = 0;
+    while( pos <= inner.size() )
+    {
+      const auto comma = inner.find(',',pos);
+      const std::string kv = inner.substr( pos , comma == std::string::npos ? std::string::npos : comma-pos );
+      const auto colon = kv.find(':');
+      if( colon != std::string::npos ) out.push_back( { trim(kv.substr(0,colon)) , trim(kv.substr(colon+1)) } );
+      else if( ! trim(kv).empty() ) return false;
+      if( comma == std::string::npos ) break;
+      pos = comma + 1;
+    }
+    return true;
+  }
+
+  bool parse_msp(const std::string& path, std::vector<BatchSpec>& batches)
+  {
+    std::ifstream in(path);
+    if( ! in ) { std::fprintf(stderr,"cannot open %s\n",path.c_str()); return false; }
+    std::string line;
+    bool in_body = false;
+    int lineno = 0;
+    while( std::getline(in,line) )
+    {
+      ++lineno;
+      const auto hash = line.find('#');
+      if( hash != std::string::npos ) line = line.substr(0,hash);
+      if( trim(line).empty() ) continue;
+      const size_t indent = line.find_first_not_of(' ');
+      const std::string t = trim(line);
+      if( indent == 0 )
+      {
+        if( t.back() != ':' ) { std::fprintf(stderr,"%s:%d: only `<batch>:` definitions are supported at top level\n",path.c_str(),lineno); return false; }
+        batches.push_back( BatchSpec{} ); batches.back().key = batches.back().name = trim(t.substr(0,t.size()-1));
+        in_body = false;
+        continue;
+      }
+      if( batches.empty() ) { std::fprintf(stderr,"%s:%d: value outside of a batch\n",path.c_str(),lineno); return false; }
+      auto& b = batches.back();
+      if( t[0] == '-' )
+      {
+        if( ! in_body ) { std::fprintf(stderr,"%s:%d: list item outside of body\n",path.c_str(),lineno); return false; }
+        const std::string item = trim(t.substr(1));
+        BodyItem bi;
+        const auto colon = item.find(':');
+        bi.op = trim( item.substr(0,colon) );
+        if( colon != std::string::npos && ! trim(item.substr(colon+1)).empty() && ! parse_flow_map( item.substr(colon+1) , bi.values ) )
+        { std::fprintf(stderr,"%s:%d: expected `- op: { slot: value , ... }`\n",path.c_str(),lineno); return false; }
+        b.body.push_back( bi );
+        continue;
+      }
+      const auto colon = t.find(':');
+      if( colon == std::string::npos ) { std::fprintf(stderr,"%s:%d: expected key: value\n",path.c_str(),lineno); return false; }
+      const std::string key = trim(t.substr(0,colon)), val = trim(t.substr(colon+1));
+      in_body = false;
+      if( key == "name" ) b.name = val;
+      else if( key == "task_group" ) b.task_group = ( val == "true" );
+      else if( key == "body" ) in_body = true;
+      else { std::fprintf(stderr,"%s:%d: unsupported batch attribute '%s'\n",path.c_str(),lineno,key.c_str()); return false; }
+    }
+    return true;
+  }
+
+  // a flat batch: runs its operators in order; with task_group they all enqueue into this node's queue
+  class FlatBatch : public OperatorNode
+  {
+  public:
+    std::vector< std::shared_ptr<OperatorNode> > m_ops;
+    void execute() override final { for(auto& op : m_ops) op->run(); }
+  };
+
+  void fill_array(extras::Array2D* arr, size_t r, size_t c)
+  {
+    arr->resize(r,c);
+    for(size_t k=0;k<r*c;k++)
+    { // tests/_inputs.py:lcg_uniform(seed 8, [1e-3,1))
+      uint64_t h = ( k * 2654435761ull + 8ull * 40503ull + 12345ull ) & 0xFFFFFFFFull;
+      h = ( ( h ^ ( h >> 15 ) ) * 2246822519ull ) & 0xFFFFFFFFull; h = ( h ^ ( h >> 13 ) ) & 0xFFFFFFFFull;
+      arr->m_data[k] = 1e-3 + ( 1.0 - 1e-3 ) * ( double(h) / 4294967296.0 );
+    }
+  }
+
+  bool dump_array(OperatorSlotBase* s, const std::string& file)
+  {
+    if( s == nullptr || s->value_type() != typeid(extras::Array2D) ) return false;
+    auto* arr = static_cast<extras::Array2D*>( s->value_address() );
+    FILE* f = std::fopen( file.c_str() , "wb" );
+    if( f == nullptr ) return false;
+    const uint64_t hdr[2] = { arr->rows() , arr->columns() };
+    std::fwrite( hdr , 8 , 2 , f );
+    std::fwrite( arr->data() , 8 , arr->rows()*arr->columns() , f );
+    std::fclose(f);
+    return true;
+  }
+
+  int run_msp(int argc, char* argv[])
+  {
+    std::vector<BatchSpec> specs;
+    if( argc < 3 || ! parse_msp( argv[2] , specs ) ) return 2;
+    std::string want; SlotValues dumps;
+    for(int i=3;i<argc;i++)
+    {
+      std::string a = argv[i];
+      if( a.rfind("dump:",0) == 0 && a.find('=') != std::string::npos ) dumps.push_back( { a.substr(5,a.find('=')-5) , a.substr(a.find('=')+1) } );
+      else want = a;
+    }
+    const BatchSpec* spec = nullptr;
+    for(const auto& s : specs) if( ! s.body.empty() && ( want.empty() || s.key == want || s.name == want ) ) { spec = &s; break; }
+    if( spec == nullptr ) { std::fprintf(stderr,"no runnable batch%s%s in %s\n", want.empty() ? "" : " named ", want.c_str(), argv[2]); return 2; }
+
+    auto batch = std::make_shared<FlatBatch>();
+    batch->set_name( spec->name );
+    batch->set_task_group( spec->task_group );
+    // slot connection by name, as the reference's graph builder resolves it for a flat batch: a slot that consumes
+    // (INPUT / INPUT_OUTPUT) and gets no value from the file aliases the latest earlier slot of that name that produces
+    // (OUTPUT / INPUT_OUTPUT); INPUT slots never feed each other
+    std::map<std::string,OperatorSlotBase*> producer;
+    auto produces = [](const OperatorSlotBase* s) { return ! s->is_private() && ( s->direction() == OUTPUT || s->direction() == INPUT_OUTPUT ); };
+    auto consumes = [](const OperatorSlotBase* s) { return ! s->is_private() && ( s->direction() == INPUT || s->direction() == INPUT_OUTPUT ); };
+    for(const auto& item : spec->body)
+    {
+      std::shared_ptr<OperatorNode> op;
+      try { op = OperatorNodeFactory::instance()->make_operator( item.op ); }
+      catch( const OperatorCreationException& e ) { std::fprintf(stderr,"%s\n",e.what()); return 2; }
+      op->set_parent( batch.get() );
+      for(const auto& [sname,slot] : op->slots())
+      {
+        bool valued = false;
+        for(const auto& kv : item.values) valued = valued || ( kv.first == sname );
+        auto it = producer.find(sname);
+        if( ! valued && consumes(slot) && it != producer.end() && ! slot->share_value_of( * it->second ) )
+        { std::fprintf(stderr,"slot %s of %s: type differs from its producer\n",sname.c_str(),item.op.c_str()); return 2; }
+        if( produces(slot) ) producer[sname] = slot;
+      }
+      for(const auto& [k,v] : item.values)
+      {
+        auto* s = op->slot(k);
+        if( s == nullptr || ! s->set_from_string(v) ) { std::fprintf(stderr,"cannot set slot %s of %s\n",k.c_str(),item.op.c_str()); return 2; }
+      }
+      batch->m_ops.push_back( op );
+    }
+    std::printf("batch %s : %d operator(s)%s\n", spec->name.c_str(), int(batch->m_ops.size()), spec->task_group ? ", task_group" : "");
+    batch->run();
+    for(const auto& d : dumps)
+      if( producer.find(d.first) == producer.end() || ! dump_array( producer[d.first] , d.second ) ) { std::fprintf(stderr,"cannot dump slot %s\n",d.first.c_str()); return 2; }
+    batch->m_ops.clear();
+    return 0;
+  }
+}
+
 int main(int argc, char* argv[])
 {
   if( argc < 2 )
   {
-    std::printf("usage: %s <operator> [slot=value ...] [dump:<array2d slot>=<file>] [fill:<array2d slot>=<rows>x<cols>]\navailable operators:\n", argv[0]);
+    std::printf("usage: %s <operator> [slot=value ...] [dump:<array2d slot>=<file>] [fill:<array2d slot>=<rows>x<cols>]\n"
+                "       %s --msp <file.msp> [batch] [dump:<array2d slot>=<file>]\navailable operators:\n", argv[0], argv[0]);
     for(const auto& n : OperatorNodeFactory::instance()->available_operators()) std::printf("  %s\n", n.c_str());
     return 2;
   }
-  auto op = OperatorNodeFactory::instance()->make_operator( argv[1] );
-  std::vector< std::pair<std::string,std::string> > dumps;
+  if( std::strcmp( argv[1] , "--msp" ) == 0 ) return run_msp( argc , argv );
+
+  std::shared_ptr<OperatorNode> op;
+  try { op = OperatorNodeFactory::instance()->make_operator( argv[1] ); }
+  catch( const OperatorCreationException& e ) { std::fprintf(stderr,"%s\n",e.what()); return 2; }
+  SlotValues dumps;
   for(int i=2;i<argc;i++)
   {
     std::string a = argv[i];
@@ -31,16 +219,10 @@ int main(int argc, char* argv[])
     if( key.rfind("fill:",0) == 0 )
     {
       auto* s = op->slot( key.substr(5) );
-      if( s == nullptr ) { std::fprintf(stderr,"no slot %s\n",key.c_str()+5); return 2; }
-      size_t r=0,c=0; std::sscanf( val.c_str() , "%zux%zu" , &r , &c );
-      auto* arr = static_cast<extras::Array2D*>( s->value_address() );
-      arr->resize(r,c);
-      for(size_t k=0;k<r*c;k++)
-      { // tests/_inputs.py:lcg_uniform(seed 8, [1e-3,1))
-        uint64_t h = ( k * 2654435761ull + 8ull * 40503ull + 12345ull ) & 0xFFFFFFFFull;
-        h = ( ( h ^ ( h >> 15 ) ) * 2246822519ull ) & 0xFFFFFFFFull; h = ( h ^ ( h >> 13 ) ) & 0xFFFFFFFFull;
-        arr->m_data[k] = 1e-3 + ( 1.0 - 1e-3 ) * ( double(h) / 4294967296.0 );
-      }
+      size_t r=0,c=0;
+      if( s == nullptr || s->value_type() != typeid(extras::Array2D) || std::sscanf( val.c_str() , "%zux%zu" , &r , &c ) != 2 )
+      { std::fprintf(stderr,"cannot fill slot %s\n",key.c_str()+5); return 2; }
+      fill_array( static_cast<extras::Array2D*>( s->value_address() ) , r , c );
       continue;
     }
     auto* s = op->slot(key);
@@ -48,16 +230,7 @@ int main(int argc, char* argv[])
   }
   op->run();
   for(const auto& d : dumps)
-  {
-    auto* s = op->slot( d.first );
-    if( s == nullptr ) { std::fprintf(stderr,"no slot %s\n",d.first.c_str()); return 2; }
-    auto* arr = static_cast<extras::Array2D*>( s->value_address() );
-    FILE* f = std::fopen( d.second.c_str() , "wb" );
-    const uint64_t hdr[2] = { arr->rows() , arr->columns() };
-    std::fwrite( hdr , 8 , 2 , f );
-    std::fwrite( arr->data() , 8 , arr->rows()*arr->columns() , f );
-    std::fclose(f);
-  }
+    if( ! dump_array( op->slot( d.first ) , d.second ) ) { std::fprintf(stderr,"cannot dump slot %s\n",d.first.c_str()); return 2; }
   op.reset();
   return 0;
 }

@@ -66,6 +66,48 @@ def test_parallel_queue_lane_scenarios(prog, tmp_path, orc, mode, kernel_1d):
     assert np.array_equal(d[0], a1) and np.array_equal(d[1], a2)
 
 
+def test_automatic_lanes_from_declared_accesses(prog, tmp_path):
+    """any_lane() + declared accesses -> lane DAG (parallel_execution_queue.h:pre_process_queue): independent arrays
+    overlap on different lanes, an operation touching two arrays waits for both lanes, and the outcome equals serial FIFO
+    execution (the reference serialises these operations: src/parallel/parallel_execution_queue.cpp:185-207)."""
+    rows, cols, iters = 64, 4096, 2000
+    d = run(prog, tmp_path, "autolanes", rows, cols, iters).view(np.float64)
+    n = rows * cols
+    A, B, C = lcg_uniform(n, 8), lcg_uniform(n, 9), lcg_uniform(n, 10)
+    A += 1.1
+    for _ in range(iters):
+        B += 1.3
+    A += 1.2
+    B += A
+    A += 1.4
+    for _ in range(3):
+        C += 0.7
+    assert np.array_equal(d[:n], A) and np.array_equal(d[n:2 * n], B) and np.array_equal(d[2 * n:3 * n], C)
+    lanes, waits = d[3 * n:3 * n + 6].astype(int), d[3 * n + 6:3 * n + 12].astype(int)
+    assert lanes[0] == lanes[2] == lanes[3] == lanes[4]           # chain on A
+    assert lanes[1] != lanes[0] and lanes[5] not in (lanes[0], lanes[1])
+    assert list(waits) == [0, 0, 0, 1, 0, 0]                      # only B += A carries a cross-lane edge (to B's lane)
+
+
+def test_automatic_lanes_overlap_like_explicit_lanes(prog, tmp_path):
+    """few-block kernels on two arrays: any_lane()+accesses must overlap them like explicit lanes 0/1 do (and both beat one
+    lane); results stay exact: 9 sequential runs of (k1,k2) per array"""
+    rows, cols, iters = 4, 8192, 20000
+    d = run(prog, tmp_path, "autolanes_perf", rows, cols, iters).view(np.float64)
+    one_lane, explicit, auto = d[:3]
+    assert auto < 0.75 * one_lane and auto < 1.25 * explicit, (one_lane, explicit, auto)
+    n = rows * cols
+    A, B = lcg_uniform(n, 8), lcg_uniform(n, 9)
+    for _ in range(9):
+        for v in (1.1, 1.2):
+            for _ in range(iters):
+                A += v
+        for v in (1.3, 1.4):
+            for _ in range(iters):
+                B += v
+    assert np.array_equal(d[3:3 + n], A) and np.array_equal(d[3 + n:], B)
+
+
 def test_3d_spaces(prog, tmp_path, orc, gold):
     d = run(prog, tmp_path, "grid3d").view(np.float64)
     assert np.array_equal(d[:64], np.ones(64))          # block_parallel_for over {0..4}^3: every cell once
@@ -247,3 +289,34 @@ def test_reference_plugin_parallel_for_benchmarks(tmp_path):
     body = out.split("parallel_for 3D test")[-1]
     ones = sum(line.split(":")[1].split().count("1") for line in body.splitlines() if " J=" in line)
     assert ones == 13 * 10 * 10
+
+
+MSP_DIR = os.path.join(os.path.dirname(__file__), "cxx", "msp")
+
+
+def _run_msp(tmp_path, msp, *args):
+    exe = _refplugins()
+    out = os.path.join(tmp_path, os.path.basename(msp) + ".bin")
+    r = subprocess.run([exe, "--msp", msp, *[a.replace("@OUT", out) for a in args]], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stdout[-1500:], r.stderr[-1500:])
+    return out, r.stdout
+
+
+def test_reference_plugins_from_msp_batch_connected_slots(tmp_path):
+    """.msp flat batch: three unchanged tutorial operators in a task group, `my_array` connected by name"""
+    out, stdout = _run_msp(tmp_path, os.path.join(MSP_DIR, "tutorial_chain.msp"), "dump:my_array=@OUT")
+    assert "3 operator(s), task_group" in stdout
+    want = np.zeros((1024, 1024))            # first operator allocates 1024x1024 zeros (synchronous_block_parallel.cu:28-31)
+    for v in (1.1, 1.2, 1.3):
+        want += v
+    assert np.array_equal(_load_array(out), want)
+
+
+def test_reference_plugins_from_msp_example_shape(tmp_path):
+    """the layout of data/exemples/concurrent_block_parallel.msp (comments, flow maps, a second operator re-using the
+    arrays of the first through the connected array1/array2 slots)"""
+    out, stdout = _run_msp(tmp_path, os.path.join(MSP_DIR, "concurrent_lanes.msp"), "run_test", "dump:array2=@OUT")
+    assert stdout.count("All operations have terminated") == 2
+    x = _chain(np.zeros((4, 256)), 2.3, 2) + 2.3           # concurrent_block_parallel
+    x = _chain(x, 0.5, 1) + 0.5                            # automatic_concurrent_parallel on the same arrays
+    assert np.allclose(_load_array(out), x, rtol=1e-10, atol=0)     # pow/sin: libm vs libdevice, few iterations (the map is chaotic)
