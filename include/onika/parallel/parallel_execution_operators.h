@@ -68,6 +68,16 @@ namespace onika { namespace parallel {
   template< std::derived_from<ParallelExecutionQueueBase> Q >
   inline Q & operator << ( Q & q , const ParallelDataAccess& pda ) { q.add_data_access( pda ); return q; }
 
+  // queue << capture(g) ... << flush : the flush records into g instead of executing (parallel_execution_graph.h)
+  struct capture_t { ParallelExecutionGraph* m_graph = nullptr; };
+  static inline capture_t capture( ParallelExecutionGraph& g ) { return { &g }; }
+  inline ParallelExecutionQueue& operator << ( ParallelExecutionQueue& q , const capture_t& c )
+  {
+    if( ! q.empty() ) fatal_error() << "capture : the queue must be empty (flush and synchronize it first)" << std::endl;
+    q.m_capture_target = c.m_graph;
+    return q;
+  }
+
   inline ParallelExecutionQueue& operator << ( ParallelExecutionQueue& q , flush_t ) { q.schedule_all(); q.set_lane(DEFAULT_EXECUTION_LANE); return q; }
   inline ParallelExecutionQueue& operator << ( ParallelExecutionQueue& q , synchronize_t ) { q.wait(); return q; }
 

@@ -18,6 +18,7 @@
 #include <onika/parallel/parallel_data_access.h>
 #include <onika/parallel/constants.h>
 #include <onika/parallel/block_parallel_for_functor.h>
+#include <onika/parallel/parallel_execution_graph.h>
 #include <onika/log.h>
 
 #ifndef ONIKA_AUTO_LANE_CYCLE_HINT
@@ -159,6 +160,8 @@ namespace onika { namespace parallel {
   {
     ParallelExecutionStreamPool m_stream_pool = {};
     ParallelExecutionContext* m_exec_list = nullptr;
+    ParallelExecutionGraph* m_capture_target = nullptr;   // set by `queue << capture(g)`: the next flush records into g
+    bool m_capturing = false;
 
     static inline std::shared_ptr<ParallelExecutionQueue> s_default_queue = nullptr;
     static inline std::shared_ptr<ParallelExecutionStreamAutoAllocator> s_default_stream_allocator = nullptr;
@@ -187,6 +190,7 @@ namespace onika { namespace parallel {
       bool any_undefined = false;
       for(auto* p=m_queue_list; p!=nullptr; p=p->m_next) any_undefined = any_undefined || ( p->m_lane == UNDEFINED_EXECUTION_LANE );
       if( any_undefined ) pre_process_queue( m_queue_list , m_exec_list );
+      if( m_capture_target != nullptr ) { capture_all(); return; }
       ParallelExecutionContext *keep = nullptr, *scheduled = nullptr;
       auto* p = m_queue_list;
       while( p != nullptr )
@@ -201,9 +205,51 @@ namespace onika { namespace parallel {
       m_exec_list = pec_list_append( m_exec_list , scheduled );
     }
 
+    // records everything queued into m_capture_target instead of running it (see parallel_execution_graph.h)
+    inline void capture_all()
+    {
+      auto & g = * m_capture_target;
+      m_capture_target = nullptr;
+      if( g.valid() || g.m_pec_list != nullptr ) fatal_error() << "capture : ParallelExecutionGraph already holds a capture, release() it first" << std::endl;
+      if( m_queue_list == nullptr ) return;
+      // everything that allocates (lane streams, device scratch, events) happens before the capture starts
+      int lanes[MAX_EXECUTION_LANES]; int nlanes = 0;
+      for(auto* p=m_queue_list; p!=nullptr; p=p->m_next)
+      {
+        if( p->m_lane == UNDEFINED_EXECUTION_LANE || p->m_lane == DEFAULT_EXECUTION_LANE ) p->m_lane = 0;
+        bool seen = false;
+        for(int i=0;i<nlanes;i++) seen = seen || ( lanes[i] == p->m_lane );
+        if( ! seen ) { lanes[nlanes++] = p->m_lane; m_stream_pool( p->m_lane ); }
+        if( p->m_execution_target == ParallelExecutionContext::EXECUTION_TARGET_CUDA ) p->init_device_scratch();
+      }
+      g.m_origin_lane = lanes[0];
+      g.m_num_lanes = nlanes;
+      ONIKA_B200_CHECK( onk_graph_begin( lanes[0] , lanes+1 , nlanes-1 ) );
+      m_capturing = true;
+      auto* p = m_queue_list;
+      m_queue_list = nullptr;
+      while( p != nullptr )
+      {
+        auto* next = p->m_next;
+        p->m_next = nullptr;
+        schedule( p );
+        g.m_pec_list = pec_list_append( g.m_pec_list , p );
+        ++ g.m_num_operations;
+        p = next;
+      }
+      m_capturing = false;
+      ONIKA_B200_CHECK( onk_graph_end( & g.m_graph ) );
+    }
+
     static inline void host_operation_trampoline(void* p)
     {
       auto* pec = static_cast<ParallelExecutionContext*>(p);
+      get_block_parallel_functor(pec).execute_omp_parallel_region( pec , pec->m_stream );
+    }
+    static inline void host_operation_replay_trampoline(void* p)   // host node of a captured graph: runs once per replay
+    {
+      auto* pec = static_cast<ParallelExecutionContext*>(p);
+      pec->m_stream->m_omp_execution_count.fetch_add(1);
       get_block_parallel_functor(pec).execute_omp_parallel_region( pec , pec->m_stream );
     }
     static inline void gpu_epilog_trampoline(void* p)
@@ -249,8 +295,12 @@ namespace onika { namespace parallel {
       {
         // user-declared host-only functor: a host node in the lane's stream keeps it ordered with the lane's kernels
         pec->m_scheduled_on_gpu = false;
-        exec_stream->m_omp_execution_count.fetch_add(1);
-        ONIKA_B200_CHECK( onk_lane_host_func( lane , host_operation_trampoline , pec ) );
+        if( m_capturing ) ONIKA_B200_CHECK( onk_lane_host_func( lane , host_operation_replay_trampoline , pec ) );
+        else
+        {
+          exec_stream->m_omp_execution_count.fetch_add(1);
+          ONIKA_B200_CHECK( onk_lane_host_func( lane , host_operation_trampoline , pec ) );
+        }
       }
     }
 

@@ -328,6 +328,7 @@ struct onk_op
   void       (*epilog)(void*) = nullptr;
   void*        user = nullptr;
   bool         began = false, ended = false;
+  bool         captured = false;    // bracket recorded into a CUDA graph: no timing events
 };
 
 static void CUDART_CB onk_op_epilog_trampoline(void* p)
@@ -378,7 +379,10 @@ int onk_op_begin(onk_op* op, int lane, const void* return_init_host, size_t retu
   void* scratch; if (int rc = onk_op_device_scratch(op, &scratch)) return rc;
   op->stream = L->stream;
   op->began = true; op->ended = false;
-  ONK_CUDA(cudaEventRecord(op->start, op->stream));
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  ONK_CUDA(cudaStreamIsCapturing(op->stream, &cap));
+  op->captured = (cap != cudaStreamCaptureStatusNone);   // timing events mean nothing inside a graph: skipped, elapsed = 0
+  if (!op->captured) ONK_CUDA(cudaEventRecord(op->start, op->stream));
   if (return_init_host != nullptr && return_bytes > 0)
     ONK_CUDA(cudaMemcpyAsync((char*)scratch + 64, return_init_host, return_bytes, cudaMemcpyDefault, op->stream));
   if (reset_counters)
@@ -397,7 +401,7 @@ int onk_op_end(onk_op* op, void* return_out_host, size_t return_bytes, void (*ep
   }
   if (return_out_host != nullptr && return_bytes > 0)
     ONK_CUDA(cudaMemcpyAsync(return_out_host, (char*)op->scratch + 64, return_bytes, cudaMemcpyDefault, op->stream));
-  ONK_CUDA(cudaEventRecord(op->stop, op->stream));
+  if (!op->captured) ONK_CUDA(cudaEventRecord(op->stop, op->stream));
   op->ended = true;
   return ONK_OK;
 }
@@ -405,6 +409,7 @@ int onk_op_end(onk_op* op, void* return_out_host, size_t return_bytes, void (*ep
 int onk_op_elapsed_ms(onk_op* op, float* ms)
 {
   ONK_REQUIRE(op != nullptr && ms != nullptr && op->ended, "onk_op_elapsed_ms: op has not ended");
+  if (op->captured) { *ms = 0.0f; return ONK_OK; }
   ONK_CUDA(cudaEventElapsedTime(ms, op->start, op->stop));
   return ONK_OK;
 }

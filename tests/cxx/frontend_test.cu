@@ -374,6 +374,73 @@ static int scenario_autolanes_perf(Out& out, size_t rows, size_t cols, int iters
   return pq.empty() ? 0 : 3;
 }
 
+// capture(g) : the tutorial lane pattern (GPU kernel then host-only kernel per array, any_lane + accesses, plus a
+// return-data reduction) recorded once and replayed `replays` times; also times N small operations direct vs replayed
+static int scenario_graph(Out& out, size_t rows, size_t cols, int replays, int nsmall)
+{
+  extras::Array2D A, B;
+  A.resize(rows,cols); B.resize(rows,cols);
+  fill(A.m_data,8,1e-3,1.0); fill(B.m_data,9,1e-3,1.0);
+  const auto a_rw = local_access( A.m_data.data() , 2 , AccessStencilElement::RW , "a_rw" );
+  const auto b_rw = local_access( B.m_data.data() , 2 , AccessStencilElement::RW , "b_rw" );
+  auto & pq = ParallelExecutionQueue::default_queue();
+  ReduceResult* red = nullptr;                                  // pinned: the D2H copy of every replay lands here
+  ONIKA_B200_CHECK( onk_alloc( sizeof(ReduceResult) , 64 , ONK_MEM_PINNED , (void**) &red ) );
+  *red = ReduceResult{ DBL_MAX , -DBL_MAX , 0.0 , 0 };
+  double n_ops = 0, n_lanes = 0;
+  {
+    ParallelExecutionGraph g;
+    auto* red_pec = parallel_execution_context("A","reduce");
+    red_pec->init_device_scratch();
+    BlockParallelForOptions ropts; ropts.return_data = red; ropts.return_data_size = sizeof(ReduceResult);
+    pq << capture(g) << any_lane(4)
+       << a_rw << block_parallel_for( rows , extras::BlockParallelValueAddFunctor<true>{ A , 1.1 } , parallel_execution_context("A","k1") )
+       << b_rw << block_parallel_for( rows , extras::BlockParallelValueAddFunctor<true>{ B , 1.3 } , parallel_execution_context("B","k1") )
+       << a_rw << block_parallel_for( rows , extras::BlockParallelValueAddFunctor<false>{ A , 1.2 } , parallel_execution_context("A","k2host") )
+       << b_rw << block_parallel_for( rows , extras::BlockParallelValueAddFunctor<true>{ B , 1.4 } , parallel_execution_context("B","k2") )
+       << a_rw << block_parallel_for( rows , RowReduceFunctor{ A.data() , cols , (ReduceResult*) red_pec->get_device_return_data_ptr() } , red_pec , ropts )
+       << flush;
+    if( ! pq.empty() ) return 4;                              // recorded operations belong to the graph, not to the queue
+    n_ops = g.number_of_operations(); n_lanes = g.number_of_lanes();
+    for(int r=0;r<replays;r++) g.launch();
+    g.wait();
+  }
+  out.doubles( A.data() , rows*cols ); out.doubles( B.data() , rows*cols );
+  const double redv[4] = { red->vmin , red->vmax , red->vsum , double(red->count) };
+  out.doubles( redv , 4 ); out.doubles( &n_ops , 1 ); out.doubles( &n_lanes , 1 );
+  onk_free( red , sizeof(ReduceResult) );
+
+  // launch overhead: nsmall dependent small operations, scheduled one by one vs replayed from a graph
+  extras::Array2D S; S.resize(8,256);
+  for(size_t k=0;k<8*256;k++) S.m_data[k] = 0.0;
+  double ms[2] = { 0 , 0 };
+  for(int rep=0;rep<3;rep++)
+  {
+    for(int k=0;k<nsmall;k++) pq << set_lane(0) << block_parallel_for( 8 , RepeatedAddFunctor{ S , 1.0 , 1 } , parallel_execution_context("S","direct") );
+    auto t0 = std::chrono::steady_clock::now();
+    pq << flush << synchronize;
+    const double t = std::chrono::duration<double,std::milli>( std::chrono::steady_clock::now() - t0 ).count();
+    if( rep == 0 || t < ms[0] ) ms[0] = t;
+  }
+  {
+    ParallelExecutionGraph g;
+    pq << capture(g);
+    for(int k=0;k<nsmall;k++) pq << set_lane(0) << block_parallel_for( 8 , RepeatedAddFunctor{ S , 1.0 , 1 } , parallel_execution_context("S","graph") );
+    pq << flush;
+    for(int rep=0;rep<3;rep++)
+    {
+      auto t0 = std::chrono::steady_clock::now();
+      g.launch(); g.wait();
+      const double t = std::chrono::duration<double,std::milli>( std::chrono::steady_clock::now() - t0 ).count();
+      if( rep == 0 || t < ms[1] ) ms[1] = t;
+    }
+  }
+  std::printf("graph: %d small operations : scheduled one by one %.3f ms , one graph replay %.3f ms\n", nsmall, ms[0], ms[1]);
+  out.doubles( ms , 2 );
+  out.doubles( S.data() , 8*256 );                             // every element was incremented 6*nsmall times
+  return pq.empty() ? 0 : 3;
+}
+
 static int scenario_grid3d(Out& out)
 {
   {
@@ -598,6 +665,7 @@ int main(int argc, char* argv[])
   else if( sc == "lanes" ) rc = scenario_lanes( out , argc>3 ? argv[3] : "hybrid-lane" , arg(4,1024) , arg(5,1024) , arg(6,1) != 0 );
   else if( sc == "autolanes" ) rc = scenario_autolanes( out , arg(3,64) , arg(4,4096) , int(arg(5,2000)) );
   else if( sc == "autolanes_perf" ) rc = scenario_autolanes_perf( out , arg(3,4) , arg(4,8192) , int(arg(5,20000)) );
+  else if( sc == "graph" ) rc = scenario_graph( out , arg(3,128) , arg(4,512) , int(arg(5,3)) , int(arg(6,200)) );
   else if( sc == "grid3d" ) rc = scenario_grid3d( out );
   else if( sc == "reduce" ) rc = scenario_reduce( out , arg(3,777) , arg(4,1001) );
   else if( sc == "cells" ) rc = scenario_cells( out , arg(3,4096) );

@@ -108,6 +108,31 @@ def test_automatic_lanes_overlap_like_explicit_lanes(prog, tmp_path):
     assert np.array_equal(d[3:3 + n], A) and np.array_equal(d[3 + n:], B)
 
 
+def test_queue_capture_and_replay(prog, tmp_path):
+    """queue << capture(g) ... << flush records the lane DAG (GPU kernels, a host-only functor as a host node, the
+    return-data bracket of a reduction) into one CUDA graph; every replay must equal one more serial pass"""
+    rows, cols, replays, nsmall = 128, 512, 3, 200
+    d = run(prog, tmp_path, "graph", rows, cols, replays, nsmall).view(np.float64)
+    n = rows * cols
+    A, B = lcg_uniform(n, 8), lcg_uniform(n, 9)
+    vmin, vmax, vsum, cnt = np.finfo(np.float64).max, -np.finfo(np.float64).max, 0.0, 0
+    for _ in range(replays):
+        A += 1.1
+        B += 1.3
+        A += 1.2
+        B += 1.4
+        vmin, vmax, vsum, cnt = min(vmin, A.min()), max(vmax, A.max()), vsum + float(np.sum(A)), cnt + n
+    assert np.array_equal(d[:n], A) and np.array_equal(d[n:2 * n], B)
+    r = d[2 * n:2 * n + 6]
+    assert r[0] == vmin and r[1] == vmax and r[3] == cnt          # accumulated through the return-data channel, replay after replay
+    assert abs(r[2] - vsum) <= SUM_RTOL * abs(vsum)
+    assert r[4] == 5 and r[5] == 2                                # 5 operations on 2 lanes (arrays A and B)
+    direct_ms, graph_ms = d[2 * n + 6:2 * n + 8]
+    small = d[2 * n + 8:]
+    assert np.array_equal(small, np.full(8 * 256, 6.0 * nsmall))
+    assert graph_ms < direct_ms, (direct_ms, graph_ms)
+
+
 def test_3d_spaces(prog, tmp_path, orc, gold):
     d = run(prog, tmp_path, "grid3d").view(np.float64)
     assert np.array_equal(d[:64], np.ones(64))          # block_parallel_for over {0..4}^3: every cell once
