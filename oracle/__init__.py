@@ -26,6 +26,7 @@ _u8p = C.POINTER(C.c_uint8)
 _u32p = C.POINTER(C.c_uint32)
 _u64p = C.POINTER(C.c_uint64)
 _i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
 
 
 def _host_env():
@@ -94,6 +95,13 @@ class _Oracle:
             L.orc_cell_grid_layout.restype = C.c_uint64
             L.orc_cell_grid_layout.argtypes = [_u32p, C.c_uint64, C.c_uint64, C.c_uint64, _u32p, C.c_int, C.c_uint64, _u32p, _u64p]
             L.orc_lane_sequence_f64.argtypes = [_dp, _dp, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double]
+            L.orc_xs_process_for_id.restype = C.c_int
+            L.orc_xs_process_for_id.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_uint64]
+            L.orc_xs_range_start.restype = C.c_uint64
+            L.orc_xs_range_start.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64]
+            L.orc_xs_comm_scheme.restype = C.c_int
+            L.orc_xs_comm_scheme.argtypes = [C.c_int, C.c_uint64, C.c_uint64, _u64p, _u64p, _u64p, _u64p] + [_i32p] * 6
+            L.orc_xs_data_move.argtypes = [C.c_int, _u64p, _u64p] + [_i32p] * 6 + [C.c_uint64, _u8p, _u8p]
             self._lib = L
         return self._lib
 
@@ -255,6 +263,7 @@ class _Reference:
             L.ref_soatl_serialize.argtypes = [C.c_uint64, _dp, _u8p, _dp, C.POINTER(C.c_int32), _dp, _dp, _u8p, C.c_uint64]
             L.ref_cell_sum.restype = C.c_double
             L.ref_cell_sum.argtypes = [C.c_uint64, _u32p, _dp, _dp, _dp, _u64p, C.c_int]
+            L.ref_xs_data_move.argtypes = [C.c_int, C.c_uint64, C.c_uint64, _u64p, _u64p, _u64p, _u64p] + [_i32p] * 6 + [_dp, _dp, _u8p, _u8p]
             self._lib = L
         return self._lib
 
@@ -336,6 +345,84 @@ class _Reference:
                                   C.byref(nbytes), schedule)
         return sums, total.value, int(nbytes.value), t
 
+
+def _xs_offsets(per_rank):
+    off = np.zeros(len(per_rank) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(a) for a in per_rank])
+    cat = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.uint64) for a in per_rank]) if len(per_rank) else np.zeros(0, np.uint64))
+    return off, cat
+
+
+class XsScheme:
+    """index tables of communication_scheme_from_ids for every rank (rank-concatenated; counts/displs world x world)"""
+
+    def __init__(self, world, before_off, after_off):
+        self.world, self.before_off, self.after_off = world, before_off, after_off
+        self.send_indices = np.full(int(before_off[-1]), -1, dtype=np.int32)
+        self.recv_indices = np.full(int(after_off[-1]), -1, dtype=np.int32)
+        self.send_count, self.send_displ, self.recv_count, self.recv_displ = (np.full((world, world), -1, dtype=np.int32) for _ in range(4))
+
+    def tables(self):
+        return (self.send_indices, self.recv_indices, self.send_count, self.send_displ, self.recv_count, self.recv_displ)
+
+    def _ptrs(self):
+        return [_ptr(t, _i32p) for t in self.tables()]
+
+
+def _orc_xs_comm_scheme(self, id_min: int, id_max: int, ids_before, ids_after) -> XsScheme:
+    """ids_before / ids_after: one uint64 array per rank.  oracle.c:orc_xs_comm_scheme"""
+    world = len(ids_before)
+    boff, bcat = _xs_offsets(ids_before)
+    aoff, acat = _xs_offsets(ids_after)
+    sch = XsScheme(world, boff, aoff)
+    rc = self.lib.orc_xs_comm_scheme(world, id_min, id_max, _ptr(boff, _u64p), _ptr(bcat, _u64p), _ptr(aoff, _u64p), _ptr(acat, _u64p), *sch._ptrs())
+    if rc != 0:
+        raise ValueError("an id has no source or no destination")
+    return sch
+
+
+def _orc_xs_data_move(self, sch: XsScheme, data_before: np.ndarray) -> np.ndarray:
+    """data_before: rank-concatenated elements (first axis = element).  oracle.c:orc_xs_data_move"""
+    data_before = np.ascontiguousarray(data_before)
+    elem = data_before.dtype.itemsize * int(np.prod(data_before.shape[1:], dtype=np.int64))
+    out = np.zeros((int(sch.after_off[-1]),) + data_before.shape[1:], dtype=data_before.dtype)
+    self.lib.orc_xs_data_move(sch.world, _ptr(sch.before_off, _u64p), _ptr(sch.after_off, _u64p), *sch._ptrs(), elem,
+                              _ptr(data_before.view(np.uint8).reshape(-1), _u8p), _ptr(out.view(np.uint8).reshape(-1), _u8p))
+    return out
+
+
+def _ref_xs_data_move(self, id_min: int, id_max: int, ids_before, ids_after, in8=None, in32=None):
+    """the UNMODIFIED reference (src/mpi/xs_data_move.cpp + xs_data_move_impl.h) on len(ids_before) in-process ranks.
+    Returns (XsScheme, out8, out32)."""
+    world = len(ids_before)
+    boff, bcat = _xs_offsets(ids_before)
+    aoff, acat = _xs_offsets(ids_after)
+    sch = XsScheme(world, boff, aoff)
+    out8 = np.zeros(int(aoff[-1])) if in8 is not None else None
+    out32 = np.zeros((int(aoff[-1]), 32), dtype=np.uint8) if in32 is not None else None
+    null_d, null_b = C.cast(None, _dp), C.cast(None, _u8p)
+    self.lib.ref_xs_data_move(world, id_min, id_max, _ptr(boff, _u64p), _ptr(bcat, _u64p), _ptr(aoff, _u64p), _ptr(acat, _u64p), *sch._ptrs(),
+                              _ptr(_f64(in8), _dp) if in8 is not None else null_d, _ptr(out8, _dp) if out8 is not None else null_d,
+                              _ptr(np.ascontiguousarray(in32, dtype=np.uint8).reshape(-1), _u8p) if in32 is not None else null_b,
+                              _ptr(out32.reshape(-1), _u8p) if out32 is not None else null_b)
+    return sch, out8, out32
+
+
+_Oracle.xs_comm_scheme = _orc_xs_comm_scheme
+_Oracle.xs_data_move = _orc_xs_data_move
+_Oracle.xs_process_for_id = lambda self, i, nprocs, lo, hi: self.lib.orc_xs_process_for_id(int(i), nprocs, lo, hi)
+_Oracle.xs_range_start = lambda self, rank, nprocs, lo, hi: self.lib.orc_xs_range_start(rank, nprocs, lo, hi)
+_Reference.xs_data_move = _ref_xs_data_move
+
+
+def _ref_run_unit_tests(self):
+    """runs the reference's own ONIKA_UNIT_TESTs compiled into oracle/_ref (xs_data_move_range_utils.h:103-150); (run, failed)"""
+    n = C.c_int(0)
+    failed = self.lib.ref_run_unit_tests(C.byref(n))
+    return n.value, failed
+
+
+_Reference.run_unit_tests = _ref_run_unit_tests
 
 orc = _Oracle()
 ref = _Reference()

@@ -324,3 +324,102 @@ void orc_lane_sequence_f64(double* a1, double* a2, uint64_t rows, uint64_t cols,
   orc_value_add_f64(a1, rows, cols, v12);
   orc_value_add_f64(a2, rows, cols, v22);
 }
+
+/* ============================ id-based redistribution (src/mpi/xs_data_move.cpp) ============================ */
+
+/* xs_data_move_range_utils.h:39-45 */
+int orc_xs_process_for_id(uint64_t id, int nprocs, uint64_t id_min, uint64_t id_max)
+{
+  return (int)( ( ( id - id_min + 1 ) * (uint64_t)nprocs - 1 ) / ( id_max - id_min ) );
+}
+
+/* xs_data_move_range_utils.h:48-55 */
+uint64_t orc_xs_range_start(int rank, int nprocs, uint64_t id_min, uint64_t id_max)
+{
+  const uint64_t range = id_max - id_min;
+  return id_min + ( (uint64_t)rank * range ) / (uint64_t)nprocs;
+}
+
+/* What the three exchanges of communication_scheme_from_ids compute, rank by rank:
+ *  (1) .cpp:76-247  every rank tells the rendezvous rank of each id where the id is before (owner, index) and where it must
+ *      be after; the rendezvous ranks hold id_move[id - range_start] = {src_owner, src_index, dst_owner, dst_index};
+ *  (2) .cpp:279-355 each rendezvous rank walks ITS id range in increasing id and hands every entry to the id's source
+ *      owner; a source rank reads the lists of rendezvous ranks 0,1,... one after the other, i.e. its own elements in
+ *      increasing id (ranges increase with the rank);
+ *  (3) .cpp:357-416 the source rank gives the k-th element it meets for destination d the send-buffer slot
+ *      send_displ[d]+k, and sends the matching dst_index list to d, which lays the lists of sources 0,1,... end to end;
+ *  (4) .cpp:418-433 both tables are inverted into scatter form: table[local element] = buffer slot.
+ * The union of the rendezvous tables is one directory over [id_min,id_max); one walk in increasing id serves (2)-(3). */
+int orc_xs_comm_scheme(int world, uint64_t id_min, uint64_t id_max,
+                       const uint64_t* before_off, const uint64_t* ids_before, const uint64_t* after_off, const uint64_t* ids_after,
+                       int32_t* send_indices, int32_t* recv_indices,
+                       int32_t* send_count, int32_t* send_displ, int32_t* recv_count, int32_t* recv_displ)
+{
+  const uint64_t range = id_max - id_min;
+  const size_t W = (size_t)world;
+  int32_t* src_owner = (int32_t*)malloc( sizeof(int32_t) * ( range ? range : 1 ) );
+  int32_t* dst_owner = (int32_t*)malloc( sizeof(int32_t) * ( range ? range : 1 ) );
+  uint64_t* src_index = (uint64_t*)malloc( sizeof(uint64_t) * ( range ? range : 1 ) );
+  uint64_t* dst_index = (uint64_t*)malloc( sizeof(uint64_t) * ( range ? range : 1 ) );
+  int32_t* cursor = (int32_t*)calloc( W * W , sizeof(int32_t) );
+  int rc = 0;
+  for(uint64_t k=0;k<range;k++) { src_owner[k] = -1; dst_owner[k] = -1; }      /* IdMove{0,0,-1,-1}, .cpp:218 */
+  for(int r=0;r<world;r++)
+  {
+    for(uint64_t i=before_off[r];i<before_off[r+1];i++) { const uint64_t k = ids_before[i] - id_min; src_owner[k] = r; src_index[k] = i - before_off[r]; }
+    for(uint64_t i=after_off[r];i<after_off[r+1];i++)   { const uint64_t k = ids_after[i] - id_min;  dst_owner[k] = r; dst_index[k] = i - after_off[r]; }
+  }
+  /* counts: send_count[s][d] = elements s sends to d ; recv_count[d][s] is the same number seen from d (.cpp:372,391) */
+  for(size_t k=0;k<W*W;k++) { send_count[k] = 0; recv_count[k] = 0; }
+  for(uint64_t k=0;k<range;k++)
+  {
+    if( src_owner[k] < 0 || dst_owner[k] < 0 ) { rc = -1; goto done; }
+    ++ send_count[ (size_t)src_owner[k]*W + (size_t)dst_owner[k] ];
+    ++ recv_count[ (size_t)dst_owner[k]*W + (size_t)src_owner[k] ];
+  }
+  for(int r=0;r<world;r++)
+  {
+    send_displ[(size_t)r*W] = 0; recv_displ[(size_t)r*W] = 0;                   /* .cpp:385-389, 423-427 */
+    for(int p=1;p<world;p++)
+    {
+      send_displ[(size_t)r*W+p] = send_displ[(size_t)r*W+p-1] + send_count[(size_t)r*W+p-1];
+      recv_displ[(size_t)r*W+p] = recv_displ[(size_t)r*W+p-1] + recv_count[(size_t)r*W+p-1];
+    }
+  }
+  /* slots, in increasing id: the k-th element of the pair (s,d) sits at send_displ[s][d]+k on s and recv_displ[d][s]+k on d */
+  for(uint64_t k=0;k<range;k++)
+  {
+    const size_t s = (size_t)src_owner[k], d = (size_t)dst_owner[k];
+    const int32_t nth = cursor[s*W+d] ++;
+    send_indices[ before_off[s] + src_index[k] ] = send_displ[s*W+d] + nth;
+    recv_indices[ after_off[d] + dst_index[k] ]  = recv_displ[d*W+s] + nth;
+  }
+done:
+  free(src_owner); free(dst_owner); free(src_index); free(dst_index); free(cursor);
+  return rc;
+}
+
+/* xs_data_move_impl.h:74-111 */
+void orc_xs_data_move(int world, const uint64_t* before_off, const uint64_t* after_off,
+                      const int32_t* send_indices, const int32_t* recv_indices,
+                      const int32_t* send_count, const int32_t* send_displ, const int32_t* recv_count, const int32_t* recv_displ,
+                      uint64_t elem_bytes, const uint8_t* in, uint8_t* out)
+{
+  const size_t W = (size_t)world;
+  const uint64_t total_before = before_off[world], total_after = after_off[world];
+  uint8_t* comm_input  = (uint8_t*)malloc( ( total_before ? total_before : 1 ) * elem_bytes );   /* all ranks' send buffers, rank after rank */
+  uint8_t* comm_output = (uint8_t*)malloc( ( total_after ? total_after : 1 ) * elem_bytes );
+  for(int r=0;r<world;r++)                                                                      /* pack, :74-82 */
+    for(uint64_t i=before_off[r];i<before_off[r+1];i++)
+      memcpy( comm_input + ( before_off[r] + (uint64_t)send_indices[i] ) * elem_bytes , in + i*elem_bytes , elem_bytes );
+  for(int d=0;d<world;d++)                                                                      /* MPI_Alltoallv, :88-94 */
+    for(int s=0;s<world;s++)
+      memcpy( comm_output + ( after_off[d] + (uint64_t)recv_displ[(size_t)d*W+s] ) * elem_bytes ,
+              comm_input  + ( before_off[s] + (uint64_t)send_displ[(size_t)s*W+d] ) * elem_bytes ,
+              (uint64_t)recv_count[(size_t)d*W+s] * elem_bytes );
+  (void)send_count;
+  for(int r=0;r<world;r++)                                                                      /* unpack, :96-103 */
+    for(uint64_t j=after_off[r];j<after_off[r+1];j++)
+      memcpy( out + j*elem_bytes , comm_output + ( after_off[r] + (uint64_t)recv_indices[j] ) * elem_bytes , elem_bytes );
+  free(comm_input); free(comm_output);
+}

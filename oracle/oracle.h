@@ -90,6 +90,26 @@ uint64_t orc_cell_grid_layout(const uint32_t* cell_size, uint64_t ncells, uint64
 void orc_lane_sequence_f64(double* a1, double* a2, uint64_t rows, uint64_t cols,
                            double v11, double v12, double v21, double v22);
 
+/* ---- id-based redistribution between ranks ---- */
+/* include/onika/mpi/xs_data_move_range_utils.h:39-63 : rendezvous rank of an id and the id range a rank is in charge of */
+int      orc_xs_process_for_id(uint64_t id, int nprocs, uint64_t id_min, uint64_t id_max);
+uint64_t orc_xs_range_start(int rank, int nprocs, uint64_t id_min, uint64_t id_max);
+/* src/mpi/xs_data_move.cpp:42-462 communication_scheme_from_ids, for all `world` ranks at once (the MPI_Alltoall(v) calls
+ * become loops over ranks).  Rank-concatenated arrays: before_off/after_off hold world+1 prefix sums; ids_* the ids;
+ * send_indices/recv_indices the scatter tables (position of a local element in its rank's send / receive buffer);
+ * send_count/send_displ/recv_count/recv_displ are world x world, row = rank.  Returns 0, or -1 when an id has no source or
+ * no destination (the reference aborts: .cpp:286-289,331-334,366-369). */
+int orc_xs_comm_scheme(int world, uint64_t id_min, uint64_t id_max,
+                       const uint64_t* before_off, const uint64_t* ids_before, const uint64_t* after_off, const uint64_t* ids_after,
+                       int32_t* send_indices, int32_t* recv_indices,
+                       int32_t* send_count, int32_t* send_displ, int32_t* recv_count, int32_t* recv_displ);
+/* include/onika/mpi/xs_data_move_impl.h:44-113 data_move for all ranks: pack by send_indices, exchange blocks
+ * (MPI_Alltoallv), unpack by recv_indices.  elem_bytes-sized opaque elements. */
+void orc_xs_data_move(int world, const uint64_t* before_off, const uint64_t* after_off,
+                      const int32_t* send_indices, const int32_t* recv_indices,
+                      const int32_t* send_count, const int32_t* send_displ, const int32_t* recv_count, const int32_t* recv_displ,
+                      uint64_t elem_bytes, const uint8_t* in, uint8_t* out);
+
 #ifdef __cplusplus
 }
 #endif

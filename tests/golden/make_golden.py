@@ -124,6 +124,16 @@ def main():
     sums, total, nbytes, _ = ref.cell_sum(counts, ec, schedule=2)
     g["cell_sum"] = dict(counts=[int(v) for v in counts], e=hx(ec), cell_sum=hx(sums), total=float(total).hex(), allocated_bytes=nbytes)
 
+    # ---- id-based redistribution: index tables of communication_scheme_from_ids, run on in-process ranks ----
+    from tests._inputs import xs_random_case, xs_simple_case
+    g["xs_data_move"] = []
+    for kind, args in (("simple", (3, 0, 20, 3)), ("simple", (3, 0, 107, 3)), ("simple", (7, 1, 111, 77)),
+                       ("random", (2, 3, 97, 50)), ("random", (8, 1976, 110, 1000))):
+        id_min, id_max, before, after = (xs_simple_case if kind == "simple" else xs_random_case)(*args)
+        sch, _, _ = ref.xs_data_move(id_min, id_max, before, after)
+        g["xs_data_move"].append(dict(kind=kind, args=list(args), send_indices=sch.send_indices.tolist(), recv_indices=sch.recv_indices.tolist(),
+                                      send_count=sch.send_count.tolist(), recv_displ=sch.recv_displ.tolist()))
+
     with open(os.path.join(HERE, "reference_vectors.json"), "w") as f:
         json.dump(g, f, indent=0, separators=(",", ":"))
     print("wrote", os.path.join(HERE, "reference_vectors.json"), os.path.getsize(os.path.join(HERE, "reference_vectors.json")), "bytes")
