@@ -158,6 +158,39 @@ int onk_xchg_export(onk_xchg* x, unsigned char handle[ONK_IPC_HANDLE_BYTES]);
 int onk_xchg_connect(onk_xchg* x, const unsigned char* handles /* world x ONK_IPC_HANDLE_BYTES, rank order */);
 int onk_xchg_destroy(onk_xchg* x);
 int onk_reduce_xchg_f64(int op, const double* in_dev, uint64_t n, double* out_dev, onk_xchg* x, int lane);
+int onk_xchg_info(onk_xchg* x, int* rank, int* world);
+/* device-side barrier between the ranks' lanes (same flag exchange, no payload): what every rank queued on `lane` before
+ * it, peer stores included, is complete and visible once it has passed on any rank.  Collective, counts as one epoch. */
+int onk_xchg_barrier(onk_xchg* x, int lane);
+
+/* ---- id-based redistribution between the GPUs of a node ----
+ * Replaces communication_scheme_from_ids (src/mpi/xs_data_move.cpp:42-462; include/onika/mpi/xs_data_move.h:31-50) +
+ * data_move (include/onika/mpi/xs_data_move_impl.h:44-113): after[d][j] = before[s][i] wherever ids_after[d][j] ==
+ * ids_before[s][i].  Instead of index tables + pack / MPI_Alltoallv / unpack, a plan holds one ROUTE (destination rank,
+ * destination index) per local element, found through a directory distributed by id range over the ranks (the reference's
+ * rendezvous ranks: xs_data_move_range_utils.h:39-63), and a move is one kernel per rank storing every element straight
+ * into the destination rank's output window over NVLink peer memory.  Windows are device allocations mapped into every
+ * peer process through CUDA IPC (export / all-gather the handles with any host transport / connect, like onk_xchg).
+ * All calls below except the *_ptr / *_send_counts accessors are collective over the ranks of `x`.
+ * onk_xs_plan_build returns ONK_ERR_ARG on EVERY rank (and the code in *status) when the ids are not a bijection over
+ * [id_min,id_max): 1 id of the range without source, 2 id without destination, 3 duplicate id before, 4 duplicate id
+ * after, 5 id out of range (the highest code present wins) -- the cases on which the reference aborts
+ * (xs_data_move.cpp:286-289,331-334,366-369). */
+typedef struct onk_window onk_window;
+int onk_window_create(size_t bytes, int rank, int world, onk_window** w);
+int onk_window_export(onk_window* w, unsigned char handle[ONK_IPC_HANDLE_BYTES]);
+int onk_window_connect(onk_window* w, const unsigned char* handles /* world x ONK_IPC_HANDLE_BYTES, rank order */);
+int onk_window_ptr(onk_window* w, void** local_dev, size_t* bytes);
+int onk_window_destroy(onk_window* w);
+typedef struct onk_xs_plan onk_xs_plan;
+int onk_xs_plan_create(onk_xchg* x, uint64_t id_min /* included */, uint64_t id_max /* excluded */, onk_xs_plan** plan);
+int onk_xs_plan_export(onk_xs_plan* plan, unsigned char handle[ONK_IPC_HANDLE_BYTES]);
+int onk_xs_plan_connect(onk_xs_plan* plan, const unsigned char* handles);
+int onk_xs_plan_build(onk_xs_plan* plan, const uint64_t* ids_before_dev, uint64_t n_before,
+                      const uint64_t* ids_after_dev, uint64_t n_after, int lane, int* status);
+int onk_xs_plan_send_counts(onk_xs_plan* plan, uint64_t* send_count_host /* world entries: the reference's send_count */);
+int onk_xs_move(onk_xs_plan* plan, onk_window* out, uint64_t elem_bytes, const void* in_dev, int lane);
+int onk_xs_plan_destroy(onk_xs_plan* plan);
 
 /* parallel_for(N, y[i] += a*x[i])   include/onika/parallel/parallel_for.h:91-112 (config C1) */
 int onk_axpy_f64(double* y_dev, const double* x_dev, double a, uint64_t n, int lane);

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libonika_b200.so")
-SOURCES = ["onk_runtime.cu", "onk_reduce.cu", "onk_stream.cu", "onk_cells.cu", "onk_host.cu"]
+SOURCES = ["onk_runtime.cu", "onk_reduce.cu", "onk_stream.cu", "onk_cells.cu", "onk_host.cu", "onk_xsmove.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--fmad=false",

@@ -62,6 +62,20 @@ PROTOTYPES = {
     "onk_xchg_connect": (i32, [vp, C.c_char_p]),
     "onk_xchg_destroy": (i32, [vp]),
     "onk_reduce_xchg_f64": (i32, [i32, vp, u64, vp, vp, i32]),
+    "onk_xchg_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
+    "onk_xchg_barrier": (i32, [vp, i32]),
+    "onk_window_create": (i32, [C.c_size_t, i32, i32, C.POINTER(vp)]),
+    "onk_window_export": (i32, [vp, C.c_char_p]),
+    "onk_window_connect": (i32, [vp, C.c_char_p]),
+    "onk_window_ptr": (i32, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+    "onk_window_destroy": (i32, [vp]),
+    "onk_xs_plan_create": (i32, [vp, u64, u64, C.POINTER(vp)]),
+    "onk_xs_plan_export": (i32, [vp, C.c_char_p]),
+    "onk_xs_plan_connect": (i32, [vp, C.c_char_p]),
+    "onk_xs_plan_build": (i32, [vp, vp, u64, vp, u64, i32, C.POINTER(i32)]),
+    "onk_xs_plan_send_counts": (i32, [vp, C.POINTER(u64)]),
+    "onk_xs_move": (i32, [vp, vp, u64, vp, i32]),
+    "onk_xs_plan_destroy": (i32, [vp]),
     "onk_axpy_f64": (i32, [vp, vp, dbl, u64, i32]),
     "onk_parallel_memset": (i32, [vp, u64, u64, i32, i32]),
     "onk_value_add_f64": (i32, [vp, u64, u64, dbl, i32]),

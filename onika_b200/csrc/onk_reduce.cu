@@ -181,6 +181,17 @@ namespace onk
 
 using namespace onk;
 
+namespace onk
+{
+  // device-side barrier between the ranks' lanes: everything queued before it on every rank's lane (peer stores
+  // included: a kernel's writes are performed before a later kernel of the same stream publishes its release flag)
+  // is complete and visible when it returns on any rank
+  __global__ void xchg_barrier_kernel(const __grid_constant__ XchgParams xp)
+  {
+    (void) xchg_combine<ONK_OP_MIN>(0.0, xp);
+  }
+}
+
 struct onk_xchg
 {
   XchgBuffer* local = nullptr;
@@ -241,6 +252,25 @@ int onk_xchg_destroy(onk_xchg* x)
   for (int r = 0; r < ONK_XCHG_MAX_WORLD; r++) if (x->opened[r]) cudaIpcCloseMemHandle(x->opened[r]);
   if (x->local) cudaFree(x->local);
   delete x;
+  return ONK_OK;
+}
+
+int onk_xchg_info(onk_xchg* x, int* rank, int* world)
+{
+  ONK_REQUIRE(x != nullptr, "onk_xchg_info: null exchange");
+  if (rank) *rank = x->params.rank;
+  if (world) *world = x->params.world;
+  return ONK_OK;
+}
+
+int onk_xchg_barrier(onk_xchg* x, int lane)
+{
+  ONK_REQUIRE(x != nullptr && x->connected, "onk_xchg_barrier: exchange is not connected");
+  Lane* L; if (int rc = lane_get(lane, &L)) return rc;
+  x->params.epoch += 1;
+  xchg_barrier_kernel<<<1, 32, 0, L->stream>>>(x->params);
+  ONK_CHECK_LAUNCH();
+  count_launch();
   return ONK_OK;
 }
 

@@ -106,3 +106,118 @@ class PeerExchange:
         if self.handle:
             self._check(self._lib.onk_xchg_destroy(self.handle))
             self.handle = None
+
+
+def _share_handles(export, connect, group, what: str) -> None:
+    """export the local CUDA IPC handle, all-gather the handles (host plumbing), open the peers'; collective-safe: every
+    rank reaches every collective even when a local step failed, then all raise together"""
+    import ctypes as C
+    import torch.distributed as dist
+    from ._capi import ONK_IPC_HANDLE_BYTES
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return
+    mine = C.create_string_buffer(ONK_IPC_HANDLE_BYTES)
+    rc = export(mine)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, bytes(mine.raw) if rc == 0 else None, group=group)
+    if rc != 0 or any(g is None for g in gathered):
+        raise RuntimeError(f"CUDA IPC export of {what} failed on some rank")
+    rc = connect(b"".join(gathered))
+    oks = [None] * world
+    dist.all_gather_object(oks, rc == 0, group=group)
+    if not all(oks):
+        raise RuntimeError(f"CUDA IPC open of a peer's {what} failed on some rank (no peer access?)")
+
+
+class PeerWindow:
+    """`nbytes` of device memory of this rank mapped into every peer process (onk_window_*): the landing zone of
+    IdRedistribution.move().  Collective constructor."""
+
+    def __init__(self, nbytes: int, exchange: "PeerExchange", group=None):
+        import ctypes as C
+        from ._capi import check, lib
+        self._C, self._check, self._lib = C, check, lib()
+        self.nbytes = int(nbytes)
+        self.handle = C.c_void_p()
+        check(self._lib.onk_window_create(self.nbytes, exchange.rank, exchange.world, C.byref(self.handle)))
+        _share_handles(lambda buf: self._lib.onk_window_export(self.handle, buf),
+                       lambda allh: self._lib.onk_window_connect(self.handle, allh), group, "an output window")
+
+    def tensor(self, dtype, shape=None):
+        """the local window viewed as a torch tensor (no copy)"""
+        import torch
+        C = self._C
+        p = C.c_void_p()
+        self._check(self._lib.onk_window_ptr(self.handle, C.byref(p), None))
+        itemsize = torch.empty(0, dtype=dtype).element_size()
+        n = self.nbytes // itemsize
+        if n == 0:
+            return torch.empty(shape if shape is not None else (0,), dtype=dtype, device="cuda")
+        from .runtime import tensor_from_ptr
+        t = tensor_from_ptr(p.value, n, dtype, owner=self)
+        return t.reshape(shape) if shape is not None else t
+
+    def close(self):
+        if self.handle:
+            self._check(self._lib.onk_window_destroy(self.handle))
+            self.handle = None
+
+
+class IdRedistribution:
+    """Id-based redistribution of elements between the GPUs of a node: the counterpart of the reference's
+    communication_scheme_from_ids + data_move (include/onika/mpi/xs_data_move.h:31-50, xs_data_move_impl.h:44-113).
+
+        mv = IdRedistribution(exchange, id_min, id_max)            # collective
+        mv.plan(ids_before, ids_after)                             # collective; raises on every rank if ids do not match up
+        out = PeerWindow(n_after * elem_bytes, exchange)           # collective
+        mv.move(values_before, out)                                # collective: out.tensor(...)[j] = value of the same id
+
+    Every id of [id_min, id_max) must appear exactly once before and once after (the reference aborts otherwise)."""
+
+    ERRORS = {1: "an id of the range has no source", 2: "an id has no destination", 3: "an id appears twice before",
+              4: "an id appears twice after", 5: "an id lies outside the id range"}
+
+    def __init__(self, exchange: "PeerExchange", id_min: int, id_max: int, group=None):
+        import ctypes as C
+        from ._capi import check, lib
+        self._C, self._check, self._lib = C, check, lib()
+        self.exchange, self.group = exchange, group
+        self.handle = C.c_void_p()
+        check(self._lib.onk_xs_plan_create(exchange.handle, int(id_min), int(id_max), C.byref(self.handle)))
+        _share_handles(lambda buf: self._lib.onk_xs_plan_export(self.handle, buf),
+                       lambda allh: self._lib.onk_xs_plan_connect(self.handle, allh), group, "the id directory")
+        self.n_before = self.n_after = 0
+
+    def plan(self, ids_before, ids_after, lane: int = -1) -> None:
+        import torch
+        from .runtime import ptr
+        C = self._C
+        for t in (ids_before, ids_after):
+            if t.dtype not in (torch.int64, torch.uint64) or not t.is_cuda or not t.is_contiguous():
+                raise ValueError("ids must be contiguous 64-bit integer CUDA tensors")
+        status = C.c_int(0)
+        rc = self._lib.onk_xs_plan_build(self.handle, ptr(ids_before), ids_before.numel(), ptr(ids_after), ids_after.numel(), lane, C.byref(status))
+        if rc != 0 and status.value != 0:
+            raise ValueError("id redistribution: " + self.ERRORS.get(status.value, f"error {status.value}"))
+        self._check(rc)
+        self.n_before, self.n_after = ids_before.numel(), ids_after.numel()
+
+    def send_counts(self):
+        """elements this rank sends to each rank (the reference's send_count)"""
+        C = self._C
+        buf = (C.c_uint64 * self.exchange.world)()
+        self._check(self._lib.onk_xs_plan_send_counts(self.handle, buf))
+        return [int(v) for v in buf]
+
+    def move(self, values, out: PeerWindow, lane: int = -1) -> None:
+        from .runtime import ptr
+        if values.shape[0] != self.n_before or not values.is_contiguous():
+            raise ValueError("values must be contiguous with one row per local element before")
+        elem = values.element_size() * (values.numel() // max(values.shape[0], 1)) if values.shape[0] else values.element_size()
+        self._check(self._lib.onk_xs_move(self.handle, out.handle, elem, ptr(values), lane))
+
+    def close(self):
+        if self.handle:
+            self._check(self._lib.onk_xs_plan_destroy(self.handle))
+            self.handle = None

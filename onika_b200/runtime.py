@@ -62,3 +62,19 @@ def ptr(t) -> C.c_void_p:
     if hasattr(t, "ctypes"):
         return C.c_void_p(t.ctypes.data)
     raise TypeError(f"cannot take the address of {type(t)}")
+
+
+class _DeviceBytes:
+    """raw device memory owned by the library, exposed through __cuda_array_interface__ so torch can view it"""
+
+    def __init__(self, address: int, nbytes: int, owner):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (address, False), "version": 2}
+        self._owner = owner          # keeps the allocation's handle alive as long as the view lives
+
+
+def tensor_from_ptr(address: int, count: int, dtype, owner=None):
+    """`count` elements of `dtype` at device address `address` as a torch tensor (no copy)"""
+    import torch
+    itemsize = torch.empty(0, dtype=dtype).element_size()
+    raw = torch.as_tensor(_DeviceBytes(int(address), count * itemsize, owner), device="cuda")
+    return raw.view(dtype)

@@ -134,3 +134,88 @@ def test_config_c5_lane_sequence_sharded_over_two_gpus(orc):
         assert abs(s1 - orc.reduce_sum_ld(a1.ravel())) <= 1e-12 * np.abs(a1).sum()
         assert abs(s2 - orc.reduce_sum_ld(a2.ravel())) <= 1e-12 * np.abs(a2).sum()
     assert got[0][5] == got[1][5]
+
+
+# ---------------------------------------------------------------- id-based redistribution over peer memory
+def _worker_xs(rank, world, port, cases, q):
+    import time
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import onika_b200 as ob
+    from onika_b200 import distributed as D
+    from tests._inputs import xs_random_case, xs_simple_case
+    ob.init(rank)
+    ob.bind_lane_to_torch_stream(0)
+    x = D.PeerExchange()
+    res = {}
+    for ci, (kind, args) in enumerate(cases):
+        id_min, id_max, before, after = (xs_simple_case if kind == "simple" else xs_random_case)(*args)
+        nb_all = sum(b.size for b in before)
+        b0 = sum(b.size for b in before[:rank])
+        rs = np.random.RandomState(3)
+        vals8 = rs.rand(nb_all)[b0:b0 + before[rank].size]
+        vals32 = rs.randint(0, 256, (nb_all, 32)).astype(np.uint8)[b0:b0 + before[rank].size]
+        mv = D.IdRedistribution(x, id_min, id_max)
+        ib = torch.from_numpy(before[rank].astype(np.int64)).cuda()
+        ia = torch.from_numpy(after[rank].astype(np.int64)).cuda()
+        mv.plan(ib, ia, lane=0)
+        na = after[rank].size
+        w8, w32 = D.PeerWindow(max(na, 1) * 8, x), D.PeerWindow(max(na, 1) * 32, x)
+        for rep in range(2):                                   # windows are re-used: leading barrier of move()
+            mv.move(torch.from_numpy(vals8).cuda(), w8, lane=0)
+            mv.move(torch.from_numpy(vals32).cuda(), w32, lane=0)
+        torch.cuda.synchronize()
+        res[ci] = (w8.tensor(torch.float64).cpu().numpy()[:na].copy(), w32.tensor(torch.uint8).cpu().numpy()[:na * 32].reshape(na, 32).copy(),
+                   mv.send_counts())
+        # a rejected plan is rejected on every rank (rank 1 drops one id after)
+        if ci == 0 and world > 1:
+            bad = ia[:-1].contiguous() if rank == 1 else ia
+            try:
+                mv.plan(ib, bad, lane=0)
+                res["rejected"] = False
+            except ValueError:
+                res["rejected"] = True
+        dist.barrier()
+        mv.close(); w8.close(); w32.close()
+    q.put((rank, res))
+    dist.barrier()
+    x.close()
+    dist.destroy_process_group()
+
+
+def test_id_redistribution_two_gpus(orc):
+    import torch
+    import torch.multiprocessing as mp
+    from tests._inputs import xs_random_case, xs_simple_case
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    cases = [("simple", (2, 0, 107, 3)), ("simple", (2, 1023, 1023 + 100000, 77)), ("random", (2, 1976, 110, 1000)),
+             ("random", (2, 0, 100000, 1000)), ("random", (2, 7, 1 << 20, 1 << 18))]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_xs, args=(r, world, port, cases, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for ci, (kind, args) in enumerate(cases):
+        id_min, id_max, before, after = (xs_simple_case if kind == "simple" else xs_random_case)(*args)
+        sch = orc.xs_comm_scheme(id_min, id_max, before, after)
+        nb_all = sum(b.size for b in before)
+        rs = np.random.RandomState(3)
+        want8 = orc.xs_data_move(sch, rs.rand(nb_all))
+        want32 = orc.xs_data_move(sch, rs.randint(0, 256, (nb_all, 32)).astype(np.uint8))
+        for rank in range(world):
+            a0, a1 = int(sch.after_off[rank]), int(sch.after_off[rank + 1])
+            out8, out32, counts = got[rank][ci]
+            assert np.array_equal(out8, want8[a0:a1]) and np.array_equal(out32, want32[a0:a1]), (ci, rank)
+            assert counts == sch.send_count[rank].tolist()
+    assert got[0]["rejected"] and got[1]["rejected"]
