@@ -1,0 +1,153 @@
+"""Id-based redistribution between GPUs: this repo's direct peer scatter (onk_xs_move) against the reference's scheme
+(pack by send order, all-to-all, unpack -- include/onika/mpi/xs_data_move_impl.h:74-103) carried by NCCL.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tools/bench_xs_move.py [--n-per-gpu 16777216] [--elem-bytes 32] [--reps 20]
+
+Workloads (ids 0..N*n): `migrate` = every rank keeps its particles except a band of `--migrate` (default 5 %) at each end
+of its block that goes to the neighbouring rank (what a domain decomposition step does between two time steps);
+`shuffle` = a global random permutation (worst case: every element a separate peer transaction).
+Device-timed (CUDA events on the lane's stream, max over ranks), inputs resident in HBM.  One JSON line per workload."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import onika_b200 as ob                                   # noqa: E402
+from onika_b200 import distributed as D                   # noqa: E402
+
+
+def ids_after_for(workload, rank, world, n, frac, seed=11):
+    total = n * world
+    if workload == "migrate":
+        band = int(n * frac)
+        lo, hi = rank * n, (rank + 1) * n
+        # rank keeps [lo+band, hi-band), receives the upper band of the left neighbour and the lower band of the right one
+        parts = [torch.arange(lo + band, hi - band, dtype=torch.int64)]
+        left, right = (rank - 1) % world, (rank + 1) % world
+        parts.insert(0, torch.arange((left + 1) * n - band, (left + 1) * n, dtype=torch.int64))
+        parts.append(torch.arange(right * n, right * n + band, dtype=torch.int64))
+        return torch.cat(parts)
+    g = torch.Generator().manual_seed(seed)
+    perm = torch.randperm(total, generator=g)
+    return perm[rank * n:(rank + 1) * n].contiguous()
+
+
+def nccl_tables(ids_before, ids_after, rank, world):
+    """send order / splits / receive positions for the pack + all-to-all + unpack scheme (plumbing, not timed)"""
+    dev = ids_before.device
+    n_after_all = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(n_after_all, torch.tensor([ids_after.numel()], dtype=torch.int64, device=dev))
+    counts = [int(t.item()) for t in n_after_all]
+    gathered = [torch.empty(c, dtype=torch.int64, device=dev) for c in counts]
+    dist.all_gather(gathered, ids_after)
+    all_after = torch.cat(gathered)
+    owner = torch.cat([torch.full((c,), r, dtype=torch.int64, device=dev) for r, c in enumerate(counts)])
+    local_index = torch.cat([torch.arange(c, dtype=torch.int64, device=dev) for c in counts])
+    order = torch.argsort(all_after)
+    pos = torch.searchsorted(all_after[order], ids_before)
+    d, j = owner[order][pos], local_index[order][pos]
+    send_perm = torch.argsort(d * (int(all_after.max().item()) + 1) + ids_before)      # by destination, then by id
+    send_splits = torch.bincount(d, minlength=world).tolist()
+    recv_splits_t = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv_splits_t, torch.tensor(send_splits, dtype=torch.int64, device=dev))
+    recv_splits = recv_splits_t.tolist()
+    recv_pos = torch.empty(sum(recv_splits), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv_pos, j[send_perm].contiguous(), recv_splits, send_splits)
+    return send_perm, send_splits, recv_splits, recv_pos
+
+
+def timed(fn, reps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n-per-gpu", type=int, default=1 << 24)
+    ap.add_argument("--elem-bytes", type=int, default=32)
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--migrate", type=float, default=0.05)
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ob.init(local)
+    ob.bind_lane_to_torch_stream(0)
+    x = D.PeerExchange()
+    n, eb = a.n_per_gpu, a.elem_bytes
+    ids_before = torch.arange(rank * n, (rank + 1) * n, dtype=torch.int64, device="cuda")
+    vals = torch.randint(0, 256, (n, eb), dtype=torch.uint8, device="cuda")
+    for workload in ("migrate", "shuffle"):
+        ids_after = ids_after_for(workload, rank, world, n, a.migrate).cuda()
+        mv = D.IdRedistribution(x, 0, n * world)
+        plan_ms = timed(lambda: mv.plan(ids_before, ids_after, lane=0), max(a.reps // 4, 2), warmup=1)
+        win = D.PeerWindow(ids_after.numel() * eb, x)
+        move_ms = timed(lambda: mv.move(vals, win, lane=0), a.reps)
+        ours = win.tensor(torch.uint8).reshape(-1, eb).clone()
+        sent_away = n - mv.send_counts()[rank]
+        # the reference's scheme over NCCL
+        send_perm, send_splits, recv_splits, recv_pos = nccl_tables(ids_before, ids_after, rank, world)
+        # widest element view torch can index (8-byte words when the record allows); the pack step uses whichever of
+        # torch's row-gather forms is fastest here, so that the baseline is the library at its best
+        wide = torch.float64 if eb % 8 == 0 else torch.uint8
+        vals_w = vals.view(wide)
+        out = torch.empty((ids_after.numel(), vals_w.shape[1]), dtype=wide, device="cuda")
+        recvbuf = torch.empty((sum(recv_splits), vals_w.shape[1]), dtype=wide, device="cuda")
+        inv_perm = torch.empty_like(send_perm)
+        inv_perm[send_perm] = torch.arange(send_perm.numel(), device="cuda")
+        packed_buf = torch.empty_like(vals_w)
+        packs = {"index_copy_inverse": lambda: packed_buf.index_copy_(0, inv_perm, vals_w),
+                 "index_select": lambda: torch.index_select(vals_w, 0, send_perm),
+                 "advanced_indexing": lambda: vals_w[send_perm],
+                 "gather_expand": lambda: torch.gather(vals_w, 0, send_perm.unsqueeze(1).expand(-1, vals_w.shape[1]))}
+        pack_ms = {k: timed(f, max(a.reps // 4, 3), warmup=1) for k, f in packs.items()}
+        best_pack = min(pack_ms, key=pack_ms.get)
+
+        def nccl_move():
+            packed = packs[best_pack]()
+            dist.all_to_all_single(recvbuf, packed, recv_splits, send_splits)
+            out.index_copy_(0, recv_pos, recvbuf)
+
+        nccl_ms = timed(nccl_move, a.reps)
+        packed = packs[best_pack]()
+        stage_ms = [pack_ms[best_pack],
+                    timed(lambda: dist.all_to_all_single(recvbuf, packed, recv_splits, send_splits), a.reps),
+                    timed(lambda: out.index_copy_(0, recv_pos, recvbuf), a.reps)]
+        same = bool(torch.equal(out.view(torch.uint8), ours))
+        flags = [None] * world
+        dist.all_gather_object(flags, same)
+        if rank == 0:
+            gb = 2.0 * n * eb / 1e9                      # every element read once and written once, per GPU
+            print(json.dumps({"bench": "xs_move", "workload": workload, "n_gpus": world, "n_per_gpu": n, "elem_bytes": eb,
+                              "fraction_leaving_rank": round(sent_away / n, 4), "plan_ms": round(plan_ms, 4),
+                              "move_ms": round(move_ms, 4), "move_GBps_per_gpu": round(gb / (move_ms * 1e-3), 1),
+                              "nccl_pack_alltoall_unpack_ms": round(nccl_ms, 4),
+                              "nccl_stage_ms": {"pack_" + best_pack: round(stage_ms[0], 4), "all_to_all_single": round(stage_ms[1], 4),
+                                                "unpack_index_copy": round(stage_ms[2], 4)}, "speedup_vs_nccl_scheme": round(nccl_ms / move_ms, 2),
+                              "identical_to_nccl_scheme": all(flags)}), flush=True)
+        dist.barrier()
+        mv.close(); win.close()
+    x.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
