@@ -73,24 +73,18 @@ class PeerExchange:
     def __init__(self, group=None):
         import ctypes as C
         import torch.distributed as dist
-        from ._capi import check, lib, ONK_IPC_HANDLE_BYTES
+        from ._capi import check, lib
         self._C, self._check, self._lib = C, check, lib()
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.handle = C.c_void_p()
         check(self._lib.onk_xchg_create(self.rank, self.world, C.byref(self.handle)))
-        if self.world > 1:
-            mine = C.create_string_buffer(ONK_IPC_HANDLE_BYTES)
-            rc = self._lib.onk_xchg_export(self.handle, mine)
-            gathered = [None] * self.world
-            dist.all_gather_object(gathered, bytes(mine.raw) if rc == 0 else None, group=group)   # collective: always reached
-            if rc != 0 or any(g is None for g in gathered):
-                raise RuntimeError("CUDA IPC export of the exchange buffer failed on some rank")
-            rc = self._lib.onk_xchg_connect(self.handle, b"".join(gathered))
-            oks = [None] * self.world
-            dist.all_gather_object(oks, rc == 0, group=group)          # every rank has mapped every buffer before first use
-            if not all(oks):
-                raise RuntimeError("CUDA IPC open of a peer exchange buffer failed on some rank (no peer access?)")
+        _share_handles(lambda buf: self._lib.onk_xchg_export(self.handle, buf),
+                       lambda allh: self._lib.onk_xchg_connect(self.handle, allh), group, "the exchange buffer")
+
+    def barrier(self, lane: int = -1) -> None:
+        """device-side barrier between the ranks' lanes (onk_xchg_barrier); collective"""
+        self._check(self._lib.onk_xchg_barrier(self.handle, lane))
 
     def reduce(self, op: int, data, n=None, out=None, lane: int = -1):
         import torch

@@ -85,3 +85,52 @@ def test_shard_range_properties():
             assert max(sizes) - min(sizes) <= 1
     assert D.fold_partials(0, [3.0, float("nan"), 2.0]) == 2.0
     assert D.fold_partials(2, [0.1, 0.2, 0.3]) == (0.1 + 0.2) + 0.3
+
+
+# ---- handle exchange of peer-mapped buffers (exchange buffers, id directories, output windows): host plumbing only ----
+def _worker_handles(rank, world, port, fail_rank, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from onika_b200 import distributed as D
+    from onika_b200._capi import ONK_IPC_HANDLE_BYTES
+    seen = {}
+
+    def export(buf):                      # stands in for onk_window_export / onk_xs_plan_export
+        if rank == fail_rank:
+            return -2
+        buf.raw = bytes([rank + 1]) * ONK_IPC_HANDLE_BYTES
+        return 0
+
+    def connect(all_handles):             # stands in for onk_window_connect: receives world handles in rank order
+        seen["handles"] = all_handles
+        return 0
+
+    try:
+        D._share_handles(export, connect, None, "a test buffer")
+        q.put((rank, "ok", seen.get("handles")))
+    except RuntimeError as e:
+        q.put((rank, "raised", str(e)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_rank", [-1, 1])
+def test_world2_peer_handle_exchange_is_collective_safe(fail_rank):
+    from onika_b200._capi import ONK_IPC_HANDLE_BYTES
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_handles, args=(r, world, port, fail_rank, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if fail_rank < 0:
+        want = bytes([1]) * ONK_IPC_HANDLE_BYTES + bytes([2]) * ONK_IPC_HANDLE_BYTES
+        assert [r[1] for r in res] == ["ok", "ok"] and all(r[2] == want for r in res)
+    else:                                 # one rank could not export: every rank raises, nobody hangs in a collective
+        assert [r[1] for r in res] == ["raised", "raised"]
