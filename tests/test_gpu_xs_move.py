@@ -32,10 +32,13 @@ def _move(xch, id_min, id_max, before, after, values, dtype):
     mv.plan(ib, ia, lane=0)
     v = torch.from_numpy(values).cuda()
     elem = values.dtype.itemsize * int(np.prod(values.shape[1:], dtype=np.int64))
-    out = PeerWindow(max(after.size, 1) * elem, xch)
+    guard = 512                                              # windows are zero-filled: bytes past the payload must stay zero
+    out = PeerWindow(after.size * elem + guard, xch)
     mv.move(v, out, lane=0)
     torch.cuda.synchronize()
-    got = out.tensor(dtype).cpu().numpy()[:after.size * (elem // values.dtype.itemsize)].reshape((after.size,) + values.shape[1:])
+    raw = out.tensor(torch.uint8).cpu().numpy()
+    assert not raw[after.size * elem:].any(), "scatter wrote past the last element of the window"
+    got = raw[:after.size * elem].view(values.dtype).reshape((after.size,) + values.shape[1:])
     counts = mv.send_counts()
     mv.close()
     out.close()
