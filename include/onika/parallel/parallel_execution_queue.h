@@ -308,6 +308,9 @@ namespace onika { namespace parallel {
     {
       ParallelExecutionContext *keep = nullptr;
       auto* pec = head;
+      // every operation of the list was submitted before this call and a lane runs in order: one synchronisation per
+      // lane covers all of the lane's operations
+      uint64_t lane_synced[4] = { 0 , 0 , 0 , 0 };
       while( pec != nullptr )
       {
         auto* next = pec->m_next;
@@ -315,7 +318,12 @@ namespace onika { namespace parallel {
         if( lane < 0 || pec->m_lane == lane )
         {
           std::lock_guard lk( pec->m_stream->m_mutex );
-          pec->m_stream->wait_nolock();
+          const unsigned l = unsigned( pec->m_lane ) & 255u;
+          if( ( ( lane_synced[l>>6] >> (l&63) ) & 1 ) == 0 )
+          {
+            pec->m_stream->wait_nolock();
+            lane_synced[l>>6] |= uint64_t(1) << (l&63);
+          }
           if( pec->m_scheduled_on_gpu )
           {
             float ms = 0.0f;

@@ -24,7 +24,6 @@ namespace onk
     for (int i = 0; i < nbuf; i++)
     {
       if (!r.stage_dev[i]) ONK_CUDA(cudaMalloc(&r.stage_dev[i], STAGE_BYTES));
-      if (!r.stage_evt[i]) ONK_CUDA(cudaEventCreateWithFlags(&r.stage_evt[i], cudaEventDisableTiming));
     }
     r.stage_bytes = STAGE_BYTES;
     return ONK_OK;

@@ -59,11 +59,9 @@ namespace onk
     std::vector<Lane> lanes;                       // indexed by lane id
     std::unordered_map<const void*, std::pair<size_t,int>> allocs;   // ptr -> (bytes, kind)
     std::atomic<uint64_t> launches{0};
-    // pinned staging for the host-buffer entry points (lazily allocated)
-    void*  stage_host[2] = {nullptr, nullptr};
+    // device staging for the host-buffer entry points (lazily allocated, onk_host.cu)
     void*  stage_dev[4]  = {nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes   = 0;
-    cudaEvent_t stage_evt[4] = {nullptr, nullptr, nullptr, nullptr};
   };
 
   Runtime& rt();

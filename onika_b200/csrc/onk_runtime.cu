@@ -119,9 +119,7 @@ int onk_finalize(void)
     L = Lane{};
   }
   r.lanes.clear();
-  for (int i = 0; i < 2; i++) if (r.stage_host[i]) { cudaFreeHost(r.stage_host[i]); r.stage_host[i] = nullptr; }
   for (int i = 0; i < 4; i++) if (r.stage_dev[i]) { cudaFree(r.stage_dev[i]); r.stage_dev[i] = nullptr; }
-  for (int i = 0; i < 4; i++) if (r.stage_evt[i]) { cudaEventDestroy(r.stage_evt[i]); r.stage_evt[i] = nullptr; }
   r.stage_bytes = 0;
   r.initialised = false;
   r.device = -1;
