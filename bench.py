@@ -287,6 +287,13 @@ def secondary_kernels(ob, torch):
     t = flushed(lambda: cg.cell_sum(3))
     out["C4_cell_sum_128^3"] = {"GB/s": round(alg / t / 1e9, 1), "ms": round(t * 1e3, 4), "algorithmic_bytes": alg,
                                 "arena_bytes": cg.arena_bytes, "particles": npart, "l2": "flushed", "variant": "field e only (8 B/particle + 24 B/cell tables+out)"}
+    del cg
+    fm = cellgrid.FieldMajorCellGrid(counts, nfields=1)
+    fm.columns[0].uniform_(-1, 1)
+    alg = 8 * npart + fm.ncells * (8 + 8)
+    t = flushed(lambda: fm.cell_sum(0))
+    out["C4_cell_sum_128^3_field_major"] = {"GB/s": round(alg / t / 1e9, 1), "ms": round(t * 1e3, 4), "algorithmic_bytes": alg, "particles": npart, "l2": "flushed",
+                                            "variant": "same cells, field-major layout: 8 B/particle + 16 B/cell (offset + out)"}
     return out
 
 

@@ -49,7 +49,7 @@ class CellGrid:
     def host_arena_with_field(self, field: int, values_concat: np.ndarray) -> np.ndarray:
         """host-side construction of the arena bytes with one fp64 field filled cell after cell (test/bench input)"""
         arena = np.zeros(max(self.arena_bytes, 1), np.uint8)
-        a64 = arena[: self.arena_bytes - self.arena_bytes % 8].view(np.float64) if self.arena_bytes >= 8 else arena.view(np.float64)[:0]
+        a64 = arena[: self.arena_bytes - self.arena_bytes % 8].view(np.float64) if self.arena_bytes >= 8 else np.zeros(0, np.float64)
         starts = self.field_byte_offsets(field) // np.uint64(8)
         sizes = self.cell_size_host.astype(np.int64)
         # element index of every particle: start[cell] + local index
@@ -71,4 +71,36 @@ class CellGrid:
         fb = (C.c_uint32 * len(self.field_bytes))(*self.field_bytes)
         check(lib().onk_cell_sum_f64(ptr(self.arena), ptr(self.cell_off), ptr(self.cell_size), ptr(self.cell_cap), self.ncells, self.align,
                                      fb, len(self.field_bytes), field, ptr(sums), ptr(total) if with_total else None, lane))
+        return sums, total
+
+
+class FieldMajorCellGrid:
+    """Cell grid stored FIELD-MAJOR: every field is one contiguous column over all cells, cell c owning
+    [cell_begin[c], cell_begin[c+1]) in each column.  The B200-first layout of config C4: per-cell work streams the
+    columns it needs at full HBM rate instead of picking 128-byte lines out of 512-byte per-cell blocks.
+    Per-cell results are bit-identical to the per-cell FieldArrays layout (same particle order)."""
+
+    def __init__(self, cell_size: np.ndarray, nfields: int = 4, device="cuda"):
+        import torch
+        self.cell_size_host = np.ascontiguousarray(cell_size, dtype=np.uint32)
+        self.ncells = self.cell_size_host.size
+        begin = np.zeros(self.ncells + 1, dtype=np.int64)
+        np.cumsum(self.cell_size_host, dtype=np.int64, out=begin[1:])
+        self.cell_begin_host = begin
+        self.nparticles = int(begin[-1])
+        self.device = device
+        self.cell_begin = torch.from_numpy(begin).to(device)
+        self.columns = [torch.zeros(max(self.nparticles, 1), dtype=torch.float64, device=device)[: self.nparticles] for _ in range(nfields)]
+
+    def set_field(self, field: int, values_concat) -> None:
+        import torch
+        self.columns[field].copy_(torch.as_tensor(values_concat, dtype=torch.float64))
+
+    def cell_sum(self, field: int, with_total: bool = True, lane: int = LANE_DEFAULT):
+        """per-cell sum of `field` (onk_cell_sum_packed_f64); returns (cell_sum tensor, total tensor or None)"""
+        import torch
+        sums = torch.empty(max(self.ncells, 1), dtype=torch.float64, device=self.device)[: self.ncells]
+        total = torch.zeros(1, dtype=torch.float64, device=self.device) if with_total else None
+        check(lib().onk_cell_sum_packed_f64(ptr(self.columns[field]), ptr(self.cell_begin), self.ncells, ptr(sums),
+                                            ptr(total) if with_total else None, lane))
         return sums, total

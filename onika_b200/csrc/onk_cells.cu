@@ -205,6 +205,10 @@ namespace onk
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
   }
 
+  // PACKED: field-major grid -- `arena` is the summed column of all cells back to back and cell_off holds ncells+1 element
+  // offsets (cell c = [cell_off[c], cell_off[c+1])); rows are staged from the even element at or below the cell's first
+  // one (16-byte aligned source), the possible leading stranger is replaced by +0.0 in the fold.
+  template<bool PACKED>
   __global__ void __launch_bounds__(THREADS, ASY_CTAS_PER_SM)
   cell_sum_f64_async_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restrict__ cell_off, const uint32_t* __restrict__ cell_size,
                             const uint32_t* __restrict__ cell_cap, uint64_t ncells, const __grid_constant__ CellFieldParams fp,
@@ -223,7 +227,7 @@ namespace onk
     double thread_total = 0.0;
 
     // per-stage bookkeeping in registers (stage index is a compile-time constant after unrolling)
-    const uint8_t* col_s[ASY_STAGES]; uint32_t sz_s[ASY_STAGES]; uint32_t staged_s[ASY_STAGES];
+    const uint8_t* col_s[ASY_STAGES]; uint32_t sz_s[ASY_STAGES]; uint32_t staged_s[ASY_STAGES]; uint32_t odd_s[ASY_STAGES];
 
     // tables of the NEXT step to be issued, loaded one issue ahead so that their DRAM latency is never on the critical path
     uint64_t nx_off = 0; uint32_t nx_sz = 0, nx_cap = 0;
@@ -231,7 +235,17 @@ namespace onk
     {
       const uint64_t c = (warp_global + step * nwarps) * 32 + lane;
       nx_off = 0; nx_sz = 0; nx_cap = 0;
-      if (step < my_steps && c < ncells) { nx_off = __ldg(cell_off + c); nx_sz = __ldg(cell_size + c); nx_cap = __ldg(cell_cap + c); }
+      if (step < my_steps && c < ncells)
+      {
+        if constexpr (PACKED)
+        {
+          const uint64_t b = __ldg(cell_off + c), e = __ldg(cell_off + c + 1);
+          nx_cap = (uint32_t)(b & 1ull);                     // leading stranger
+          nx_off = (b - nx_cap) * 8ull;                      // byte offset of the even element the row starts at
+          nx_sz = (uint32_t)(e - b) + nx_cap;                // row length including the stranger
+        }
+        else { nx_off = __ldg(cell_off + c); nx_sz = __ldg(cell_size + c); nx_cap = __ldg(cell_cap + c); }
+      }
     };
     load_next_tables(0);
 
@@ -239,7 +253,8 @@ namespace onk
     {
       const uint64_t off = nx_off; const uint32_t sz = nx_sz, cap = nx_cap;
       load_next_tables(step + 1);                        // steps are issued in order: the next call is for step+1
-      const uint8_t* col = arena + off + cell_field_offset(cap, fp);
+      const uint8_t* col = PACKED ? arena + off : arena + off + cell_field_offset(cap, fp);
+      if constexpr (PACKED) odd_s[stage] = cap;
       uint32_t n_st = sz < (uint32_t)ASY_RCAP ? sz : (uint32_t)ASY_RCAP;
       if ((((uintptr_t)col) & 15u) != 0) n_st = 0;                 // unaligned column: this lane reads global memory itself
       col_s[stage] = col; sz_s[stage] = sz; staged_s[stage] = n_st;
@@ -291,7 +306,12 @@ namespace onk
           double s = 0.0;
           // particle order; zero-filled slots add +0.0, which leaves s unchanged
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) { double x0, x1; lds128(row + i, x0, x1); s = __dadd_rn(s, x0); s = __dadd_rn(s, x1); }
+          for (int i = 0; i < 16; i += 2)
+          {
+            double x0, x1; lds128(row + i, x0, x1);
+            if constexpr (PACKED) { if (i == 0 && odd_s[sgi] != 0u && n_st != 0u) x0 = 0.0; }
+            s = __dadd_rn(s, x0); s = __dadd_rn(s, x1);
+          }
           if (n_st > 16u)
           {
 #pragma unroll
@@ -300,12 +320,163 @@ namespace onk
           if (sz > n_st)                                   // long or unaligned cells: the rest straight from global memory
           {
             const double* e = reinterpret_cast<const double*>(col_s[sgi]);
-            for (uint32_t i = n_st; i < sz; i++) s = __dadd_rn(s, ld_stream_ro1(e + i));
+            uint32_t i0 = n_st;
+            if constexpr (PACKED) { if (n_st == 0u) i0 = odd_s[sgi]; }     // nothing staged (unaligned column): skip the stranger here
+            for (uint32_t i = i0; i < sz; i++) s = __dadd_rn(s, ld_stream_ro1(e + i));
           }
           const uint64_t c = (warp_global + k * nwarps) * 32 + lane;
           if (c < ncells) { cell_sum[c] = s; thread_total = __dadd_rn(thread_total, s); }
           __syncwarp();                                    // every lane is done reading this stage
           if (k + ASY_STAGES < my_steps) issue(sgi, k + ASY_STAGES);
+          else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    cell_total_finish(thread_total, partials, ticket, total);
+  }
+}
+
+namespace onk
+{
+  // ------------------------------------------------------------------------------------------------------------
+  // FIELD-MAJOR cell grid: the summed field of ALL cells is one contiguous column, cell c owning the run
+  // [cell_begin[c], cell_begin[c+1]) (what an exaNBody-style grid calls its cell offsets).  The per-cell blocks of the
+  // reference layout force 128 useful bytes out of every 512 through the memory system (DRAM traffic 1.4x the
+  // algorithmic bytes, kernel above); in this layout the kernel is a pure stream: a CTA takes 256 consecutive cells per
+  // step, moves their values global -> shared with 8-byte cp.async (LDGSTS.64, consecutive lanes = consecutive values,
+  // 3 tiles in flight per SM) and thread t folds cell t in particle order from shared memory -- same bits as the
+  // per-cell host loop.  Shared-memory index i lives at i + i/16: with 16-particle cells the 256 threads would
+  // otherwise start 128 bytes apart, i.e. all in the same bank.
+  constexpr int PK_CELLS  = THREADS;                 // cells per tile (one per thread)
+  constexpr int PK_CAP    = 4352;                    // values staged per tile (17 per cell on average: Poisson(16) tiles fit with 4 sigma to
+                                                     // spare; whatever exceeds it is read from global memory by the owning thread)
+  constexpr int PK_ROW    = PK_CAP + PK_CAP / 16 + 16;
+  template<int STAGES> constexpr size_t pk_smem() { return (size_t)STAGES * PK_ROW * sizeof(double); }
+
+  // Tile staging: values go global -> shared as 16-byte pieces (LDGSTS.128 bypassing L1; the 8-byte form drags three
+  // no-op shared loads per copy along on sm_100), starting at the 16-byte aligned element at or below the tile's first
+  // one.  Local value i lives in slot i + 2*(i/32): pairs stay together and 16-byte aligned, and runs that start a
+  // multiple of 16 values apart (uniform 16-particle cells) spread over the banks instead of piling up on one.
+  // STAGES tiles per CTA ring, CTAS resident CTAs per SM: the folds of one CTA overlap the copies of the others.
+  __device__ __forceinline__ void cp_async16(unsigned dst, const void* src)
+  {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+  }
+  __device__ __forceinline__ double lds64_u32(unsigned a)
+  {
+    double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v;
+  }
+  __device__ __forceinline__ void lds128_u32(unsigned a, double& x0, double& x1)
+  {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(a) : "memory");
+  }
+
+  template<int STAGES, int CTAS>
+  __global__ void __launch_bounds__(THREADS, CTAS)
+  cell_sum_packed_f64_kernel(const double* __restrict__ values, const uint64_t* __restrict__ cell_begin, uint64_t ncells,
+                             double* __restrict__ cell_sum, double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ total)
+  {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    const unsigned ring = smem_u32(dyn_smem);
+    constexpr unsigned STAGE_BYTES = PK_ROW * 8u;
+    constexpr int COPY_ITERS = (PK_CAP / 2 + THREADS - 1) / THREADS;       // 16-byte pieces per thread and tile
+    const uint64_t ntiles = (ncells + PK_CELLS - 1) / PK_CELLS;
+    const uint64_t my_tiles = (blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const unsigned parity = (unsigned)(((uintptr_t)values >> 3) & 1u);   // element g is 16-byte aligned iff g + parity is even
+    const unsigned pair_slot0 = (threadIdx.x + (threadIdx.x >> 4)) * 16u;  // byte offset of pair j = tid + 256*it: pair_slot0 + 272*16*it
+    const uint64_t tile_stride = (uint64_t)gridDim.x * PK_CELLS;
+    double thread_total = 0.0;
+
+    uint32_t pb_s[STAGES], pe_s[STAGES], cnt_s[STAGES];
+
+    // offsets of the NEXT tile to issue, loaded one issue ahead (their latency never sits in front of the data loads)
+    uint64_t nx_b = 0, nx_e = 0, nx_base = 0, nx_end = 0;
+    uint64_t nx_c0 = (uint64_t)blockIdx.x * PK_CELLS;                    // first cell of the next tile whose tables get loaded
+    auto load_next_tables = [&]()
+    {
+      nx_b = nx_e = nx_base = nx_end = 0;
+      if (nx_c0 < ncells)
+      {
+        const uint64_t c = nx_c0 + threadIdx.x;
+        const uint64_t cend = (nx_c0 + PK_CELLS < ncells) ? nx_c0 + PK_CELLS : ncells;
+        nx_base = __ldg(cell_begin + nx_c0); nx_end = __ldg(cell_begin + cend);
+        if (c < ncells) { nx_b = __ldg(cell_begin + c); nx_e = __ldg(cell_begin + c + 1); } else { nx_b = nx_e = nx_end; }
+      }
+      nx_c0 += tile_stride;
+    };
+    load_next_tables();
+
+    auto issue = [&](int stage)
+    {
+      // the staged window starts at the aligned element at or below the tile's first value: one stranger in front at most
+      const uint64_t lead = (nx_base + parity) & 1ull;
+      const uint64_t span = nx_end - nx_base + lead;
+      const uint64_t rb = nx_b - nx_base + lead, re = nx_e - nx_base + lead;
+      pb_s[stage] = rb < 0xffffffffull ? (uint32_t)rb : 0xffffffffu;
+      pe_s[stage] = re < 0xffffffffull ? (uint32_t)re : 0xffffffffu;
+      const uint32_t cnt = span < (uint64_t)PK_CAP ? (uint32_t)span : (uint32_t)PK_CAP;
+      cnt_s[stage] = cnt;
+      const uint4* src = reinterpret_cast<const uint4*>(values + ((int64_t)nx_base - (int64_t)lead)) + threadIdx.x;
+      load_next_tables();
+      const unsigned dst = ring + (unsigned)stage * STAGE_BYTES + pair_slot0;
+      const uint32_t npairs = cnt >> 1;
+#pragma unroll
+      for (int it = 0; it < COPY_ITERS; it++)
+        if (threadIdx.x + (unsigned)it * THREADS < npairs) cp_async16(dst + (unsigned)it * (272u * 16u), src + it * THREADS);
+      if ((cnt & 1u) != 0u && threadIdx.x == (npairs & (THREADS - 1u)))       // odd tail: 8 valid bytes, the rest zero-filled
+        cp_async16_zfill(dst + (npairs / THREADS) * (272u * 16u), src + (npairs / THREADS) * THREADS, 8u);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+#pragma unroll
+    for (int sgi = 0; sgi < STAGES; sgi++)
+    {
+      if ((uint64_t)sgi < my_tiles) issue(sgi);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
+    uint64_t c = (uint64_t)blockIdx.x * PK_CELLS + threadIdx.x;           // this thread's cell in the tile being folded
+    for (uint64_t k0 = 0; k0 < my_tiles; k0 += STAGES)
+    {
+#pragma unroll
+      for (int sgi = 0; sgi < STAGES; sgi++)
+      {
+        const uint64_t k = k0 + sgi;
+        if (k < my_tiles)                                  // CTA-uniform
+        {
+          asm volatile("cp.async.wait_group %0;" :: "n"(STAGES - 1) : "memory");
+          __syncthreads();                                 // every thread's pieces of this tile have landed
+          const unsigned tile = ring + (unsigned)sgi * STAGE_BYTES;
+          const uint32_t cnt = cnt_s[sgi], pb = pb_s[sgi], pe = pe_s[sgi];
+          const uint32_t staged_end = pe < cnt ? pe : cnt;
+          double s = 0.0;
+          if (pb < staged_end)                             // particle order; value p sits in slot p + 2*(p/32)
+          {
+            uint32_t p = pb;
+            unsigned a = tile + (p + 2u * (p >> 5)) * 8u;
+            if (p & 1u) { s = __dadd_rn(s, lds64_u32(a)); ++p; a += (p & 31u) ? 8u : 24u; }
+            uint32_t npair = (staged_end - p) >> 1;
+            uint32_t r = (32u - (p & 31u)) >> 1;           // pairs left before the next skipped slot pair
+            for (; npair != 0u; --npair)
+            {
+              double x0, x1; lds128_u32(a, x0, x1);
+              s = __dadd_rn(s, x0); s = __dadd_rn(s, x1);
+              a += 16u;
+              if (--r == 0u) { a += 16u; r = 16u; }
+            }
+            if ((staged_end - p) & 1u) s = __dadd_rn(s, lds64_u32(a));
+          }
+          if (pe > cnt && c < ncells)                      // long tiles: the rest of the run straight from global memory
+          {
+            const uint64_t gb = __ldg(cell_begin + c), ge = __ldg(cell_begin + c + 1);
+            const uint64_t staged_g = gb + (uint64_t)(staged_end > pb ? staged_end - pb : 0u);
+            for (uint64_t g = staged_g; g < ge; g++) s = __dadd_rn(s, ld_stream_ro1(values + g));
+          }
+          if (c < ncells) { cell_sum[c] = s; thread_total = __dadd_rn(thread_total, s); }
+          c += tile_stride;
+          __syncthreads();                                 // everybody is done reading this stage
+          if (k + STAGES < my_tiles) issue(sgi);
           else asm volatile("cp.async.commit_group;" ::: "memory");
         }
       }
@@ -363,14 +534,64 @@ int onk_cell_sum_f64(const void* arena_dev, const uint64_t* cell_off_dev, const 
   if (variant == 1)
   {
     static bool configured = false;
-    if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_f64_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ASY_SMEM)); configured = true; }
+    if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_f64_async_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ASY_SMEM)); configured = true; }
     grid = grid_for(ncells, cells_per_cta, ASY_CTAS_PER_SM);
-    cell_sum_f64_async_kernel<<<grid, THREADS, ASY_SMEM, L->stream>>>((const uint8_t*)arena_dev, cell_off_dev, cell_size_dev, cell_cap_dev, ncells, fp,
+    cell_sum_f64_async_kernel<false><<<grid, THREADS, ASY_SMEM, L->stream>>>((const uint8_t*)arena_dev, cell_off_dev, cell_size_dev, cell_cap_dev, ncells, fp,
                                                                     cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev);
   }
   else
     cell_sum_f64_kernel<<<grid, THREADS, 0, L->stream>>>((const uint8_t*)arena_dev, cell_off_dev, cell_size_dev, cell_cap_dev, ncells, fp,
                                                          cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev);
+  ONK_CHECK_LAUNCH(); count_launch();
+  return ONK_OK;
+}
+
+int onk_cell_sum_packed_f64(const double* values_dev, const uint64_t* cell_begin_dev, uint64_t ncells,
+                            double* cell_sum_dev, double* total_dev, int lane)
+{
+  Lane* L; if (int rc = lane_get(lane, &L)) return rc;
+  if (ncells == 0)
+  {
+    if (total_dev) ONK_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(double), L->stream));
+    return ONK_OK;
+  }
+  ONK_REQUIRE(cell_begin_dev && cell_sum_dev, "onk_cell_sum_packed_f64: null pointer");
+  ONK_REQUIRE(((uintptr_t)values_dev & 7) == 0, "onk_cell_sum_packed_f64: values are not 8-byte aligned");
+  // variants (env ONK_PK_CFG, tuning only): "rows" = the row-staged kernel of the per-cell layout fed from the packed
+  // column (83 us on 128^3 cells); "SxC" = CTA-tile kernel with ring depth S and C resident CTAs per SM:
+  // 3x2 77 us, 2x3 67 us, 1x6 66 us, 1x5 64 us (default) -- resident warps, not ring depth, hide the latency here
+  static const int cfg = []{ const char* e = getenv("ONK_PK_CFG");
+                             if (!e) return 3;
+                             if (e[0] == 'r') return 2;
+                             if (e[0] == '3') return 0;
+                             if (e[0] == '2') return 1;
+                             return e[2] == '6' ? 4 : 3; }();
+  if (cfg == 2)
+  {
+    static bool rows_configured = false;
+    if (!rows_configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_f64_async_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ASY_SMEM)); rows_configured = true; }
+    unsigned g = grid_for(ncells, (THREADS / 32) * 32, ASY_CTAS_PER_SM);
+    if (g > (unsigned)MAX_PARTIALS) g = MAX_PARTIALS;
+    cell_sum_f64_async_kernel<true><<<g, THREADS, ASY_SMEM, L->stream>>>((const uint8_t*)values_dev, cell_begin_dev, nullptr, nullptr, ncells, CellFieldParams{},
+                                                                       cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev);
+    ONK_CHECK_LAUNCH(); count_launch();
+    return ONK_OK;
+  }
+  static bool configured = false;
+  if (!configured)
+  {
+    ONK_CUDA(cudaFuncSetAttribute(cell_sum_packed_f64_kernel<3,2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pk_smem<3>()));
+    ONK_CUDA(cudaFuncSetAttribute(cell_sum_packed_f64_kernel<2,3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pk_smem<2>()));
+    ONK_CUDA(cudaFuncSetAttribute(cell_sum_packed_f64_kernel<1,5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pk_smem<1>()));
+    ONK_CUDA(cudaFuncSetAttribute(cell_sum_packed_f64_kernel<1,6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pk_smem<1>()));
+    configured = true;
+  }
+  const unsigned ctas = cfg == 0 ? 2u : cfg == 1 ? 3u : cfg == 3 ? 5u : 6u;
+  unsigned grid = grid_for(ncells, PK_CELLS, ctas);
+  if (grid > (unsigned)MAX_PARTIALS) grid = MAX_PARTIALS;
+#define ONK_PK_LAUNCH(S, C) cell_sum_packed_f64_kernel<S,C><<<grid, THREADS, pk_smem<S>(), L->stream>>>(values_dev, cell_begin_dev, ncells, cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev)
+  if (cfg == 0) ONK_PK_LAUNCH(3, 2); else if (cfg == 1) ONK_PK_LAUNCH(2, 3); else if (cfg == 3) ONK_PK_LAUNCH(1, 5); else ONK_PK_LAUNCH(1, 6);
+#undef ONK_PK_LAUNCH
   ONK_CHECK_LAUNCH(); count_launch();
   return ONK_OK;
 }

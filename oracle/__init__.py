@@ -95,6 +95,7 @@ class _Oracle:
             L.orc_cell_grid_layout.restype = C.c_uint64
             L.orc_cell_grid_layout.argtypes = [_u32p, C.c_uint64, C.c_uint64, C.c_uint64, _u32p, C.c_int, C.c_uint64, _u32p, _u64p]
             L.orc_lane_sequence_f64.argtypes = [_dp, _dp, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double]
+            L.orc_cell_sum_packed_f64.argtypes = [_dp, _u64p, C.c_uint64, _dp, _dp]
             L.orc_xs_process_for_id.restype = C.c_int
             L.orc_xs_process_for_id.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_uint64]
             L.orc_xs_range_start.restype = C.c_uint64
@@ -408,6 +409,17 @@ def _ref_xs_data_move(self, id_min: int, id_max: int, ids_before, ids_after, in8
     return sch, out8, out32
 
 
+def _orc_cell_sum_packed(self, values, cell_begin):
+    """oracle.c:orc_cell_sum_packed_f64 -> (cell_sum, total)"""
+    values = _f64(values)
+    cell_begin = np.ascontiguousarray(cell_begin, dtype=np.uint64)
+    sums = np.zeros(cell_begin.size - 1)
+    total = C.c_double(0.0)
+    self.lib.orc_cell_sum_packed_f64(_ptr(values, _dp), _ptr(cell_begin, _u64p), sums.size, _ptr(sums, _dp), C.byref(total))
+    return sums, total.value
+
+
+_Oracle.cell_sum_packed = _orc_cell_sum_packed
 _Oracle.xs_comm_scheme = _orc_xs_comm_scheme
 _Oracle.xs_data_move = _orc_xs_data_move
 _Oracle.xs_process_for_id = lambda self, i, nprocs, lo, hi: self.lib.orc_xs_process_for_id(int(i), nprocs, lo, hi)

@@ -423,3 +423,17 @@ void orc_xs_data_move(int world, const uint64_t* before_off, const uint64_t* aft
       memcpy( out + j*elem_bytes , comm_output + ( after_off[r] + (uint64_t)recv_indices[j] ) * elem_bytes , elem_bytes );
   free(comm_input); free(comm_output);
 }
+
+/* field-major cell grid: per-cell fold in particle order, total in cell order (same functor as orc_cell_sum_f64) */
+void orc_cell_sum_packed_f64(const double* values, const uint64_t* cell_begin, uint64_t ncells, double* cell_sum, double* total)
+{
+  double t = 0.0;
+  for(uint64_t c=0;c<ncells;c++)
+  {
+    double s = 0.0;
+    for(uint64_t p=cell_begin[c];p<cell_begin[c+1];p++) s += values[p];
+    cell_sum[c] = s;
+    t += s;
+  }
+  if( total != NULL ) *total = t;
+}

@@ -79,6 +79,9 @@ void orc_soatl_repack(uint8_t* dst, uint64_t dst_align, uint64_t dst_capacity,
 void orc_cell_sum_f64(const uint8_t* arena, const uint64_t* cell_off, const uint32_t* cell_size, const uint32_t* cell_cap,
                       uint64_t ncells, uint64_t align, const uint32_t* field_sizes, int nfields, int field,
                       double* cell_sum, double* total);
+/* the same sums over a field-major grid: values of all cells back to back, cell c = [cell_begin[c], cell_begin[c+1]).
+ * Equals oracle/_ref's ref_cell_sum (the reference's block_parallel_for over per-cell FieldArrays) on the same particles. */
+void orc_cell_sum_packed_f64(const double* values, const uint64_t* cell_begin, uint64_t ncells, double* cell_sum, double* total);
 /* builds cell_cap / cell_off for given sizes (capacity = update_capacity(size,0,chunk); offsets aligned to
  * `cell_align`); returns arena bytes */
 uint64_t orc_cell_grid_layout(const uint32_t* cell_size, uint64_t ncells, uint64_t align, uint64_t chunk,

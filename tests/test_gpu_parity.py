@@ -404,6 +404,69 @@ def test_cell_sum_config_c4_full_size_properties(ob):
     assert host(total)[0] == float(counts.sum())
 
 
+def test_field_major_cell_sum_golden_and_reference_inputs(ob, gold, orc):
+    """field-major grid (onk_cell_sum_packed_f64): the golden vector was produced by the reference's block_parallel_for over
+    per-cell FieldArrays from exactly these (counts, e) -- the per-cell bits must be the same in this layout"""
+    from tests._inputs import unhx
+    from onika_b200 import cellgrid
+    g = gold["cell_sum"]
+    counts = np.array(g["counts"], np.uint32)
+    e = unhx(g["e"])
+    fm = cellgrid.FieldMajorCellGrid(counts)
+    fm.set_field(3, e)
+    sums, total = fm.cell_sum(3)
+    ob.lane_sync()
+    assert np.array_equal(host(sums), unhx(g["cell_sum"]))
+    assert abs(host(total)[0] - float.fromhex(g["total"])) <= SUM_RTOL * np.abs(e).sum()
+    so, to = orc.cell_sum_packed(e, fm.cell_begin_host)
+    assert np.array_equal(so, unhx(g["cell_sum"])) and to == float.fromhex(g["total"])
+
+
+@pytest.mark.parametrize("side,mean,maxn", [(1, 16.0, 64), (7, 16.0, 64), (40, 16.0, 64), (24, 40.0, 400), (16, 0.3, 4)])
+def test_field_major_cell_sum_vs_oracle(ob, orc, side, mean, maxn):
+    """ragged cells: empty ones, tiles whose values exceed the staged capacity (mean 40 > 24 per cell: the rest is read
+    from global memory), a last partial tile"""
+    from tests._inputs import lcg_uniform, poisson_counts
+    from onika_b200 import cellgrid
+    counts = poisson_counts(side ** 3, mean, 42, 0, maxn)
+    if maxn > 64:
+        counts[::53] = maxn
+    counts[min(5, counts.size - 1)] = 0
+    e = lcg_uniform(int(counts.sum()), 40, -1, 1)
+    fm = cellgrid.FieldMajorCellGrid(counts)
+    fm.set_field(0, e)
+    sums, total = fm.cell_sum(0)
+    ob.lane_sync()
+    so, to = orc.cell_sum_packed(e, fm.cell_begin_host)
+    assert np.array_equal(host(sums), so)
+    assert abs(host(total)[0] - to) <= SUM_RTOL * max(np.abs(e).sum(), 1e-300)
+    s2, t2 = fm.cell_sum(0)
+    ob.lane_sync()
+    assert host(t2)[0] == host(total)[0]
+    # same particles in the reference layout (per-cell FieldArrays blocks): same per-cell bits
+    cg = cellgrid.CellGrid(counts, 64, 16, (8, 8, 8, 8), 64)
+    cg.upload(cg.host_arena_with_field(3, e))
+    s3, _ = cg.cell_sum(3)
+    ob.lane_sync()
+    assert np.array_equal(host(s3), host(sums))
+
+
+def test_field_major_cell_sum_config_c4_full_size(ob):
+    from tests._inputs import poisson_counts
+    from onika_b200 import cellgrid
+    counts = poisson_counts(128 ** 3)
+    fm = cellgrid.FieldMajorCellGrid(counts, nfields=1)
+    fm.set_field(0, np.ones(int(counts.sum())))
+    sums, total = fm.cell_sum(0)
+    ob.lane_sync()
+    assert np.array_equal(host(sums), counts.astype(np.float64))
+    assert host(total)[0] == float(counts.sum())
+    empty = cellgrid.FieldMajorCellGrid(np.zeros(0, np.uint32), nfields=1)
+    s0, t0 = empty.cell_sum(0)
+    ob.lane_sync()
+    assert s0.numel() == 0 and host(t0)[0] == 0.0
+
+
 # ---------------------------------------------------------------- op bracket, host-buffer paths, errors
 def test_op_bracket_return_data_and_timing(ob):
     """the return-data protocol of schedule(): host value copied in before, out after (parallel_execution_queue.cpp:331-352)"""

@@ -92,6 +92,12 @@ def test_cell_sum_32k_cells(orc, ref):
     sums, total = orc.cell_sum(arena, off, counts, cap, 64, fields, 3)
     assert np.array_equal(sums, s_ref)
     assert abs(total - t_ref) <= 1e-12 * np.abs(e).sum()
+    # field-major restatement (values cell after cell + offsets): same per-cell bits as the reference's FieldArrays loop
+    begin = np.zeros(counts.size + 1, np.uint64)
+    begin[1:] = np.cumsum(counts, dtype=np.uint64)
+    sp, tp = orc.cell_sum_packed(e, begin)
+    assert np.array_equal(sp, s_ref)
+    assert abs(tp - t_ref) <= 1e-12 * np.abs(e).sum()
 
 
 def test_parallel_for_3d(orc, ref):
