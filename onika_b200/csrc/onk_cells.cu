@@ -50,10 +50,11 @@ namespace onk
 
 
   // grid-wide total: per-thread partials -> block reduction -> ticketed two-pass finish (fixed order)
+  template<unsigned NT = THREADS>
   __device__ __forceinline__ void cell_total_finish(double thread_total, double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ total)
   {
     if (total == nullptr) return;
-    const double blk = block_reduce<ONK_OP_SUM, THREADS>(thread_total);
+    const double blk = block_reduce<ONK_OP_SUM, NT>(thread_total);
     __shared__ bool is_last;
     if (threadIdx.x == 0)
     {
@@ -66,8 +67,8 @@ namespace onk
     {
       __threadfence();
       double r = 0.0;
-      for (unsigned i = threadIdx.x; i < gridDim.x; i += THREADS) r = __dadd_rn(r, __ldcg(partials + i));
-      r = block_reduce<ONK_OP_SUM, THREADS>(r);
+      for (unsigned i = threadIdx.x; i < gridDim.x; i += NT) r = __dadd_rn(r, __ldcg(partials + i));
+      r = block_reduce<ONK_OP_SUM, NT>(r);
       if (threadIdx.x == 0) { *total = r; *ticket = 0u; }
     }
   }
@@ -193,11 +194,12 @@ namespace onk
   // 146 us on 128^3 cells against 105 us for the register-staged kernel above: ~20 cycles per small bulk request and
   // SM, the request rate and not the bandwidth being the limit at 128-256 B per copy.)
   // Particles beyond ASY_RCAP, columns that are not 16-byte aligned: summed straight from global memory by their lane.
-  constexpr int ASY_STAGES = 3;
-  constexpr int ASY_RCAP = 32;                       // particles staged per cell (two 128-byte lines)
-  constexpr int ASY_ROW = ASY_RCAP + 2;              // doubles per row: 272 B (16-byte multiple, staggers banks)
+  // shape of the ring: NWARPS warps per CTA (one CTA per SM), STAGES steps in flight per warp, RCAP particles staged per
+  // cell (first 128-byte line + whatever of the second one fits); rows are RCAP+2 doubles apart (16-byte multiple, staggers
+  // the banks).  8 warps x 3 stages x 32 particles and 12 x 2 x 32 fill the same 204 KB; more resident warps hide more of
+  // the table -> address -> data latency, deeper rings keep more bytes in flight per warp.
   constexpr unsigned ASY_CTAS_PER_SM = 1;
-  constexpr size_t ASY_SMEM = (size_t)(THREADS / 32) * ASY_STAGES * 32 * ASY_ROW * sizeof(double);
+  template<int NWARPS, int STAGES, int RCAP> constexpr size_t asy_smem() { return (size_t)NWARPS * STAGES * 32 * (RCAP + 2) * sizeof(double); }
 
   __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
   __device__ __forceinline__ void cp_async16_zfill(unsigned dst, const void* src, unsigned src_bytes)
@@ -208,20 +210,23 @@ namespace onk
   // PACKED: field-major grid -- `arena` is the summed column of all cells back to back and cell_off holds ncells+1 element
   // offsets (cell c = [cell_off[c], cell_off[c+1])); rows are staged from the even element at or below the cell's first
   // one (16-byte aligned source), the possible leading stranger is replaced by +0.0 in the fold.
-  template<bool PACKED>
-  __global__ void __launch_bounds__(THREADS, ASY_CTAS_PER_SM)
+  template<bool PACKED, int NWARPS, int ASY_STAGES, int ASY_RCAP>
+  __global__ void __launch_bounds__(NWARPS * 32, ASY_CTAS_PER_SM)
   cell_sum_f64_async_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restrict__ cell_off, const uint32_t* __restrict__ cell_size,
                             const uint32_t* __restrict__ cell_cap, uint64_t ncells, const __grid_constant__ CellFieldParams fp,
                             double* __restrict__ cell_sum, double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ total)
   {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
+    constexpr int ASY_ROW = ASY_RCAP + 2;
+    constexpr unsigned NT = NWARPS * 32;
+    static_assert(ASY_RCAP >= 16 && ASY_RCAP <= 32 && ASY_RCAP % 2 == 0, "first line fully staged, second line partly");
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const unsigned piece = lane & 7u;          // which 16-byte piece of a 128-byte line this lane moves
     const unsigned g4 = lane >> 3;             // cell within the group of 4 served by one cp.async instruction
     double* ring = reinterpret_cast<double*>(dyn_smem) + (size_t)w * ASY_STAGES * 32 * ASY_ROW;
 
-    const uint64_t warp_global = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * THREADS) >> 5;
+    const uint64_t warp_global = ((uint64_t)blockIdx.x * NT + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * NT) >> 5;
     const uint64_t nsteps_total = (ncells + 31) / 32;
     const uint64_t my_steps = (warp_global < nsteps_total) ? (nsteps_total - warp_global + nwarps - 1) / nwarps : 0;
     double thread_total = 0.0;
@@ -277,7 +282,7 @@ namespace onk
         {
           const uint32_t o = 128u + piece * 16u;
           const uint32_t valid = (nb > o) ? ((nb - o < 16u) ? nb - o : 16u) : 0u;
-          cp_async16_zfill(dst + 128u, a + o, valid);
+          if (o < (uint32_t)ASY_RCAP * 8u) cp_async16_zfill(dst + 128u, a + o, valid);     // the row ends at RCAP particles
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -315,7 +320,7 @@ namespace onk
           if (n_st > 16u)
           {
 #pragma unroll
-            for (int i = 16; i < 32; i += 2) { double x0, x1; lds128(row + i, x0, x1); s = __dadd_rn(s, x0); s = __dadd_rn(s, x1); }
+            for (int i = 16; i < ASY_RCAP; i += 2) { double x0, x1; lds128(row + i, x0, x1); s = __dadd_rn(s, x0); s = __dadd_rn(s, x1); }
           }
           if (sz > n_st)                                   // long or unaligned cells: the rest straight from global memory
           {
@@ -333,7 +338,7 @@ namespace onk
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    cell_total_finish(thread_total, partials, ticket, total);
+    cell_total_finish<NT>(thread_total, partials, ticket, total);
   }
 }
 
@@ -530,14 +535,18 @@ int onk_cell_sum_f64(const void* arena_dev, const uint64_t* cell_off_dev, const 
   const unsigned cells_per_cta = (THREADS / 32) * 32;
   unsigned grid = grid_for(ncells, cells_per_cta, CELL_CTAS_PER_SM);
   if (grid > (unsigned)MAX_PARTIALS) grid = MAX_PARTIALS;
-  static const int variant = []{ const char* e = getenv("ONK_CELL_KERNEL"); return (e && e[0] == 'l') ? 0 : 1; }();   // "ldg" | "async" (default)
+  // "ldg" = register-staged kernel; default = cp.async ring of 8 warps x 3 stages x 32 particles.  Other shapes were
+  // measured on 128^3 cells and dropped: 12 warps x 2 stages x 32 -> same 81 us, 16 x 2 x 24 -> 85 us, 16 x 3 x 16 -> 122 us
+  // (cells longer than the staged part fall back to per-lane global loads): this layout is bound by its DRAM access
+  // pattern (0.42 GB of 64-byte bursts for 0.30 GB of payload), not by resident warps.
+  static const int variant = []{ const char* e = getenv("ONK_CELL_KERNEL"); return (e && e[0] == 'l') ? 0 : 1; }();
   if (variant == 1)
   {
     static bool configured = false;
-    if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_f64_async_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ASY_SMEM)); configured = true; }
+    if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_f64_async_kernel<false,8,3,32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asy_smem<8,3,32>())); configured = true; }
     grid = grid_for(ncells, cells_per_cta, ASY_CTAS_PER_SM);
-    cell_sum_f64_async_kernel<false><<<grid, THREADS, ASY_SMEM, L->stream>>>((const uint8_t*)arena_dev, cell_off_dev, cell_size_dev, cell_cap_dev, ncells, fp,
-                                                                    cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev);
+    cell_sum_f64_async_kernel<false,8,3,32><<<grid, THREADS, asy_smem<8,3,32>(), L->stream>>>((const uint8_t*)arena_dev, cell_off_dev, cell_size_dev, cell_cap_dev, ncells, fp,
+                                                                                             cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev);
   }
   else
     cell_sum_f64_kernel<<<grid, THREADS, 0, L->stream>>>((const uint8_t*)arena_dev, cell_off_dev, cell_size_dev, cell_cap_dev, ncells, fp,
@@ -569,10 +578,10 @@ int onk_cell_sum_packed_f64(const double* values_dev, const uint64_t* cell_begin
   if (cfg == 2)
   {
     static bool rows_configured = false;
-    if (!rows_configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_f64_async_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ASY_SMEM)); rows_configured = true; }
+    if (!rows_configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_f64_async_kernel<true,8,3,32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asy_smem<8,3,32>())); rows_configured = true; }
     unsigned g = grid_for(ncells, (THREADS / 32) * 32, ASY_CTAS_PER_SM);
     if (g > (unsigned)MAX_PARTIALS) g = MAX_PARTIALS;
-    cell_sum_f64_async_kernel<true><<<g, THREADS, ASY_SMEM, L->stream>>>((const uint8_t*)values_dev, cell_begin_dev, nullptr, nullptr, ncells, CellFieldParams{},
+    cell_sum_f64_async_kernel<true,8,3,32><<<g, THREADS, asy_smem<8,3,32>(), L->stream>>>((const uint8_t*)values_dev, cell_begin_dev, nullptr, nullptr, ncells, CellFieldParams{},
                                                                        cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev);
     ONK_CHECK_LAUNCH(); count_launch();
     return ONK_OK;
