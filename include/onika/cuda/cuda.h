@@ -52,6 +52,8 @@
 #  else
 #    define ONIKA_DEVICE_KERNEL_BOUNDS(T,B)
 #  endif
+   // user kernels launched directly on a lane's stream (STREAM = ParallelExecutionStream::m_cu_stream / getThreadStream(lane))
+#  define ONIKA_CU_LAUNCH_KERNEL(GDIM,BDIM,SHMEM,STREAM,FUNC, ... ) FUNC <<< GDIM , BDIM , SHMEM , STREAM >>> ( __VA_ARGS__ )
 #else
 #  define ONIKA_HOST_FUNC
 #  define ONIKA_DEVICE_FUNC
@@ -61,6 +63,10 @@
 #  define ONIKA_CU_GRID_CONSTANT
 #  define ONIKA_BUILTIN_ASSUME_ALIGNED(p,a) __builtin_assume_aligned(p,a)
 #  define ONIKA_DEVICE_KERNEL_BOUNDS(T,B)
+   // translation units compiled by the host compiler cannot launch kernels: same diagnostic + abort as the reference
+#  define ONIKA_CU_LAUNCH_KERNEL(GDIM,BDIM,SHMEM,STREAM,FUNC, ... ) do { \
+     std::printf("Illegal call to Kernel %s<<<...>>>(...) with no GPU support, in %s at %s:%d\n", #FUNC, __FUNCTION__, __FILE__, __LINE__); \
+     std::abort(); } while(false)
 #endif
 
 namespace onika

@@ -54,6 +54,7 @@ static inline constexpr auto onikaMemcpyHostToDevice = cudaMemcpyHostToDevice;
 #define ONIKA_CU_MEMCPY_TO_SYMBOL(d,s,n,...)           cudaMemcpyToSymbol(d,s,n,0,cudaMemcpyHostToDevice)
 #define ONIKA_CU_GET_DEVICE_COUNT(iPtr)                cudaGetDeviceCount(iPtr)
 #define ONIKA_CU_SET_DEVICE(id)                        cudaSetDevice(id)
+#define ONIKA_CU_SET_SHARED_MEM_CONFIG(shmc)           cudaDeviceSetSharedMemConfig(shmc)
 #define ONIKA_CU_SET_LIMIT(l,v)                        cudaDeviceSetLimit(l,v)
 #define ONIKA_CU_GET_LIMIT(vptr,l)                     cudaDeviceGetLimit(vptr,l)
 #define ONIKA_CU_GET_DEVICE_PROPERTIES(propPtr,id)     cudaGetDeviceProperties(propPtr,id)

@@ -24,6 +24,28 @@ namespace onika { namespace cuda {
   }
 
   // pointer + size view usable in kernels
+  // std::pair / std::lower_bound stand-ins usable in device code
+  template<class T, class U> struct pair
+  {
+    T first; U second;
+    ONIKA_HOST_DEVICE_FUNC inline bool operator == ( const pair & o ) const { return first == o.first && second == o.second; }
+    ONIKA_HOST_DEVICE_FUNC inline bool operator != ( const pair & o ) const { return ! ( *this == o ); }
+    ONIKA_HOST_DEVICE_FUNC inline bool operator <  ( const pair & o ) const { return first < o.first || ( first == o.first && second < o.second ); }
+    ONIKA_HOST_DEVICE_FUNC inline bool operator >= ( const pair & o ) const { return ! ( *this < o ); }
+  };
+  // first position in [first,last) whose element is not less than x; the range must be sorted (binary search)
+  template<class Iterator, class T> ONIKA_HOST_DEVICE_FUNC inline Iterator lower_bound( Iterator first , Iterator last , const T & x )
+  {
+    auto n = last - first;
+    while( n > 0 )
+    {
+      const auto half = n / 2;
+      Iterator mid = first + half;
+      if( *mid < x ) { first = mid + 1; n -= half + 1; } else n = half;
+    }
+    return first;
+  }
+
   template<class T> struct span
   {
     T* m_ptr = nullptr; size_t m_size = 0;

@@ -1,6 +1,7 @@
 // onika/parallel/parallel_execution_space.h -- the index space a parallel operation runs over:
 // a 1D/2D/3D box [m_start,m_end), optionally (1D only) an explicit list of element coordinates.
 #pragma once
+#include <vector>
 #include <cassert>
 #include <cstddef>
 #include <span>
@@ -99,5 +100,43 @@ namespace onika { namespace parallel {
   template<class T> static inline constexpr bool is_parallel_execution_space_v = is_parallel_execution_space_t<T>::value;
   template<class T> concept SortOfParallelExecutionSpace = is_parallel_execution_space_v<T>;
   template<class T, class P> concept CompatibleParallelExecutionSpace = is_parallel_execution_space_v<T> && is_parallel_execution_space_v<P> && T::SpaceNDim == P::SpaceNDim;
+
+  // Which elements of a second execution space touch, through `conflict_stencil` (relative offsets, e.g. the conflict map
+  // of two operations' data accesses), an element of a first one?  Splits pes2 into the elements that must wait for pes1
+  // (`pes2_dependent_elements`) and those that may run concurrently with it (`pes2_remaining_elements`), both in
+  // iteration order.  (Declared but left empty in the reference, include/onika/parallel/parallel_execution_space.h:152-159.)
+  // Spaces given by element lists are handled conservatively: every element of pes2 is reported dependent.
+  template<SortOfParallelExecutionSpace PES1, CompatibleParallelExecutionSpace<PES1> PES2 >
+  inline void concurrent_execution_space_elements( const PES1& pes1, const PES2& pes2
+                                                 , std::span< element_coord_t<PES1::SpaceNDim> > conflict_stencil
+                                                 , std::vector< element_coord_t<PES1::SpaceNDim> > & pes2_dependent_elements
+                                                 , std::vector< element_coord_t<PES1::SpaceNDim> > & pes2_remaining_elements )
+  {
+    constexpr unsigned int ND = PES1::SpaceNDim;
+    using Coord = element_coord_t<ND>;
+    pes2_dependent_elements.clear();
+    pes2_remaining_elements.clear();
+    auto comp = [](const Coord& c, unsigned int d) -> ssize_t { if constexpr ( ND == 1 ) { (void)d; return c; } else return c[d]; };
+    auto shifted_inside_pes1 = [&](const Coord& e, const Coord& s) -> bool
+    {
+      for(unsigned int d=0;d<ND;d++)
+      {
+        const ssize_t x = comp(e,d) + comp(s,d);
+        if( x < pes1.m_start[d] || x >= pes1.m_end[d] ) return false;
+      }
+      return true;
+    };
+    const bool listed = ( PES1::ElementListNDim != 0 ) || ( PES2::ElementListNDim != 0 );
+    if( pes2.number_of_items() == 0 ) return;
+    auto it = pes2.m_start;
+    do
+    {
+      Coord e;
+      if constexpr ( ND == 1 ) e = it[0]; else e = it;
+      bool dep = listed;
+      for(size_t k=0; !dep && k<conflict_stencil.size(); k++) dep = shifted_inside_pes1( e , conflict_stencil[k] );
+      ( dep ? pes2_dependent_elements : pes2_remaining_elements ).push_back( e );
+    } while( coord_range_iterator_increment( it , pes2.m_start , pes2.m_end ) );
+  }
 
 } }

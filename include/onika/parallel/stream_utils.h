@@ -1,2 +1,8 @@
-// onika/parallel/stream_utils.h -- placeholder kept for include compatibility.
+// onika/parallel/stream_utils.h -- output streams the parallel layer reports on.
 #pragma once
+#include <iostream>
+
+namespace onika { namespace parallel {
+  inline std::ostream& log_out() { return std::cout; }
+  inline std::ostream& log_err() { return std::cerr; }
+} }

@@ -177,6 +177,13 @@ struct HelpersFunctor
 };
 namespace onika { namespace parallel { template<> struct BlockParallelForFunctorTraits<HelpersFunctor> { static inline constexpr bool CudaCompatible = true; }; } }
 
+// a kernel of the user's own, launched with ONIKA_CU_LAUNCH_KERNEL on a lane's stream (as tests/gpu_uvm_benchmark.cu does)
+ONIKA_DEVICE_KERNEL_FUNC void user_double_kernel( double * data , size_t n )
+{
+  const size_t i = size_t(ONIKA_CU_BLOCK_IDX) * ONIKA_CU_BLOCK_SIZE + ONIKA_CU_THREAD_IDX;
+  if( i < n ) data[i] = data[i] * 2.0;
+}
+
 static int scenario_helpers(Out& out, size_t rows)
 {
   const size_t row_bytes = 1000;
@@ -187,6 +194,11 @@ static int scenario_helpers(Out& out, size_t rows)
   CudaMMVector<double> res( rows , 0.0 );
   HelpersFunctor f = { src.data() , dst.data() , mv.data() , row_bytes , onika::cuda::InputArraySpan<double,8>( c ) , onika::cuda::VectorShallowCopy<double>( table ) , res.data() };
   block_parallel_for( rows , f , parallel_execution_context("helpers") );
+  {
+    auto stream = onika::cuda::CudaContext::default_cuda_ctx()->getThreadStream( 2 );
+    ONIKA_CU_LAUNCH_KERNEL( (rows+127)/128 , 128 , 0 , stream , user_double_kernel , res.data() , rows );
+    ONIKA_CU_CHECK_ERRORS( ONIKA_CU_STREAM_SYNCHRONIZE( stream ) );
+  }
   out.bytes( dst.data() , dst.size() );
   out.bytes( mv.data() , mv.size() );
   out.doubles( res.data() , rows );
@@ -445,6 +457,16 @@ static int scenario_graph(Out& out, size_t rows, size_t cols, int replays, int n
 
 static int scenario_grid3d(Out& out)
 {
+  { // which cells of a second 2D sweep must wait for a first one, given a cross-shaped conflict stencil (host logic)
+    using C2 = onika::oarray_t<ssize_t,2>;
+    const ParallelExecutionSpace<2> first = { {0,0} , {4,4} } , second = { {3,0} , {7,2} };
+    std::vector<C2> stencil = { C2{0,0} , C2{-1,0} , C2{1,0} , C2{0,-1} , C2{0,1} } , dep , rem;
+    concurrent_execution_space_elements( first , second , std::span<C2>( stencil ) , dep , rem );
+    // column i=3 lies inside `first`, column i=4 touches it through the (-1,0) offset, i=5,6 are independent
+    if( dep.size() != 4 || rem.size() != 4 ) return 7;
+    for(const auto& c : dep) if( c[0] > 4 ) return 8;
+    for(const auto& c : rem) if( c[0] < 5 ) return 9;
+  }
   {
     const ssize_t N = 4;
     CudaMMVector<double> m( N*N*N , 0.0 );
@@ -563,6 +585,33 @@ static int scenario_soatl(Out& out, size_t n)
     copy( wire , fa );
     out.u64( wire.storage_size() );
     out.bytes( wire.storage_ptr() , wire.storage_size() );
+    // value tuples and pointer bundles (tests/soatupletest.cpp idioms): zero by default, field-wise conversion, views
+    {
+      FieldTuple<_tag_particle_rx,_tag_particle_mid,_tag_particle_atype> z;
+      if( z[particle_rx] != 0.0 || z[particle_mid] != 0 || z[particle_atype] != 0 ) return 7;
+      FieldTuple<_tag_particle_rx,_tag_particle_e,_tag_particle_mid> part( t );            // rx, e, mid from the 6-field element
+      if( part[particle_rx] != t[particle_rx] || part[particle_e] != t[particle_e] || part[particle_mid] != t[particle_mid] ) return 8;
+      FieldTuple<_tag_particle_rx,_tag_particle_rz> two( 7.0 , 9.0 );
+      FieldTuple<_tag_particle_rz,_tag_particle_ry> conv( two );                           // rz copied, ry absent in the source -> 0
+      if( conv[particle_rz] != 9.0 || conv[particle_ry] != 0.0 ) return 9;
+      conv[particle_ry] = 5.0; conv.copy_existing_fields( FieldTuple<_tag_particle_rz>( 1.0 ) );
+      if( conv[particle_rz] != 1.0 || conv[particle_ry] != 5.0 || ! ( conv == conv ) || conv != conv ) return 10;
+      int nfields = 0; double acc = 0.0;
+      two.apply_fields( [&](auto , double v) { ++nfields; acc += v; } );
+      if( nfields != 2 || acc != 16.0 ) return 11;
+      static_assert( field_tuple_has_field_v< decltype(two) , _tag_particle_rz > && ! field_tuple_has_field_v< decltype(two) , _tag_particle_e > );
+      static_assert( std::is_same_v< FieldTupleFromFieldIds< FieldIds<_tag_particle_rx,_tag_particle_rz> > , decltype(two) > );
+
+      auto view = make_field_arrays_view( fa , particle_rz , particle_e );
+      if( view.size() != n || view[particle_rz] != fa[particle_rz] || view[particle_e] != fa[particle_e] ) return 12;
+      auto nul = make_field_pointer_tuple( cst::align<64>() , cst::chunk<8>() , particle_rz , particle_ry );
+      if( nul[particle_rz] != nullptr || nul[particle_ry] != nullptr ) return 13;
+      nul.copy_or_zero_fields( view );
+      if( nul[particle_rz] != fa[particle_rz] || nul[particle_ry] != nullptr || ! ( nul == nul ) ) return 14;
+      onika::cuda::pair<int,double> pa{ 1 , 2.0 }, pb{ 1 , 3.0 };
+      const double sorted[5] = { 1.0 , 2.0 , 2.0 , 4.0 , 8.0 };
+      if( ! ( pa < pb ) || pa == pb || onika::cuda::lower_bound( sorted , sorted+5 , 2.0 ) != sorted+1 || onika::cuda::lower_bound( sorted , sorted+5 , 9.0 ) != sorted+5 ) return 15;
+    }
     wire.clear(); fa.clear();
   }
   // --- tests/benchmark.cpp kernel through parallel_apply_simd with a device lambda ---
