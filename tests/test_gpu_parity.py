@@ -121,6 +121,37 @@ def test_reduce_min_full_size_2pow28_properties(ob):
     del t
 
 
+def test_more_than_2pow32_elements(ob):
+    """maximum sizes: the reference's GPU trampoline carries the start index as `unsigned int`
+    (block_parallel_for_adapter.h:51-66), i.e. N <= 2^32; here indices are 64-bit throughout.  2^32 + 4099 doubles (34.4 GB):
+    memset -> exact sum, value_add on everything, a planted minimum / maximum beyond the 2^32-th element, axpy."""
+    import torch
+    from onika_b200 import parallel as P, _capi
+    L = _capi.lib()
+    n = (1 << 32) + 4099
+    free, _ = torch.cuda.mem_get_info()
+    if free < 2 * 8 * n + (4 << 30):
+        pytest.skip("not enough free device memory for two 34 GB arrays")
+    t = torch.empty(n, dtype=torch.float64, device="cuda")
+    _capi.check(L.onk_parallel_memset(t.data_ptr(), n, np.float64(1.0).view(np.uint64).item(), 8, 0))
+    assert host(P.reduce_sum(t))[0] == float(n)                        # exact: n < 2^53, every partial is an integer
+    assert host(P.reduce_min(t))[0] == 1.0 and host(P.reduce_max(t))[0] == 1.0
+    _capi.check(L.onk_value_add_f64(t.data_ptr(), 1, n, 0.5, 0))      # one row of n columns
+    ob.lane_sync()
+    assert float(t[n - 1].item()) == 1.5 and float(t[(1 << 32) + 7].item()) == 1.5 and float(t[0].item()) == 1.5
+    assert host(P.reduce_sum(t))[0] == 1.5 * n
+    t[(1 << 32) + 4098] = -3.0
+    t[(1 << 32) + 1] = 9.0
+    assert host(P.reduce_min(t))[0] == -3.0 and host(P.reduce_max(t))[0] == 9.0
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    _capi.check(L.onk_parallel_memset(x.data_ptr(), n, np.float64(2.0).view(np.uint64).item(), 8, 0))
+    _capi.check(L.onk_axpy_f64(t.data_ptr(), x.data_ptr(), 0.25, n, 0))   # t += 0.25 * 2
+    ob.lane_sync()
+    assert float(t[n - 1].item()) == -2.5 and float(t[(1 << 32) + 1].item()) == 9.5 and float(t[123].item()) == 2.0
+    assert host(P.reduce_sum(t))[0] == 2.0 * (n - 2) - 2.5 + 9.5
+    del t, x
+
+
 # ---------------------------------------------------------------- streaming
 @pytest.mark.parametrize("n", [1, 7, 2047, 2048, 2049, 100_003, 1_000_003])
 def test_axpy_vs_oracle(ob, orc, n):
