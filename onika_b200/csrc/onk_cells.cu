@@ -377,54 +377,70 @@ namespace onk
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(a) : "memory");
   }
 
-  template<int STAGES, int CTAS>
+  // One tile in flight per CTA, CTAS resident CTAs per SM (resident warps, not a deeper ring per CTA, hide the latency
+  // here: 3 stages x 2 CTAs 77 us, 2 x 3 67 us, 1 x 6 66 us, 1 x 5 64 us on 128^3 cells).  Tiles are handed out
+  // dynamically: the first one is the CTA's own index, further ones come from a global ticket drawn by thread 0 one tile
+  // ahead (so the draw, like the offset tables, is never waited for).  Tiles hold equal numbers of cells, not of
+  // particles: with uneven densities a static round robin would leave SMs idle; on the uniform Poisson(16) grid both
+  // measure the same 64 us.  Every CTA draws until its first out-of-range ticket: exactly ntiles draws in total, and
+  // whoever draws the last one puts the counter back to zero for the next launch.
+  template<int CTAS>
   __global__ void __launch_bounds__(THREADS, CTAS)
   cell_sum_packed_f64_kernel(const double* __restrict__ values, const uint64_t* __restrict__ cell_begin, uint64_t ncells,
                              double* __restrict__ cell_sum, double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ total)
   {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    const unsigned ring = smem_u32(dyn_smem);
-    constexpr unsigned STAGE_BYTES = PK_ROW * 8u;
+    __shared__ unsigned long long s_next_tile[2];
+    const unsigned tile_smem = smem_u32(dyn_smem);
     constexpr int COPY_ITERS = (PK_CAP / 2 + THREADS - 1) / THREADS;       // 16-byte pieces per thread and tile
     const uint64_t ntiles = (ncells + PK_CELLS - 1) / PK_CELLS;
-    const uint64_t my_tiles = (blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const unsigned parity = (unsigned)(((uintptr_t)values >> 3) & 1u);   // element g is 16-byte aligned iff g + parity is even
     const unsigned pair_slot0 = (threadIdx.x + (threadIdx.x >> 4)) * 16u;  // byte offset of pair j = tid + 256*it: pair_slot0 + 272*16*it
-    const uint64_t tile_stride = (uint64_t)gridDim.x * PK_CELLS;
+    unsigned* tile_counter = ticket + 1;
     double thread_total = 0.0;
+    bool drawing = true;                                                  // thread 0: this CTA has not yet drawn an out-of-range ticket
 
-    uint32_t pb_s[STAGES], pe_s[STAGES], cnt_s[STAGES];
+    auto draw = [&](int slot)                                             // thread 0 only
+    {
+      unsigned long long t = ~0ull;
+      if (drawing)
+      {
+        const unsigned old = atomicAdd(tile_counter, 1u);
+        t = (unsigned long long)gridDim.x + old;
+        if (t >= ntiles) drawing = false;
+        if ((uint64_t)old + 1u == ntiles) atomicExch(tile_counter, 0u);   // the last draw of the launch
+      }
+      s_next_tile[slot] = t;
+    };
 
-    // offsets of the NEXT tile to issue, loaded one issue ahead (their latency never sits in front of the data loads)
+    // offsets of a tile, loaded one tile ahead of their use
     uint64_t nx_b = 0, nx_e = 0, nx_base = 0, nx_end = 0;
-    uint64_t nx_c0 = (uint64_t)blockIdx.x * PK_CELLS;                    // first cell of the next tile whose tables get loaded
-    auto load_next_tables = [&]()
+    auto load_tables = [&](uint64_t tile)
     {
       nx_b = nx_e = nx_base = nx_end = 0;
-      if (nx_c0 < ncells)
+      if (tile < ntiles)
       {
-        const uint64_t c = nx_c0 + threadIdx.x;
-        const uint64_t cend = (nx_c0 + PK_CELLS < ncells) ? nx_c0 + PK_CELLS : ncells;
-        nx_base = __ldg(cell_begin + nx_c0); nx_end = __ldg(cell_begin + cend);
+        const uint64_t c0 = tile * PK_CELLS, c = c0 + threadIdx.x;
+        const uint64_t cend = (c0 + PK_CELLS < ncells) ? c0 + PK_CELLS : ncells;
+        nx_base = __ldg(cell_begin + c0); nx_end = __ldg(cell_begin + cend);
         if (c < ncells) { nx_b = __ldg(cell_begin + c); nx_e = __ldg(cell_begin + c + 1); } else { nx_b = nx_e = nx_end; }
       }
-      nx_c0 += tile_stride;
     };
-    load_next_tables();
 
-    auto issue = [&](int stage)
+    uint32_t pb = 0, pe = 0, cnt = 0;
+    // copies the tile whose offsets are in nx_*, then fetches the offsets of `following`
+    auto issue = [&](uint64_t following)
     {
       // the staged window starts at the aligned element at or below the tile's first value: one stranger in front at most
       const uint64_t lead = (nx_base + parity) & 1ull;
       const uint64_t span = nx_end - nx_base + lead;
       const uint64_t rb = nx_b - nx_base + lead, re = nx_e - nx_base + lead;
-      pb_s[stage] = rb < 0xffffffffull ? (uint32_t)rb : 0xffffffffu;
-      pe_s[stage] = re < 0xffffffffull ? (uint32_t)re : 0xffffffffu;
-      const uint32_t cnt = span < (uint64_t)PK_CAP ? (uint32_t)span : (uint32_t)PK_CAP;
-      cnt_s[stage] = cnt;
+      pb = rb < 0xffffffffull ? (uint32_t)rb : 0xffffffffu;
+      pe = re < 0xffffffffull ? (uint32_t)re : 0xffffffffu;
+      cnt = span < (uint64_t)PK_CAP ? (uint32_t)span : (uint32_t)PK_CAP;
       const uint4* src = reinterpret_cast<const uint4*>(values + ((int64_t)nx_base - (int64_t)lead)) + threadIdx.x;
-      load_next_tables();
-      const unsigned dst = ring + (unsigned)stage * STAGE_BYTES + pair_slot0;
+      load_tables(following);
+      const unsigned dst = tile_smem + pair_slot0;
       const uint32_t npairs = cnt >> 1;
 #pragma unroll
       for (int it = 0; it < COPY_ITERS; it++)
@@ -434,59 +450,49 @@ namespace onk
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-#pragma unroll
-    for (int sgi = 0; sgi < STAGES; sgi++)
-    {
-      if ((uint64_t)sgi < my_tiles) issue(sgi);
-      else asm volatile("cp.async.commit_group;" ::: "memory");
-    }
+    uint64_t cur = blockIdx.x;                                            // tile being copied / folded
+    if (threadIdx.x == 0) draw(0);
+    load_tables(cur);
+    __syncthreads();
+    uint64_t nxt = s_next_tile[0];
+    if (cur < ntiles) issue(nxt);
 
-    uint64_t c = (uint64_t)blockIdx.x * PK_CELLS + threadIdx.x;           // this thread's cell in the tile being folded
-    for (uint64_t k0 = 0; k0 < my_tiles; k0 += STAGES)
+    for (int slot = 1; cur < ntiles; slot ^= 1)                           // CTA-uniform
     {
-#pragma unroll
-      for (int sgi = 0; sgi < STAGES; sgi++)
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();                                                    // every thread's pieces of this tile have landed
+      if (threadIdx.x == 0) draw(slot);                                   // ticket of the tile after the next one
+      const uint32_t staged_end = pe < cnt ? pe : cnt;
+      double s = 0.0;
+      if (pb < staged_end)                                                // particle order; value p sits in slot p + 2*(p/32)
       {
-        const uint64_t k = k0 + sgi;
-        if (k < my_tiles)                                  // CTA-uniform
+        uint32_t p = pb;
+        unsigned a = tile_smem + (p + 2u * (p >> 5)) * 8u;
+        if (p & 1u) { s = __dadd_rn(s, lds64_u32(a)); ++p; a += (p & 31u) ? 8u : 24u; }
+        uint32_t npair = (staged_end - p) >> 1;
+        uint32_t r = (32u - (p & 31u)) >> 1;                              // pairs left before the next skipped slot pair
+        for (; npair != 0u; --npair)
         {
-          asm volatile("cp.async.wait_group %0;" :: "n"(STAGES - 1) : "memory");
-          __syncthreads();                                 // every thread's pieces of this tile have landed
-          const unsigned tile = ring + (unsigned)sgi * STAGE_BYTES;
-          const uint32_t cnt = cnt_s[sgi], pb = pb_s[sgi], pe = pe_s[sgi];
-          const uint32_t staged_end = pe < cnt ? pe : cnt;
-          double s = 0.0;
-          if (pb < staged_end)                             // particle order; value p sits in slot p + 2*(p/32)
-          {
-            uint32_t p = pb;
-            unsigned a = tile + (p + 2u * (p >> 5)) * 8u;
-            if (p & 1u) { s = __dadd_rn(s, lds64_u32(a)); ++p; a += (p & 31u) ? 8u : 24u; }
-            uint32_t npair = (staged_end - p) >> 1;
-            uint32_t r = (32u - (p & 31u)) >> 1;           // pairs left before the next skipped slot pair
-            for (; npair != 0u; --npair)
-            {
-              double x0, x1; lds128_u32(a, x0, x1);
-              s = __dadd_rn(s, x0); s = __dadd_rn(s, x1);
-              a += 16u;
-              if (--r == 0u) { a += 16u; r = 16u; }
-            }
-            if ((staged_end - p) & 1u) s = __dadd_rn(s, lds64_u32(a));
-          }
-          if (pe > cnt && c < ncells)                      // long tiles: the rest of the run straight from global memory
-          {
-            const uint64_t gb = __ldg(cell_begin + c), ge = __ldg(cell_begin + c + 1);
-            const uint64_t staged_g = gb + (uint64_t)(staged_end > pb ? staged_end - pb : 0u);
-            for (uint64_t g = staged_g; g < ge; g++) s = __dadd_rn(s, ld_stream_ro1(values + g));
-          }
-          if (c < ncells) { cell_sum[c] = s; thread_total = __dadd_rn(thread_total, s); }
-          c += tile_stride;
-          __syncthreads();                                 // everybody is done reading this stage
-          if (k + STAGES < my_tiles) issue(sgi);
-          else asm volatile("cp.async.commit_group;" ::: "memory");
+          double x0, x1; lds128_u32(a, x0, x1);
+          s = __dadd_rn(s, x0); s = __dadd_rn(s, x1);
+          a += 16u;
+          if (--r == 0u) { a += 16u; r = 16u; }
         }
+        if ((staged_end - p) & 1u) s = __dadd_rn(s, lds64_u32(a));
       }
+      const uint64_t c = cur * PK_CELLS + threadIdx.x;
+      if (pe > cnt && c < ncells)                                         // long tiles: the rest of the run straight from global memory
+      {
+        const uint64_t gb = __ldg(cell_begin + c), ge = __ldg(cell_begin + c + 1);
+        const uint64_t staged_g = gb + (uint64_t)(staged_end > pb ? staged_end - pb : 0u);
+        for (uint64_t g = staged_g; g < ge; g++) s = __dadd_rn(s, ld_stream_ro1(values + g));
+      }
+      if (c < ncells) { cell_sum[c] = s; thread_total = __dadd_rn(thread_total, s); }
+      __syncthreads();                                                    // everybody is done reading the tile; the new ticket is visible
+      cur = nxt;
+      nxt = s_next_tile[slot];
+      if (cur < ntiles) issue(nxt);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     cell_total_finish(thread_total, partials, ticket, total);
   }
 }
@@ -566,16 +572,9 @@ int onk_cell_sum_packed_f64(const double* values_dev, const uint64_t* cell_begin
   }
   ONK_REQUIRE(cell_begin_dev && cell_sum_dev, "onk_cell_sum_packed_f64: null pointer");
   ONK_REQUIRE(((uintptr_t)values_dev & 7) == 0, "onk_cell_sum_packed_f64: values are not 8-byte aligned");
-  // variants (env ONK_PK_CFG, tuning only): "rows" = the row-staged kernel of the per-cell layout fed from the packed
-  // column (83 us on 128^3 cells); "SxC" = CTA-tile kernel with ring depth S and C resident CTAs per SM:
-  // 3x2 77 us, 2x3 67 us, 1x6 66 us, 1x5 64 us (default) -- resident warps, not ring depth, hide the latency here
-  static const int cfg = []{ const char* e = getenv("ONK_PK_CFG");
-                             if (!e) return 3;
-                             if (e[0] == 'r') return 2;
-                             if (e[0] == '3') return 0;
-                             if (e[0] == '2') return 1;
-                             return e[2] == '6' ? 4 : 3; }();
-  if (cfg == 2)
+  // ONK_PK_CFG=rows (tuning only): the row-staged kernel of the per-cell layout fed from the packed column (83 us on 128^3 cells)
+  static const bool rows_variant = []{ const char* e = getenv("ONK_PK_CFG"); return e && e[0] == 'r'; }();
+  if (rows_variant)
   {
     static bool rows_configured = false;
     if (!rows_configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_f64_async_kernel<true,8,3,32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asy_smem<8,3,32>())); rows_configured = true; }
@@ -586,21 +585,12 @@ int onk_cell_sum_packed_f64(const double* values_dev, const uint64_t* cell_begin
     ONK_CHECK_LAUNCH(); count_launch();
     return ONK_OK;
   }
+  constexpr int PK_CTAS = 5;
   static bool configured = false;
-  if (!configured)
-  {
-    ONK_CUDA(cudaFuncSetAttribute(cell_sum_packed_f64_kernel<3,2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pk_smem<3>()));
-    ONK_CUDA(cudaFuncSetAttribute(cell_sum_packed_f64_kernel<2,3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pk_smem<2>()));
-    ONK_CUDA(cudaFuncSetAttribute(cell_sum_packed_f64_kernel<1,5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pk_smem<1>()));
-    ONK_CUDA(cudaFuncSetAttribute(cell_sum_packed_f64_kernel<1,6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pk_smem<1>()));
-    configured = true;
-  }
-  const unsigned ctas = cfg == 0 ? 2u : cfg == 1 ? 3u : cfg == 3 ? 5u : 6u;
-  unsigned grid = grid_for(ncells, PK_CELLS, ctas);
+  if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_packed_f64_kernel<PK_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pk_smem<1>())); configured = true; }
+  unsigned grid = grid_for(ncells, PK_CELLS, PK_CTAS);
   if (grid > (unsigned)MAX_PARTIALS) grid = MAX_PARTIALS;
-#define ONK_PK_LAUNCH(S, C) cell_sum_packed_f64_kernel<S,C><<<grid, THREADS, pk_smem<S>(), L->stream>>>(values_dev, cell_begin_dev, ncells, cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev)
-  if (cfg == 0) ONK_PK_LAUNCH(3, 2); else if (cfg == 1) ONK_PK_LAUNCH(2, 3); else if (cfg == 3) ONK_PK_LAUNCH(1, 5); else ONK_PK_LAUNCH(1, 6);
-#undef ONK_PK_LAUNCH
+  cell_sum_packed_f64_kernel<PK_CTAS><<<grid, THREADS, pk_smem<1>(), L->stream>>>(values_dev, cell_begin_dev, ncells, cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev);
   ONK_CHECK_LAUNCH(); count_launch();
   return ONK_OK;
 }
