@@ -453,7 +453,7 @@ def test_field_major_cell_sum_golden_and_reference_inputs(ob, gold, orc):
     assert np.array_equal(so, unhx(g["cell_sum"])) and to == float.fromhex(g["total"])
 
 
-@pytest.mark.parametrize("side,mean,maxn", [(1, 16.0, 64), (7, 16.0, 64), (40, 16.0, 64), (24, 40.0, 400), (16, 0.3, 4)])
+@pytest.mark.parametrize("side,mean,maxn", [(1, 16.0, 64), (7, 16.0, 64), (40, 16.0, 64), (24, 40.0, 400), (16, 0.3, 4), (48, 16.0, 63)])
 def test_field_major_cell_sum_vs_oracle(ob, orc, side, mean, maxn):
     """ragged cells: empty ones, tiles whose values exceed the staged capacity (mean 40 > 24 per cell: the rest is read
     from global memory), a last partial tile"""
@@ -462,6 +462,9 @@ def test_field_major_cell_sum_vs_oracle(ob, orc, side, mean, maxn):
     counts = poisson_counts(side ** 3, mean, 42, 0, maxn)
     if maxn > 64:
         counts[::53] = maxn
+    if maxn == 63:                         # uneven density: an empty half, a dense slab (tiles of very different weight)
+        counts[: counts.size // 2] = 0
+        counts[counts.size // 2: counts.size // 2 + 3000] = 63
     counts[min(5, counts.size - 1)] = 0
     e = lcg_uniform(int(counts.sum()), 40, -1, 1)
     fm = cellgrid.FieldMajorCellGrid(counts)
