@@ -108,6 +108,18 @@ def main():
             e1.record(); e1.synchronize()
             t = e0.elapsed_time(e1) / 20 * 1e-3
             print(f"cells_raw field {field}            {t * 1e6:10.1f} us   {alg / t / 1e9:8.1f} GB/s", flush=True)
+    del cg
+    # the same cells in the field-major layout (onk_cell_sum_packed_f64)
+    fm = cellgrid.FieldMajorCellGrid(counts, nfields=1)
+    fm.columns[0].uniform_(-1, 1)
+    alg_fm = 8 * fm.nparticles + fm.ncells * 16
+    timed("cells_fm", lambda: fm.cell_sum(0), alg_fm, True)
+    sums_fm = torch.empty(fm.ncells, dtype=torch.float64, device="cuda")
+    timed("cells_fm_raw", lambda: _capi.check(_capi.lib().onk_cell_sum_packed_f64(ptr(fm.columns[0]), ptr(fm.cell_begin), fm.ncells, ptr(sums_fm), ptr(tot), 0)),
+          alg_fm, True)
+    # a plain stream over the same number of bytes, for reference (short kernels do not reach the 2 GiB rate)
+    same = torch.rand(alg_fm // 8, dtype=torch.float64, device="cuda")
+    timed("reduce_min_same_bytes", lambda: P.ReduceFunctor(ob.OP_MIN, same, o).launch(same.numel(), 0), 8 * same.numel(), True)
     torch.cuda.synchronize()
 
 
