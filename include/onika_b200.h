@@ -149,8 +149,9 @@ int onk_combine_f64(int op, const double* partials_dev, uint32_t count, double* 
  * Exchange buffers are ONK_XCHG_BYTES of device memory per rank (onk_xchg_create), shared between the processes of one
  * node through CUDA IPC: export the local handle, all-gather the handles with any host-side transport, open the peers.
  * All ranks must call onk_reduce_xchg_f64 the same number of times (the call count is the flag epoch). */
-#define ONK_XCHG_BYTES      1024
+#define ONK_XCHG_BYTES      4096
 #define ONK_XCHG_MAX_WORLD    16
+#define ONK_XCHG_MAX_VALUES    8
 #define ONK_IPC_HANDLE_BYTES  64
 typedef struct onk_xchg onk_xchg;
 int onk_xchg_create(int rank, int world, onk_xchg** x);
@@ -158,6 +159,10 @@ int onk_xchg_export(onk_xchg* x, unsigned char handle[ONK_IPC_HANDLE_BYTES]);
 int onk_xchg_connect(onk_xchg* x, const unsigned char* handles /* world x ONK_IPC_HANDLE_BYTES, rank order */);
 int onk_xchg_destroy(onk_xchg* x);
 int onk_reduce_xchg_f64(int op, const double* in_dev, uint64_t n, double* out_dev, onk_xchg* x, int lane);
+/* mpi::all_reduce_multi (include/onika/mpi/all_reduce_multi.h:30-37: k scalars packed into one MPI_Allreduce with one
+ * operator) for 1..ONK_XCHG_MAX_VALUES doubles in device memory, in place, folded in rank order; one 32-thread kernel
+ * per rank, no collective library call.  Collective, counts as one epoch. */
+int onk_xchg_allreduce_f64(onk_xchg* x, int op, double* values_dev, int count, int lane);
 int onk_xchg_info(onk_xchg* x, int* rank, int* world);
 /* device-side barrier between the ranks' lanes (same flag exchange, no payload): what every rank queued on `lane` before
  * it, peer stores included, is complete and visible once it has passed on any rank.  Collective, counts as one epoch. */

@@ -62,6 +62,7 @@ PROTOTYPES = {
     "onk_xchg_connect": (i32, [vp, C.c_char_p]),
     "onk_xchg_destroy": (i32, [vp]),
     "onk_reduce_xchg_f64": (i32, [i32, vp, u64, vp, vp, i32]),
+    "onk_xchg_allreduce_f64": (i32, [vp, i32, vp, i32, i32]),
     "onk_xchg_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
     "onk_xchg_barrier": (i32, [vp, i32]),
     "onk_window_create": (i32, [C.c_size_t, i32, i32, C.POINTER(vp)]),

@@ -24,7 +24,7 @@ namespace onk
   // one buffer per rank, mapped into every peer process: [parity][rank] values and epoch flags
   struct XchgBuffer
   {
-    double             val[2][ONK_XCHG_MAX_WORLD];
+    double             val[2][ONK_XCHG_MAX_WORLD][ONK_XCHG_MAX_VALUES];   // [parity][source rank][value]
     unsigned long long flag[2][ONK_XCHG_MAX_WORLD];
     unsigned long long error;                      // set when a peer did not show up in time
   };
@@ -56,7 +56,7 @@ namespace onk
       const int peer = (int)threadIdx.x;
       // publish: value first, then the flag with release semantics at system scope (peer stores travel over NVLink)
       XchgBuffer* pb = xp.peer[peer];
-      *reinterpret_cast<volatile double*>(&pb->val[par][xp.rank]) = s_local;
+      *reinterpret_cast<volatile double*>(&pb->val[par][xp.rank][0]) = s_local;
       st_release_sys(&pb->flag[par][xp.rank], xp.epoch);
       // gather: wait for rank `peer`'s flag in MY buffer
       XchgBuffer* mine = xp.peer[xp.rank];
@@ -67,7 +67,7 @@ namespace onk
         if (clock64() - t0 > 20000000000ll) { ok = false; break; }        // ~10 s: a peer is missing; do not hang the device
         __nanosleep(64);
       }
-      s_vals[peer] = ok ? *reinterpret_cast<volatile double*>(&mine->val[par][peer]) : __longlong_as_double(0x7ff8000000000000ll);
+      s_vals[peer] = ok ? *reinterpret_cast<volatile double*>(&mine->val[par][peer][0]) : __longlong_as_double(0x7ff8000000000000ll);
       if (!ok) mine->error = xp.epoch;
     }
     __syncthreads();
@@ -186,6 +186,41 @@ namespace onk
   // device-side barrier between the ranks' lanes: everything queued before it on every rank's lane (peer stores
   // included: a kernel's writes are performed before a later kernel of the same stream publishes its release flag)
   // is complete and visible when it returns on any rank
+  // all-reduce of `count` <= ONK_XCHG_MAX_VALUES doubles held by every rank, in place, same operator for all values:
+  // thread p publishes this rank's values into rank p's buffer and waits for rank p's; values are folded in rank order
+  template<int OP>
+  __global__ void xchg_allreduce_kernel(double* __restrict__ values, int count, const __grid_constant__ XchgParams xp)
+  {
+    using R = Red<OP>;
+    __shared__ double s_vals[ONK_XCHG_MAX_WORLD][ONK_XCHG_MAX_VALUES];
+    const int par = (int)(xp.epoch & 1ull);
+    if ((int)threadIdx.x < xp.world)
+    {
+      const int peer = (int)threadIdx.x;
+      XchgBuffer* pb = xp.peer[peer];
+      for (int k = 0; k < count; k++) *reinterpret_cast<volatile double*>(&pb->val[par][xp.rank][k]) = values[k];
+      st_release_sys(&pb->flag[par][xp.rank], xp.epoch);
+      XchgBuffer* mine = xp.peer[xp.rank];
+      const long long t0 = clock64();
+      bool ok = true;
+      while (ld_acquire_sys(&mine->flag[par][peer]) < xp.epoch)
+      {
+        if (clock64() - t0 > 20000000000ll) { ok = false; break; }
+        __nanosleep(64);
+      }
+      for (int k = 0; k < count; k++)
+        s_vals[peer][k] = ok ? *reinterpret_cast<volatile double*>(&mine->val[par][peer][k]) : __longlong_as_double(0x7ff8000000000000ll);
+      if (!ok) mine->error = xp.epoch;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < count)
+    {
+      double r = R::identity();
+      for (int p = 0; p < xp.world; p++) r = R::apply(r, s_vals[p][threadIdx.x]);
+      values[threadIdx.x] = r;
+    }
+  }
+
   __global__ void xchg_barrier_kernel(const __grid_constant__ XchgParams xp)
   {
     (void) xchg_combine<ONK_OP_MIN>(0.0, xp);
@@ -269,6 +304,24 @@ int onk_xchg_barrier(onk_xchg* x, int lane)
   Lane* L; if (int rc = lane_get(lane, &L)) return rc;
   x->params.epoch += 1;
   xchg_barrier_kernel<<<1, 32, 0, L->stream>>>(x->params);
+  ONK_CHECK_LAUNCH();
+  count_launch();
+  return ONK_OK;
+}
+
+int onk_xchg_allreduce_f64(onk_xchg* x, int op, double* values_dev, int count, int lane)
+{
+  ONK_REQUIRE(x != nullptr && x->connected, "onk_xchg_allreduce_f64: exchange is not connected");
+  ONK_REQUIRE(values_dev != nullptr && count >= 1 && count <= ONK_XCHG_MAX_VALUES, "onk_xchg_allreduce_f64: 1..%d values", ONK_XCHG_MAX_VALUES);
+  ONK_REQUIRE(op == ONK_OP_MIN || op == ONK_OP_MAX || op == ONK_OP_SUM, "onk_xchg_allreduce_f64: unknown op %d", op);
+  Lane* L; if (int rc = lane_get(lane, &L)) return rc;
+  x->params.epoch += 1;
+  switch (op)
+  {
+    case ONK_OP_MIN: xchg_allreduce_kernel<ONK_OP_MIN><<<1, 32, 0, L->stream>>>(values_dev, count, x->params); break;
+    case ONK_OP_MAX: xchg_allreduce_kernel<ONK_OP_MAX><<<1, 32, 0, L->stream>>>(values_dev, count, x->params); break;
+    default:         xchg_allreduce_kernel<ONK_OP_SUM><<<1, 32, 0, L->stream>>>(values_dev, count, x->params); break;
+  }
   ONK_CHECK_LAUNCH();
   count_launch();
   return ONK_OK;

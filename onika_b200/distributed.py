@@ -82,6 +82,13 @@ class PeerExchange:
         _share_handles(lambda buf: self._lib.onk_xchg_export(self.handle, buf),
                        lambda allh: self._lib.onk_xchg_connect(self.handle, allh), group, "the exchange buffer")
 
+    def allreduce(self, op: int, values, lane: int = -1):
+        """in-place all-reduce of 1..8 doubles held in a device tensor (onk_xchg_allreduce_f64): the counterpart of
+        mpi::all_reduce_multi; rank-order fold, same bits on every rank; collective"""
+        from .runtime import ptr
+        self._check(self._lib.onk_xchg_allreduce_f64(self.handle, op, ptr(values), values.numel(), lane))
+        return values
+
     def barrier(self, lane: int = -1) -> None:
         """device-side barrier between the ranks' lanes (onk_xchg_barrier); collective"""
         self._check(self._lib.onk_xchg_barrier(self.handle, lane))

@@ -40,6 +40,13 @@ def _worker(rank, world, port, n, q):
     # same answer as the NCCL path
     part = ob.parallel.reduce_min(shard)
     nccl = float(D.combine_across_ranks(_capi.OP_MIN, part).item())
+    # all_reduce_multi counterpart: 5 scalars, one operator, in place
+    base = np.array([0.1, -2.5, 3.0, 1e-3, 7.75])
+    for name, op in (("sum", _capi.OP_SUM), ("min", _capi.OP_MIN), ("max", _capi.OP_MAX)):
+        v = torch.from_numpy(base * (rank + 1) + rank).cuda()
+        x.allreduce(op, v)
+        torch.cuda.synchronize()
+        res[("multi", name)] = v.cpu().numpy().tolist()
     q.put((rank, res, nccl))
     dist.barrier()
     x.close()
@@ -70,6 +77,11 @@ def test_fused_reduce_exchange_two_gpus(n, orc):
             assert res[("min", rep)] == orc.reduce_min(d) and res[("max", rep)] == orc.reduce_max(d)
             assert abs(res[("sum", rep)] - orc.reduce_sum_ld(d)) <= 1e-12 * np.abs(d).sum()
         assert nccl == orc.reduce_min(d)
+        base = np.array([0.1, -2.5, 3.0, 1e-3, 7.75])
+        per_rank = [base * (r + 1) + r for r in range(world)]
+        assert res[("multi", "sum")] == ((0.0 + per_rank[0]) + per_rank[1]).tolist()      # rank-order fold from the identity
+        assert res[("multi", "min")] == np.minimum(per_rank[0], per_rank[1]).tolist()
+        assert res[("multi", "max")] == np.maximum(per_rank[0], per_rank[1]).tolist()
     assert got[0][1] == got[1][1]             # identical bits on both ranks, every repetition
 
 

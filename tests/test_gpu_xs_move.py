@@ -82,3 +82,17 @@ def test_ids_that_do_not_match_up_are_rejected(xch):
     mv.plan(ids, ids.flip(0).contiguous(), lane=0)      # the plan object stays usable after a rejected build
     assert mv.send_counts() == [8]
     mv.close()
+
+
+def test_single_rank_allreduce_and_barrier_are_identities(xch):
+    import torch
+    from onika_b200 import _capi
+    v = torch.tensor([1.5, -2.0, 3.25], dtype=torch.float64, device="cuda")
+    for op in (_capi.OP_SUM, _capi.OP_MIN, _capi.OP_MAX):
+        w = v.clone()
+        xch.allreduce(op, w, lane=0)
+        xch.barrier(lane=0)
+        torch.cuda.synchronize()
+        assert torch.equal(w, v)
+    with pytest.raises(Exception):
+        xch.allreduce(_capi.OP_SUM, torch.zeros(9, dtype=torch.float64, device="cuda"), lane=0)      # more than 8 values
