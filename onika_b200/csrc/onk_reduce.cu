@@ -166,7 +166,8 @@ namespace onk
     if (head > n) head = n;
     const uint64_t ntiles = (n - head) / RED_TILE;
     const uint64_t edge = n - ntiles * RED_TILE;
-    unsigned grid = grid_for(ntiles, 1, RED_CTAS_PER_SM);
+    static const unsigned ctas_per_sm = []{ const char* e = getenv("ONK_RED_CTAS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 8) ? (unsigned)v : RED_CTAS_PER_SM; }();   // tuning knob
+    unsigned grid = grid_for(ntiles, 1, ctas_per_sm);
     if (ntiles == 0) grid = (unsigned)((edge + THREADS - 1) / THREADS ? (edge + THREADS - 1) / THREADS : 1);
     if (grid > (unsigned)MAX_PARTIALS) grid = MAX_PARTIALS;
     if (xp != nullptr && xp->world > 1)
