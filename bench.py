@@ -209,7 +209,7 @@ def secondary_kernels(ob, torch):
     from tests._inputs import poisson_counts
     out = {}
 
-    def timed(fn, reps=10, warm=3):
+    def timed(fn, reps=20, warm=5):
         for _ in range(warm):
             fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
