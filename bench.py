@@ -414,7 +414,7 @@ def run_ours(args) -> int:
         else (6650.0, "fallback (B200_PROFILING.md)")
     achieved = n * 8 / (kernel_ms * 1e-3) / 1e9
     traffic = read_json(os.path.join(ROOT, "profiles", "roofline_traffic.json"))
-    roofline = {"bound": "hbm", "kernel": "onk::reduce_f64_kernel<MIN>", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "onk::reduce_f64_tma_kernel<MIN>", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": n * 8, "kernel_ms": round(kernel_ms, 5),
                 "traffic": (traffic or {}).get("reduce_f64_kernel_dram_bytes_per_launch")}

@@ -76,6 +76,34 @@ namespace onk
     return r;
   }
 
+  // block reduction of the per-thread values, one partial per CTA, two-pass finish inside the same launch: the last CTA to
+  // retire (atomic ticket, self-resetting) folds the per-CTA partials in index order and, for XCHG, combines across ranks
+  template<int OP, bool XCHG>
+  __device__ __forceinline__ void reduce_finish(double thread_value, double* __restrict__ partials, unsigned* __restrict__ ticket,
+                                                double* __restrict__ out, const XchgParams& xp)
+  {
+    using R = Red<OP>;
+    const double blk = block_reduce<OP, THREADS>(thread_value);
+    __shared__ bool is_last;
+    if (threadIdx.x == 0)
+    {
+      partials[blockIdx.x] = blk;
+      __threadfence();
+      const unsigned done = atomicAdd(ticket, 1u);
+      is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last)
+    {
+      __threadfence();
+      double r = R::identity();
+      for (unsigned i = threadIdx.x; i < gridDim.x; i += THREADS) r = R::apply(r, __ldcg(partials + i));
+      r = block_reduce<OP, THREADS>(r);
+      if constexpr (XCHG) r = xchg_combine<OP>(r, xp);
+      if (threadIdx.x == 0) { *out = r; *ticket = 0u; }
+    }
+  }
+
   template<int OP, bool XCHG>
   __global__ void __launch_bounds__(THREADS, RED_CTAS_PER_SM)
   reduce_f64_kernel(const double* __restrict__ in, uint64_t n, uint64_t head, uint64_t ntiles,
@@ -122,26 +150,84 @@ namespace onk
 #pragma unroll
       for (int i = 0; i < s; i++) acc[i] = R::apply(acc[i], acc[i + s]);
 
-    const double blk = block_reduce<OP, THREADS>(acc[0]);
+    reduce_finish<OP, XCHG>(acc[0], partials, ticket, out, xp);
+  }
 
-    __shared__ bool is_last;
-    if (threadIdx.x == 0)
+  // ---- large inputs: the body goes global -> shared with TMA bulk copies ----
+  // One elected thread streams 64 KiB tiles into a 2-stage ring (cp.async.bulk + mbarrier complete_tx), all 256 threads fold
+  // the landed tile from shared memory (conflict-free LDS.128), one CTA per SM.  128 KiB in flight per SM as two large
+  // requests measured 7.28-7.32 TB/s on 2 GiB against 7.11-7.18 TB/s for the register-staged loop above in the same run
+  // (tools/tune.cu r; deeper rings or 96-112 KiB tiles fall back below 7.0).  Edges and the finish are shared with it.
+  constexpr unsigned TMA_TILE_BYTES = 65536;
+  constexpr unsigned TMA_TILE = TMA_TILE_BYTES / 8;             // doubles
+  constexpr int      TMA_STAGES = 2;
+  constexpr size_t   TMA_SMEM = (size_t)TMA_STAGES * TMA_TILE_BYTES + 64;
+
+  template<int OP, bool XCHG>
+  __global__ void __launch_bounds__(THREADS, 1)
+  reduce_f64_tma_kernel(const double* __restrict__ in, uint64_t n, uint64_t head, uint64_t ntiles,
+                        double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ out,
+                        const __grid_constant__ XchgParams xp)
+  {
+    using R = Red<OP>;
+    extern __shared__ __align__(128) unsigned char tsm[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tsm + (size_t)TMA_STAGES * TMA_TILE_BYTES);
+    const unsigned tid = threadIdx.x;
+    if (tid == 0)
     {
-      partials[blockIdx.x] = blk;
-      __threadfence();
-      const unsigned done = atomicAdd(ticket, 1u);
-      is_last = (done == gridDim.x - 1);
+      for (int s = 0; s < TMA_STAGES; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(bars + s)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (is_last)
+    const double* body = in + head;                            // 32-byte aligned
+    const uint64_t mine = (blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto issue = [&](uint64_t k)
     {
-      __threadfence();
-      double r = R::identity();
-      for (unsigned i = threadIdx.x; i < gridDim.x; i += THREADS) r = R::apply(r, __ldcg(partials + i));
-      r = block_reduce<OP, THREADS>(r);
-      if constexpr (XCHG) r = xchg_combine<OP>(r, xp);
-      if (threadIdx.x == 0) { *out = r; *ticket = 0u; }
+      const int s = (int)(k % TMA_STAGES);
+      const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + s);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(tsm + (size_t)s * TMA_TILE_BYTES);
+      const uint64_t tile = blockIdx.x + k * gridDim.x;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(TMA_TILE_BYTES) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"(dst), "l"(body + tile * TMA_TILE), "r"(TMA_TILE_BYTES), "r"(bar) : "memory");
+    };
+    if (tid == 0) for (uint64_t k = 0; k < (uint64_t)TMA_STAGES && k < mine; k++) issue(k);
+
+    double acc[4] = { R::identity(), R::identity(), R::identity(), R::identity() };
+    for (uint64_t k = 0; k < mine; k++)
+    {
+      const int s = (int)(k % TMA_STAGES);
+      const unsigned phase = (unsigned)((k / TMA_STAGES) & 1);
+      const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + s);
+      unsigned landed = 0;
+      while (!landed)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(landed) : "r"(bar), "r"(phase) : "memory");
+      const unsigned base = (unsigned)__cvta_generic_to_shared(tsm + (size_t)s * TMA_TILE_BYTES) + tid * 32u;
+#pragma unroll
+      for (unsigned i = 0; i < TMA_TILE_BYTES / (THREADS * 32u); i++)          // fixed order: reproducible sums
+      {
+        double x0, x1, x2, x3;
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(base + i * (THREADS * 32u)) : "memory");
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x2), "=d"(x3) : "r"(base + i * (THREADS * 32u) + 16u) : "memory");
+        acc[0] = R::apply(acc[0], x0); acc[1] = R::apply(acc[1], x1); acc[2] = R::apply(acc[2], x2); acc[3] = R::apply(acc[3], x3);
+      }
+      __syncthreads();                                                          // the stage may be overwritten
+      if (tid == 0 && k + TMA_STAGES < mine) issue(k + TMA_STAGES);
     }
+
+    // edges (head + what is left after the last full tile): scalar, grid-strided over the whole grid
+    {
+      const uint64_t tail_begin = head + ntiles * TMA_TILE;
+      const uint64_t nedge = head + (n - tail_begin);
+      for (uint64_t e = (uint64_t)blockIdx.x * THREADS + tid; e < nedge; e += (uint64_t)gridDim.x * THREADS)
+      {
+        const uint64_t i = (e < head) ? e : (tail_begin + (e - head));
+        acc[0] = R::apply(acc[0], ld_stream_ro1(in + i));
+      }
+    }
+    acc[0] = R::apply(acc[0], acc[2]); acc[1] = R::apply(acc[1], acc[3]);
+    acc[0] = R::apply(acc[0], acc[1]);
+    reduce_finish<OP, XCHG>(acc[0], partials, ticket, out, xp);
   }
 
   template<int OP>
@@ -164,6 +250,27 @@ namespace onk
     // 32-byte alignment of the vector body; a pointer that is not even 8-byte aligned is rejected by the caller
     uint64_t head = ((32 - ((uintptr_t)in & 31)) & 31) / 8;
     if (head > n) head = n;
+    // large inputs take the TMA-staged body (ONK_RED_KERNEL=ldg forces the register-staged kernel: tuning / comparison)
+    static const bool allow_tma = []{ const char* e = getenv("ONK_RED_KERNEL"); return !(e && e[0] == 'l'); }();
+    const uint64_t tma_tiles = (n - head) / TMA_TILE;
+    if (allow_tma && tma_tiles >= 2ull * (uint64_t)rt().sm_count)
+    {
+      static bool configured = false;
+      if (!configured)
+      {
+        ONK_CUDA(cudaFuncSetAttribute(reduce_f64_tma_kernel<OP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+        ONK_CUDA(cudaFuncSetAttribute(reduce_f64_tma_kernel<OP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+        configured = true;
+      }
+      const unsigned g = (unsigned)rt().sm_count;
+      if (xp != nullptr && xp->world > 1)
+        reduce_f64_tma_kernel<OP, true><<<g, THREADS, TMA_SMEM, L->stream>>>(in, n, head, tma_tiles, L->ws.partials, L->ws.ticket, out, *xp);
+      else
+        reduce_f64_tma_kernel<OP, false><<<g, THREADS, TMA_SMEM, L->stream>>>(in, n, head, tma_tiles, L->ws.partials, L->ws.ticket, out, XchgParams{});
+      ONK_CHECK_LAUNCH();
+      count_launch();
+      return ONK_OK;
+    }
     const uint64_t ntiles = (n - head) / RED_TILE;
     const uint64_t edge = n - ntiles * RED_TILE;
     static const unsigned ctas_per_sm = []{ const char* e = getenv("ONK_RED_CTAS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 8) ? (unsigned)v : RED_CTAS_PER_SM; }();   // tuning knob

@@ -259,7 +259,57 @@ template<class F> double timeit(F f, int reps = 20)
   return ms/reps*1e-3;
 }
 
-int main()
+// TMA-bulk staged read-only reduction: one elected thread streams TB-byte tiles global->shared (cp.async.bulk + mbarrier)
+// into a ring of ST stages, all threads fold the tile from shared memory (conflict-free LDS.128)
+template<int T, int ST, int TB, int C>
+__global__ void __launch_bounds__(T, C) k_reduce_tma(const double* __restrict__ in, uint64_t ntiles, double* out)
+{
+  extern __shared__ __align__(128) unsigned char rsm[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rsm + (size_t)ST * TB);
+  const unsigned tid = threadIdx.x;
+  if (tid == 0)
+  {
+    for (int s = 0; s < ST; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(bars + s)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint64_t mine = (blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto issue = [&](uint64_t k)
+  {
+    const int s = (int)(k % ST);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + s);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(rsm + (size_t)s * TB);
+    const uint64_t tile = blockIdx.x + k * gridDim.x;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((unsigned)TB) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(in + tile * (TB / 8)), "r"((unsigned)TB), "r"(bar) : "memory");
+  };
+  if (tid == 0) for (uint64_t k = 0; k < (uint64_t)ST && k < mine; k++) issue(k);
+  double a0 = 1e308, a1 = 1e308, a2 = 1e308, a3 = 1e308;
+  for (uint64_t k = 0; k < mine; k++)
+  {
+    const int s = (int)(k % ST);
+    const unsigned phase = (unsigned)((k / ST) & 1);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + s);
+    unsigned done = 0;
+    while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+    const unsigned base = (unsigned)__cvta_generic_to_shared(rsm + (size_t)s * TB) + tid * 32u;
+#pragma unroll
+    for (int i = 0; i < TB / (T * 32); i++)
+    {
+      double x0, x1, x2, x3;
+      asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(base + i * (T * 32u)) : "memory");
+      asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x2), "=d"(x3) : "r"(base + i * (T * 32u) + 16u) : "memory");
+      a0 = x0 < a0 ? x0 : a0; a1 = x1 < a1 ? x1 : a1; a2 = x2 < a2 ? x2 : a2; a3 = x3 < a3 ? x3 : a3;
+    }
+    __syncthreads();
+    if (tid == 0 && k + ST < mine) issue(k + ST);
+  }
+  double m = fmin(fmin(a0, a1), fmin(a2, a3));
+  for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((tid & 31) == 0 && m < 0.0) out[blockIdx.x] = m;
+}
+
+int main(int argc, char** argv)
 {
   const uint64_t n = 1ull<<28;
   double *a, *b, *out;
@@ -269,6 +319,16 @@ int main()
   { std::vector<double> h(1<<20); for (size_t i=0;i<h.size();i++) h[i] = 0.25 + (i%1000)*1e-3; for (uint64_t o=0;o<n;o+=h.size()) CK(cudaMemcpy(a+o,h.data(),h.size()*8,cudaMemcpyHostToDevice)); }
   int sms; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   printf("SMs %d\n", sms);
+#define RTMA(T,ST,TB,C) { const uint64_t nt = (n*8)/TB; size_t sm = (size_t)ST*TB + 128; CK(cudaFuncSetAttribute(k_reduce_tma<T,ST,TB,C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); double t = timeit([&]{ k_reduce_tma<T,ST,TB,C><<<sms*C,T,sm>>>(a,nt,out); }); printf("reduce_tma T=%d stages=%d tile=%d C=%d : %8.1f GB/s\n",T,ST,TB,C, n*8/t/1e9); }
+  if (argc > 1 && argv[1][0] == 'r')
+  {
+    for (int rep = 0; rep < 2; rep++)
+    {
+      { const uint64_t nt = n/(256*4*4); double t = timeit([&]{ k_reduce<256,4,4,0><<<sms*4,256>>>(a,nt,out); }); printf("reduce T=256 U=4 C=4 H=0 : %8.1f GB/s\n", n*8/t/1e9); }
+      RTMA(256,2,65536,1) RTMA(512,2,65536,1) RTMA(1024,2,65536,1) RTMA(128,2,65536,1) RTMA(256,3,65536,1) RTMA(512,3,65536,1) RTMA(256,2,98304,1) RTMA(512,2,98304,1) RTMA(256,2,114688,1) RTMA(512,4,32768,1) RTMA(512,6,32768,1) RTMA(1024,4,32768,1) RTMA(256,4,49152,1) RTMA(512,4,49152,1) RTMA(256,2,49152,2) RTMA(256,2,32768,2) RTMA(256,2,32768,3) RTMA(512,2,32768,2)
+    }
+    return 0;
+  }
   { double t = timeit([&]{ CK(cudaMemcpyAsync(b,a,n*8,cudaMemcpyDeviceToDevice)); }, 10); printf("cudaMemcpy D2D           : %8.1f GB/s (r+w)\n", 2*n*8/t/1e9); }
 
 #define RED(T,U,C,H) { const uint64_t nt = n/(T*U*4); double t = timeit([&]{ k_reduce<T,U,C,H><<<sms*C,T>>>(a,nt,out); }); printf("reduce T=%d U=%d C=%d H=%d : %8.1f GB/s\n",T,U,C,H, n*8/t/1e9); }
