@@ -14,6 +14,8 @@
 #include <onika/extras/block_parallel_value_add_functor.h>
 #include <onika/cuda/cuda_reduction.h>
 #include <onika/soatl/field_arrays.h>
+#include <onika/soatl/pretty_print.h>
+#include <onika/soatl/field_id_tuple_utils.h>
 #include <onika/soatl/compute.h>
 #include <onika/soatl/copy.h>
 #include <onika/memory/allocator.h>
@@ -25,6 +27,7 @@
 
 #include <cfloat>
 #include <chrono>
+#include <sstream>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -608,6 +611,11 @@ static int scenario_soatl(Out& out, size_t n)
       if( nul[particle_rz] != nullptr || nul[particle_ry] != nullptr ) return 13;
       nul.copy_or_zero_fields( view );
       if( nul[particle_rz] != fa[particle_rz] || nul[particle_ry] != nullptr || ! ( nul == nul ) ) return 14;
+      std::ostringstream desc;
+      pretty_print_arrays( desc , fa );
+      if( desc.str().find("contains 6 fields") == std::string::npos || desc.str().find("Particle position Z") == std::string::npos ) return 16;
+      const auto fids = onika::make_flat_tuple( particle_rx , particle_atype , particle_mid );       // 8 + 1 + 4 bytes, each padded to 8
+      if( field_id_tuple_size_bytes( fids ) != 24 || field_id_size_bytes( particle_atype , 4 ) != 4 ) return 17;
       onika::cuda::pair<int,double> pa{ 1 , 2.0 }, pb{ 1 , 3.0 };
       const double sorted[5] = { 1.0 , 2.0 , 2.0 , 4.0 , 8.0 };
       if( ! ( pa < pb ) || pa == pb || onika::cuda::lower_bound( sorted , sorted+5 , 2.0 ) != sorted+1 || onika::cuda::lower_bound( sorted , sorted+5 , 9.0 ) != sorted+5 ) return 15;
