@@ -191,6 +191,11 @@ namespace onika { namespace parallel {
       for(auto* p=m_queue_list; p!=nullptr; p=p->m_next) any_undefined = any_undefined || ( p->m_lane == UNDEFINED_EXECUTION_LANE );
       if( any_undefined ) pre_process_queue( m_queue_list , m_exec_list );
       if( m_capture_target != nullptr ) { capture_all(); return; }
+      // cross-lane edges rely on FIFO submission (an edge records what its source lane holds NOW): when the queue carries
+      // such edges a lane-filtered flush would submit a dependent operation before its predecessor, so everything goes
+      if( lane >= 0 )
+        for(auto* p=m_queue_list; p!=nullptr; p=p->m_next)
+          if( ( p->m_wait_lanes[0] | p->m_wait_lanes[1] | p->m_wait_lanes[2] | p->m_wait_lanes[3] ) != 0 ) { lane = UNDEFINED_EXECUTION_LANE; break; }
       ParallelExecutionContext *keep = nullptr, *scheduled = nullptr;
       auto* p = m_queue_list;
       while( p != nullptr )
