@@ -6,6 +6,7 @@
 // is owned by one runtime-library object per PEC (onk_op, include/onika_b200.h) instead of raw events and a
 // CudaDeviceStorage.
 #pragma once
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <onika/cuda/cuda.h>
@@ -196,6 +197,8 @@ namespace onika { namespace parallel {
     static inline int s_gpu_sm_mult = -1;
     static inline int s_gpu_sm_add = -1;
     static inline int s_gpu_block_size = 128;
+    // false (or ONIKA_GPU_TIMING=0 in the environment): operations are not bracketed by timing events, m_total_gpu_execution_time stays 0
+    static inline bool s_gpu_timing = []{ const char* e = std::getenv("ONIKA_GPU_TIMING"); return !( e != nullptr && e[0] == '0' ); }();
     static inline onikaDim3_t s_gpu_block_dims = { 8 , 8 , 4 };
     static inline int parallel_task_core_mult() { return s_parallel_task_core_mult; }
     static inline int parallel_task_core_add() { return s_parallel_task_core_add; }

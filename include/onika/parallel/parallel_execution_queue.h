@@ -289,7 +289,8 @@ namespace onika { namespace parallel {
         pec->init_device_scratch();
         pec->m_scheduled_on_gpu = true;
         ONIKA_B200_CHECK( onk_op_begin( pec->m_native_op , lane , pec->m_return_data_input , pec->m_return_data_size ,
-                                        ( pec->m_reset_counters || pec->m_grid_size.x > 0 ) ? 1 : 0 ) );
+                                        ( ( pec->m_reset_counters || pec->m_grid_size.x > 0 ) ? ONK_OP_RESET_COUNTERS : 0 )
+                                        | ( ParallelExecutionContext::s_gpu_timing ? 0 : ONK_OP_NO_TIMING ) ) );
         func.stream_gpu_initialize( pec , exec_stream );
         func.stream_gpu_kernel( pec , exec_stream );
         func.stream_gpu_finalize( pec , exec_stream );

@@ -104,10 +104,14 @@ int onk_prefetch(const void* ptr, size_t bytes, int to_device, int lane); /* ONI
 typedef struct onk_op onk_op;
 #define ONK_OP_SCRATCH_BYTES      1024
 #define ONK_OP_MAX_RETURN_BYTES    960
+/* flags of onk_op_begin (its last argument; 0/1 keep their former meaning) */
+#define ONK_OP_RESET_COUNTERS      1   /* zero the 8 scratch counters (work-stealing ticket ...) before the kernel */
+#define ONK_OP_NO_TIMING           2   /* do not bracket the operation with timing events: onk_op_elapsed_ms reports 0 (saves ~3 us of
+                                          host time per operation; the reference always times, src/parallel/parallel_execution_queue.cpp:328-356) */
 int onk_op_create(onk_op** op);
 int onk_op_destroy(onk_op* op);
 int onk_op_device_scratch(onk_op* op, void** scratch_dev);   /* init_device_scratch(), parallel_execution_context.cpp:102-118 */
-int onk_op_begin(onk_op* op, int lane, const void* return_init_host, size_t return_bytes, int reset_counters);
+int onk_op_begin(onk_op* op, int lane, const void* return_init_host, size_t return_bytes, int flags);
 int onk_op_end(onk_op* op, void* return_out_host, size_t return_bytes, void (*epilog)(void*), void* user);
 int onk_op_elapsed_ms(onk_op* op, float* ms);                /* valid after the lane was synchronised */
 

@@ -379,11 +379,12 @@ int onk_op_begin(onk_op* op, int lane, const void* return_init_host, size_t retu
   op->began = true; op->ended = false;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   ONK_CUDA(cudaStreamIsCapturing(op->stream, &cap));
-  op->captured = (cap != cudaStreamCaptureStatusNone);   // timing events mean nothing inside a graph: skipped, elapsed = 0
+  // timing events mean nothing inside a graph, and a caller may opt out of them (ONK_OP_NO_TIMING): elapsed = 0 then
+  op->captured = (cap != cudaStreamCaptureStatusNone) || (reset_counters & ONK_OP_NO_TIMING) != 0;
   if (!op->captured) ONK_CUDA(cudaEventRecord(op->start, op->stream));
   if (return_init_host != nullptr && return_bytes > 0)
     ONK_CUDA(cudaMemcpyAsync((char*)scratch + 64, return_init_host, return_bytes, cudaMemcpyDefault, op->stream));
-  if (reset_counters)
+  if (reset_counters & ONK_OP_RESET_COUNTERS)
     ONK_CUDA(cudaMemsetAsync(scratch, 0, 64, op->stream));
   return ONK_OK;
 }

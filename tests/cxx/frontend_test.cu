@@ -439,6 +439,17 @@ static int scenario_graph(Out& out, size_t rows, size_t cols, int replays, int n
     const double t = std::chrono::duration<double,std::milli>( std::chrono::steady_clock::now() - t0 ).count();
     if( rep == 0 || t < ms[0] ) { ms[0] = t; submit_ms = tf; }
   }
+  double untimed_ms = 0;
+  ParallelExecutionContext::s_gpu_timing = false;              // same operations without the per-operation timing events
+  for(int rep=0;rep<3;rep++)
+  {
+    for(int k=0;k<nsmall;k++) pq << set_lane(0) << block_parallel_for( 8 , RepeatedAddFunctor{ S , 1.0 , 1 } , parallel_execution_context("S","untimed") );
+    auto t0 = std::chrono::steady_clock::now();
+    pq << flush << synchronize;
+    const double t = std::chrono::duration<double,std::milli>( std::chrono::steady_clock::now() - t0 ).count();
+    if( rep == 0 || t < untimed_ms ) untimed_ms = t;
+  }
+  ParallelExecutionContext::s_gpu_timing = true;
   {
     ParallelExecutionGraph g;
     pq << capture(g);
@@ -452,9 +463,9 @@ static int scenario_graph(Out& out, size_t rows, size_t cols, int replays, int n
       if( rep == 0 || t < ms[1] ) ms[1] = t;
     }
   }
-  std::printf("graph: %d small operations : scheduled one by one %.3f ms (flush alone %.3f ms) , one graph replay %.3f ms\n", nsmall, ms[0], submit_ms, ms[1]);
+  std::printf("graph: %d small operations : scheduled one by one %.3f ms (flush alone %.3f ms) , without timing events %.3f ms , one graph replay %.3f ms\n", nsmall, ms[0], submit_ms, untimed_ms, ms[1]);
   out.doubles( ms , 2 );
-  out.doubles( S.data() , 8*256 );                             // every element was incremented 6*nsmall times
+  out.doubles( S.data() , 8*256 );                             // every element was incremented 9*nsmall times
   return pq.empty() ? 0 : 3;
 }
 

@@ -129,7 +129,7 @@ def test_queue_capture_and_replay(prog, tmp_path):
     assert r[4] == 5 and r[5] == 2                                # 5 operations on 2 lanes (arrays A and B)
     direct_ms, graph_ms = d[2 * n + 6:2 * n + 8]
     small = d[2 * n + 8:]
-    assert np.array_equal(small, np.full(8 * 256, 6.0 * nsmall))
+    assert np.array_equal(small, np.full(8 * 256, 9.0 * nsmall))
     assert graph_ms < direct_ms, (direct_ms, graph_ms)
 
 
