@@ -121,6 +121,24 @@ def test_reduce_min_full_size_2pow28_properties(ob):
     del t
 
 
+@pytest.mark.parametrize("offset", [0, 1, 2, 3])
+@pytest.mark.parametrize("n", [296 * 8192 - 1, 296 * 8192 + 3, 5_000_001])
+def test_reduce_large_inputs_unaligned_starts_and_ragged_tails(ob, orc, offset, n):
+    """around and above the size where the reduction switches to the TMA-staged body (2 tiles of 8192 doubles per SM):
+    starts that are 8-byte but not 32-byte aligned (scalar head), tails that do not fill a tile"""
+    import torch
+    from onika_b200 import parallel as P
+    from tests._inputs import lcg_uniform
+    d = lcg_uniform(n + offset, 77, -1.0, 1.0)
+    t = torch.from_numpy(d).cuda()[offset:]
+    h = d[offset:]
+    assert host(P.reduce_min(t))[0] == orc.reduce_min(h)
+    assert host(P.reduce_max(t))[0] == orc.reduce_max(h)
+    s1, s2 = host(P.reduce_sum(t))[0], host(P.reduce_sum(t))[0]
+    assert s1 == s2
+    assert abs(s1 - orc.reduce_sum_ld(h)) <= SUM_RTOL * np.abs(h).sum()
+
+
 def test_more_than_2pow32_elements(ob):
     """maximum sizes: the reference's GPU trampoline carries the start index as `unsigned int`
     (block_parallel_for_adapter.h:51-66), i.e. N <= 2^32; here indices are 64-bit throughout.  2^32 + 4099 doubles (34.4 GB):
