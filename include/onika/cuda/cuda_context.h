@@ -29,8 +29,15 @@ static inline constexpr auto onikaErrorNotReady      = cudaErrorNotReady;
 static inline constexpr auto onikaMemcpyDeviceToHost = cudaMemcpyDeviceToHost;
 static inline constexpr auto onikaMemcpyHostToDevice = cudaMemcpyHostToDevice;
 #define ONIKA_CU_NAME_STR                              "cuda-sm100a"
-#define ONIKA_CU_PROF_RANGE_PUSH(s)                    ((void)(s))
-#define ONIKA_CU_PROF_RANGE_POP()                      ((void)0)
+// NVTX ranges (header-only NVTX3: a no-op unless a profiler injects its library), as the reference does around operators
+#if __has_include(<nvtx3/nvToolsExt.h>) && ! defined(ONIKA_B200_NO_NVTX)
+#  include <nvtx3/nvToolsExt.h>
+#  define ONIKA_CU_PROF_RANGE_PUSH(s)                  nvtxRangePush(s)
+#  define ONIKA_CU_PROF_RANGE_POP()                    nvtxRangePop()
+#else
+#  define ONIKA_CU_PROF_RANGE_PUSH(s)                  ((void)(s))
+#  define ONIKA_CU_PROF_RANGE_POP()                    ((void)0)
+#endif
 #define ONIKA_CU_PROF_START()                          ((void)0)
 #define ONIKA_CU_PROF_STOP()                           ((void)0)
 #define ONIKA_CU_MEM_PREFETCH(ptr,sz,d,st)             cudaMemPrefetchAsync((const void*)(ptr),sz,d,st)
@@ -70,6 +77,8 @@ using onikaEvent_t  = void*;
 using onikaError_t  = int;
 static inline constexpr int onikaSuccess = 0;
 #define ONIKA_CU_NAME_STR "cuda-sm100a(host TU)"
+#define ONIKA_CU_PROF_RANGE_PUSH(s)                    ((void)(s))
+#define ONIKA_CU_PROF_RANGE_POP()                      ((void)0)
 #endif
 
 struct onikaInt3_t

@@ -76,8 +76,10 @@ namespace onika { namespace scg {
     inline void run()
     {
       parallel_execution_queue() << parallel::flush << parallel::synchronize;
+      ONIKA_CU_PROF_RANGE_PUSH( m_name.c_str() );            // one NVTX range per operator (src/scg/operator.cpp:414,487)
       execute();
       parallel_execution_queue() << parallel::flush << parallel::synchronize;
+      ONIKA_CU_PROF_RANGE_POP();
     }
 
   private:
