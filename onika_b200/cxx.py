@@ -51,6 +51,14 @@ REFERENCE_TUTORIAL = "/root/reference/plugins/onikaParallelTutorial"
 REFPLUGIN_BIN = os.path.join(CXX_TESTS, "_refplugins", "run_reference_tutorial")
 
 
+REFERENCE_TESTS = os.path.join(os.path.dirname(os.path.dirname(REFERENCE_TUTORIAL)), "tests")
+REFERENCE_GPU_TESTS = ("gpu_uvm_benchmark", "gpu_reduce_min_fp64")
+
+
+def reference_test_path(name: str) -> str:
+    return os.path.join(os.path.dirname(REFPLUGIN_BIN), "ref_" + name)
+
+
 def build_reference_plugins(force: bool = False, verbose: bool = False):
     """Compile the reference's OWN tutorial plugin sources, unchanged and from where they lie (never copied), against
     this repo's include/onika + the operator runner.  Only possible where /root/reference exists; the binary lands in the
@@ -62,6 +70,12 @@ def build_reference_plugins(force: bool = False, verbose: bool = False):
     if not force and os.path.exists(REFPLUGIN_BIN) and os.path.getmtime(REFPLUGIN_BIN) > newest and not needs_build("frontend_test"):
         return REFPLUGIN_BIN
     os.makedirs(os.path.dirname(REFPLUGIN_BIN), exist_ok=True)
+    # the reference's own stand-alone GPU tests of this path (tests/gpu_uvm_benchmark.cu, tests/gpu_reduce_min_fp64.cu):
+    # each is one translation unit with its own main(), compiled unchanged against include/onika
+    for name in REFERENCE_GPU_TESTS:
+        src = os.path.join(REFERENCE_TESTS, name + ".cu")
+        if os.path.exists(src):
+            compile_program([src], reference_test_path(name), verbose=verbose)
     return compile_program([os.path.join(CXX_TESTS, "run_operator.cu")] + srcs, REFPLUGIN_BIN, verbose=verbose)
 
 

@@ -345,3 +345,33 @@ def test_reference_plugins_from_msp_example_shape(tmp_path):
     x = _chain(np.zeros((4, 256)), 2.3, 2) + 2.3           # concurrent_block_parallel
     x = _chain(x, 0.5, 1) + 0.5                            # automatic_concurrent_parallel on the same arrays
     assert np.allclose(_load_array(out), x, rtol=1e-10, atol=0)     # pow/sin: libm vs libdevice, few iterations (the map is chaotic)
+
+
+def _run_reference_test(name, stdin):
+    from onika_b200 import cxx
+    exe = cxx.reference_test_path(name)
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built (needs /root/reference at build time)")
+    r = subprocess.run([exe], input=stdin, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stdout[-1500:], r.stderr[-1500:])
+    return r.stdout
+
+
+@pytest.mark.parametrize("uvm", [1, 0])
+def test_reference_gpu_uvm_benchmark_unchanged(uvm):
+    """tests/gpu_uvm_benchmark.cu compiled unchanged: managed or explicit device memory, a kernel launched with
+    ONIKA_CU_LAUNCH_KERNEL iterating x <- x*x - 0.25 ten million times (converges to (1 - sqrt 2)/2 from [0,1))"""
+    out = _run_reference_test("gpu_uvm_benchmark", f"0 {uvm} 5\n")
+    line = [ln for ln in out.splitlines() if ln.startswith("result[5]")][0]
+    vhost, vcuda = (float(v) for v in line.split("=")[1].split("/"))
+    assert abs(vhost - 5.0 / (1024 * 1024)) < 1e-9            # printed with 6 significant digits
+    assert abs(vcuda - (1.0 - 2.0 ** 0.5) / 2.0) < 1e-6
+
+
+def test_reference_gpu_reduce_min_fp64_unchanged():
+    """tests/gpu_reduce_min_fp64.cu compiled unchanged: its CPU reduction (the oracle's restated fixture, minimum 0 at i = 0)
+    runs, its GPU part is the reference's TODO; device allocation / copy / synchronise macros are exercised"""
+    out = _run_reference_test("gpu_reduce_min_fp64", "1 0 0\n")
+    assert "GPU reduction not implemented yet" in out
+    line = [ln for ln in out.splitlines() if ln.startswith("result =")][0]
+    assert [float(v) for v in line.split("=")[1].split("/")] == [0.0, 0.0]
