@@ -52,7 +52,7 @@ REFPLUGIN_BIN = os.path.join(CXX_TESTS, "_refplugins", "run_reference_tutorial")
 
 
 REFERENCE_TESTS = os.path.join(os.path.dirname(os.path.dirname(REFERENCE_TUTORIAL)), "tests")
-REFERENCE_GPU_TESTS = ("gpu_uvm_benchmark", "gpu_reduce_min_fp64")
+REFERENCE_GPU_TESTS = ("gpu_uvm_benchmark", "gpu_reduce_min_fp64", "parallel_queue_lane")
 
 
 def reference_test_path(name: str) -> str:
@@ -70,7 +70,8 @@ def build_reference_plugins(force: bool = False, verbose: bool = False):
     if not force and os.path.exists(REFPLUGIN_BIN) and os.path.getmtime(REFPLUGIN_BIN) > newest and not needs_build("frontend_test"):
         return REFPLUGIN_BIN
     os.makedirs(os.path.dirname(REFPLUGIN_BIN), exist_ok=True)
-    # the reference's own stand-alone GPU tests of this path (tests/gpu_uvm_benchmark.cu, tests/gpu_reduce_min_fp64.cu):
+    # the reference's own stand-alone GPU tests of this path (tests/gpu_uvm_benchmark.cu, tests/gpu_reduce_min_fp64.cu,
+    # tests/parallel_queue_lane.cu -- the latter through the include/onika/app/api.h boundary shim):
     # each is one translation unit with its own main(), compiled unchanged against include/onika
     for name in REFERENCE_GPU_TESTS:
         src = os.path.join(REFERENCE_TESTS, name + ".cu")

@@ -375,3 +375,20 @@ def test_reference_gpu_reduce_min_fp64_unchanged():
     assert "GPU reduction not implemented yet" in out
     line = [ln for ln in out.splitlines() if ln.startswith("result =")][0]
     assert [float(v) for v in line.split("=")[1].split("/")] == [0.0, 0.0]
+
+
+@pytest.mark.parametrize("mode", ["hybrid-lane", "hybrid-delayed-lane", "hybrid-sequence", "singletask-dependency"])
+@pytest.mark.parametrize("omp_mode", ["task", "pfor"])
+@pytest.mark.parametrize("dims", ["1d", "2d"])
+def test_reference_parallel_queue_lane_unchanged(mode, omp_mode, dims):
+    """tests/parallel_queue_lane.cu compiled unchanged (4 queue modes x OpenMP task / parallel-for context x 1D / 2D kernels):
+    the program only prints (the reference checks nothing); results of the same scenarios are verified bit for bit by
+    test_parallel_queue_lane_scenarios above"""
+    from onika_b200 import cxx
+    exe = cxx.reference_test_path("parallel_queue_lane")
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, mode, omp_mode, dims], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[-1500:], r.stderr[-1500:])
+    assert "Synchronize parallel operations" in r.stdout and r.stdout.rstrip().endswith("done")
+    assert ("1D" if dims == "1d" else "2D") + " kernel parallelization space" in r.stdout
