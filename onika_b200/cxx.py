@@ -53,6 +53,7 @@ REFPLUGIN_BIN = os.path.join(CXX_TESTS, "_refplugins", "run_reference_tutorial")
 
 REFERENCE_TESTS = os.path.join(os.path.dirname(os.path.dirname(REFERENCE_TUTORIAL)), "tests")
 REFERENCE_GPU_TESTS = ("gpu_uvm_benchmark", "gpu_reduce_min_fp64", "parallel_queue_lane")
+REFERENCE_SOATL_TESTS = ("soatupletest", "soatlserializetest")
 
 
 def reference_test_path(name: str) -> str:
@@ -77,6 +78,12 @@ def build_reference_plugins(force: bool = False, verbose: bool = False):
         src = os.path.join(REFERENCE_TESTS, name + ".cu")
         if os.path.exists(src):
             compile_program([src], reference_test_path(name), verbose=verbose)
+    # the reference's SOATL correctness tests (tests/soatupletest.cpp, tests/soatlserializetest.cpp; asserts enabled), with
+    # the reference's own tests/declare_fields.h
+    for name in REFERENCE_SOATL_TESTS:
+        src = os.path.join(REFERENCE_TESTS, name + ".cpp")
+        if os.path.exists(src):
+            compile_program([src], reference_test_path(name), extra_flags=["-x", "cu", "-I" + REFERENCE_TESTS], verbose=verbose)
     return compile_program([os.path.join(CXX_TESTS, "run_operator.cu")] + srcs, REFPLUGIN_BIN, verbose=verbose)
 
 

@@ -392,3 +392,16 @@ def test_reference_parallel_queue_lane_unchanged(mode, omp_mode, dims):
     assert r.returncode == 0, (r.returncode, r.stdout[-1500:], r.stderr[-1500:])
     assert "Synchronize parallel operations" in r.stdout and r.stdout.rstrip().endswith("done")
     assert ("1D" if dims == "1d" else "2D") + " kernel parallelization space" in r.stdout
+
+
+@pytest.mark.parametrize("name,args", [("soatupletest", ["10"]), ("soatupletest", ["1000", "3"]), ("soatlserializetest", ["10000"]), ("soatlserializetest", ["7"])])
+def test_reference_soatl_tests_unchanged(tmp_path, name, args):
+    """tests/soatupletest.cpp and tests/soatlserializetest.cpp compiled unchanged (their own declare_fields.h, asserts on):
+    find_index_of_id static_asserts, tuple copies, clear() -> null pointers, copy variants and the storage_ptr() file round
+    trip with exact equality (CMakeLists.txt registers them with 10 and 10000)"""
+    from onika_b200 import cxx
+    exe = cxx.reference_test_path(name)
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, *args], capture_output=True, text=True, timeout=300, cwd=tmp_path)     # serialize.dat lands in cwd
+    assert r.returncode == 0, (r.returncode, r.stdout[-1500:], r.stderr[-1500:])
