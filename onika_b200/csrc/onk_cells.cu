@@ -348,16 +348,10 @@ namespace onk
   // FIELD-MAJOR cell grid: the summed field of ALL cells is one contiguous column, cell c owning the run
   // [cell_begin[c], cell_begin[c+1]) (what an exaNBody-style grid calls its cell offsets).  The per-cell blocks of the
   // reference layout force 128 useful bytes out of every 512 through the memory system (DRAM traffic 1.4x the
-  // algorithmic bytes, kernel above); in this layout the kernel is a pure stream: a CTA takes 256 consecutive cells per
-  // step, moves their values global -> shared with 8-byte cp.async (LDGSTS.64, consecutive lanes = consecutive values,
-  // 3 tiles in flight per SM) and thread t folds cell t in particle order from shared memory -- same bits as the
-  // per-cell host loop.  Shared-memory index i lives at i + i/16: with 16-particle cells the 256 threads would
-  // otherwise start 128 bytes apart, i.e. all in the same bank.
-  constexpr int PK_CELLS  = THREADS;                 // cells per tile (one per thread)
-  constexpr int PK_CAP    = 4352;                    // values staged per tile (17 per cell on average: Poisson(16) tiles fit with 4 sigma to
-                                                     // spare; whatever exceeds it is read from global memory by the owning thread)
-  constexpr int PK_ROW    = PK_CAP + PK_CAP / 16 + 16;
-  template<int STAGES> constexpr size_t pk_smem() { return (size_t)STAGES * PK_ROW * sizeof(double); }
+  // algorithmic bytes, kernel above); in this layout the kernel is a pure stream: a CTA of NT threads takes NT consecutive
+  // cells per step, moves their values global -> shared with cp.async and thread t folds cell t in particle order from
+  // shared memory -- same bits as the per-cell host loop.  17 values per cell are staged on average (Poisson(16) tiles
+  // fit with 4 sigma to spare); whatever exceeds that is read from global memory by the owning thread.
 
   // Tile staging: values go global -> shared as 16-byte pieces (LDGSTS.128 bypassing L1; the 8-byte form drags three
   // no-op shared loads per copy along on sm_100), starting at the 16-byte aligned element at or below the tile's first
@@ -384,18 +378,20 @@ namespace onk
   // particles: with uneven densities a static round robin would leave SMs idle; on the uniform Poisson(16) grid both
   // measure the same 64 us.  Every CTA draws until its first out-of-range ticket: exactly ntiles draws in total, and
   // whoever draws the last one puts the counter back to zero for the next launch.
-  template<int CTAS>
-  __global__ void __launch_bounds__(THREADS, CTAS)
+  template<int CTAS, int NT>
+  __global__ void __launch_bounds__(NT, CTAS)
   cell_sum_packed_f64_kernel(const double* __restrict__ values, const uint64_t* __restrict__ cell_begin, uint64_t ncells,
                              double* __restrict__ cell_sum, double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ total)
   {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ unsigned long long s_next_tile[2];
     const unsigned tile_smem = smem_u32(dyn_smem);
-    constexpr int COPY_ITERS = (PK_CAP / 2 + THREADS - 1) / THREADS;       // 16-byte pieces per thread and tile
+    constexpr int PK_CELLS = NT;                                             // cells per tile (one per thread)
+    constexpr int PK_CAP = 17 * NT;                                          // values staged per tile
+    constexpr int COPY_ITERS = (PK_CAP / 2 + NT - 1) / NT;       // 16-byte pieces per thread and tile
     const uint64_t ntiles = (ncells + PK_CELLS - 1) / PK_CELLS;
     const unsigned parity = (unsigned)(((uintptr_t)values >> 3) & 1u);   // element g is 16-byte aligned iff g + parity is even
-    const unsigned pair_slot0 = (threadIdx.x + (threadIdx.x >> 4)) * 16u;  // byte offset of pair j = tid + 256*it: pair_slot0 + 272*16*it
+    const unsigned pair_slot0 = (threadIdx.x + (threadIdx.x >> 4)) * 16u;  // byte offset of pair j = tid + NT*it: pair_slot0 + (NT + NT/16)*16*it
     unsigned* tile_counter = ticket + 1;
     double thread_total = 0.0;
     bool drawing = true;                                                  // thread 0: this CTA has not yet drawn an out-of-range ticket
@@ -444,9 +440,9 @@ namespace onk
       const uint32_t npairs = cnt >> 1;
 #pragma unroll
       for (int it = 0; it < COPY_ITERS; it++)
-        if (threadIdx.x + (unsigned)it * THREADS < npairs) cp_async16(dst + (unsigned)it * (272u * 16u), src + it * THREADS);
-      if ((cnt & 1u) != 0u && threadIdx.x == (npairs & (THREADS - 1u)))       // odd tail: 8 valid bytes, the rest zero-filled
-        cp_async16_zfill(dst + (npairs / THREADS) * (272u * 16u), src + (npairs / THREADS) * THREADS, 8u);
+        if (threadIdx.x + (unsigned)it * NT < npairs) cp_async16(dst + (unsigned)it * ((unsigned)(NT + NT / 16) * 16u), src + it * NT);
+      if ((cnt & 1u) != 0u && threadIdx.x == (npairs & (unsigned)(NT - 1)))       // odd tail: 8 valid bytes, the rest zero-filled
+        cp_async16_zfill(dst + (npairs / NT) * ((unsigned)(NT + NT / 16) * 16u), src + (npairs / NT) * NT, 8u);
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
@@ -493,7 +489,7 @@ namespace onk
       nxt = s_next_tile[slot];
       if (cur < ntiles) issue(nxt);
     }
-    cell_total_finish(thread_total, partials, ticket, total);
+    cell_total_finish<NT>(thread_total, partials, ticket, total);
   }
 }
 
@@ -585,12 +581,19 @@ int onk_cell_sum_packed_f64(const double* values_dev, const uint64_t* cell_begin
     ONK_CHECK_LAUNCH(); count_launch();
     return ONK_OK;
   }
-  constexpr int PK_CTAS = 5;
-  static bool configured = false;
-  if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_packed_f64_kernel<PK_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pk_smem<1>())); configured = true; }
-  unsigned grid = grid_for(ncells, PK_CELLS, PK_CTAS);
-  if (grid > (unsigned)MAX_PARTIALS) grid = MAX_PARTIALS;
-  cell_sum_packed_f64_kernel<PK_CTAS><<<grid, THREADS, pk_smem<1>(), L->stream>>>(values_dev, cell_begin_dev, ncells, cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev);
+  // CTA shape (ONK_PK_SHAPE, tuning): resident CTAs per SM x threads.  Smaller CTAs pay less per barrier, too small ones
+  // too much per tile: 10 x 128 59 us (default), 12 x 128 61, 5 x 256 61, 8 x 128 65, 20 x 64 65, 3 x 512 68, 2 x 512 76,
+  // 1 x 1024 94 us on 128^3 cells (C ABI call with preallocated outputs, cold L2)
+  static const int shape = []{ const char* e = getenv("ONK_PK_SHAPE"); return e ? atoi(e) : 0; }();
+#define ONK_PK_GO(C, NTH) do { \
+    constexpr size_t smem = (size_t)(17 * NTH + (17 * NTH) / 16 + 16) * 8; \
+    static bool configured = false; \
+    if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_packed_f64_kernel<C, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; } \
+    unsigned grid = grid_for(ncells, NTH, C); \
+    if (grid > (unsigned)MAX_PARTIALS) grid = MAX_PARTIALS; \
+    cell_sum_packed_f64_kernel<C, NTH><<<grid, NTH, smem, L->stream>>>(values_dev, cell_begin_dev, ncells, cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev); } while (0)
+  if (shape == 1) ONK_PK_GO(5, 256); else if (shape == 2) ONK_PK_GO(3, 512); else ONK_PK_GO(10, 128);
+#undef ONK_PK_GO
   ONK_CHECK_LAUNCH(); count_launch();
   return ONK_OK;
 }
