@@ -152,7 +152,9 @@ int onk_combine_f64(int op, const double* partials_dev, uint32_t count, double* 
  * partials in RANK ORDER -- every rank gets the same bits, sums are reproducible, no collective library call.
  * Exchange buffers are ONK_XCHG_BYTES of device memory per rank (onk_xchg_create), shared between the processes of one
  * node through CUDA IPC: export the local handle, all-gather the handles with any host-side transport, open the peers.
- * All ranks must call onk_reduce_xchg_f64 the same number of times (the call count is the flag epoch). */
+ * All ranks must issue the same sequence of calls on an exchange (reductions, all-reduces, barriers: the call count is the
+ * flag epoch), and all calls on one exchange must go to the same lane (they complete in issue order); use one exchange per
+ * lane for independent sequences. */
 #define ONK_XCHG_BYTES      4096
 #define ONK_XCHG_MAX_WORLD    16
 #define ONK_XCHG_MAX_VALUES    8
