@@ -97,21 +97,51 @@ namespace onk
 
   struct XsWindows { unsigned char* out[ONK_XCHG_MAX_WORLD]; };
 
-  // element i of `in` -> window[d] at index j, as pieces of sizeof(P) bytes; thread t handles piece t of the flat stream
+  // 32-byte piece moved with one 256-bit load and one 256-bit store
+  struct alignas(32) XsPiece32 { unsigned long long a, b, c, d; };
+  template<class P> __device__ __forceinline__ P xs_load(const P* p) { return *p; }
+  template<class P> __device__ __forceinline__ void xs_store(P* p, const P& v) { *p = v; }
+  template<> __device__ __forceinline__ XsPiece32 xs_load<XsPiece32>(const XsPiece32* p)
+  {
+    XsPiece32 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p));
+    return v;
+  }
+  template<> __device__ __forceinline__ void xs_store<XsPiece32>(XsPiece32* p, const XsPiece32& v)
+  {
+    asm volatile("st.global.L1::no_allocate.v4.u64 [%0], {%1,%2,%3,%4};" :: "l"(p), "l"(v.a), "l"(v.b), "l"(v.c), "l"(v.d) : "memory");
+  }
+
+  // element i of `in` -> window[d] at index j, as pieces of sizeof(P) bytes; thread t handles piece t of the flat stream.
+  // XS_UNROLL pieces per thread and step are loaded (route and payload) before the first store: the stores go to other
+  // GPUs, the loads keep the local HBM busy meanwhile.
+  constexpr int XS_UNROLL = 4;
   template<class P>
   __global__ void __launch_bounds__(256)
   xs_scatter_kernel(const P* __restrict__ in, unsigned long long n_before, unsigned pieces_per_elem,
                     const unsigned long long* __restrict__ route, const __grid_constant__ XsWindows w)
   {
     const unsigned long long total = n_before * pieces_per_elem;
-    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x)
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long t0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += stride * XS_UNROLL)
     {
-      const unsigned long long i = t / pieces_per_elem;
-      const unsigned c = (unsigned)(t - i * pieces_per_elem);
-      const unsigned long long r = route[i];
-      const int d = (int)(r >> XS_OWNER_SHIFT) - 1;
-      const unsigned long long j = r & XS_INDEX_MASK;
-      reinterpret_cast<P*>(w.out[d])[j * pieces_per_elem + c] = in[t];
+      P v[XS_UNROLL]; P* dst[XS_UNROLL];
+#pragma unroll
+      for (int u = 0; u < XS_UNROLL; u++)
+      {
+        const unsigned long long t = t0 + (unsigned long long)u * stride;
+        dst[u] = nullptr;
+        if (t < total)
+        {
+          const unsigned long long i = (pieces_per_elem == 1u) ? t : t / pieces_per_elem;
+          const unsigned c = (unsigned)(t - i * pieces_per_elem);
+          const unsigned long long r = __ldg(route + i);
+          dst[u] = reinterpret_cast<P*>(w.out[(int)(r >> XS_OWNER_SHIFT) - 1]) + (r & XS_INDEX_MASK) * pieces_per_elem + c;
+          v[u] = xs_load(in + t);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < XS_UNROLL; u++) if (dst[u] != nullptr) xs_store(dst[u], v[u]);
     }
   }
 }
@@ -339,11 +369,13 @@ int onk_xs_move(onk_xs_plan* plan, onk_window* out, uint64_t elem_bytes, const v
   if (plan->n_before > 0)
   {
     const uintptr_t a = (uintptr_t)in_dev;
-    const unsigned piece = (elem_bytes % 16 == 0 && a % 16 == 0) ? 16u : (elem_bytes % 8 == 0 && a % 8 == 0) ? 8u : (elem_bytes % 4 == 0 && a % 4 == 0) ? 4u : 1u;
+    const unsigned piece = (elem_bytes % 32 == 0 && a % 32 == 0) ? 32u : (elem_bytes % 16 == 0 && a % 16 == 0) ? 16u
+                         : (elem_bytes % 8 == 0 && a % 8 == 0) ? 8u : (elem_bytes % 4 == 0 && a % 4 == 0) ? 4u : 1u;
     const unsigned ppe = (unsigned)(elem_bytes / piece);
-    const unsigned grid = grid_for(plan->n_before * ppe, 256 * 4, 8);
+    const unsigned grid = grid_for(plan->n_before * ppe, 256 * XS_UNROLL, 8);
     switch (piece)
     {
+      case 32: xs_scatter_kernel<XsPiece32><<<grid, 256, 0, L->stream>>>((const XsPiece32*)in_dev, plan->n_before, ppe, plan->route, w); break;
       case 16: xs_scatter_kernel<uint4><<<grid, 256, 0, L->stream>>>((const uint4*)in_dev, plan->n_before, ppe, plan->route, w); break;
       case 8:  xs_scatter_kernel<unsigned long long><<<grid, 256, 0, L->stream>>>((const unsigned long long*)in_dev, plan->n_before, ppe, plan->route, w); break;
       case 4:  xs_scatter_kernel<unsigned><<<grid, 256, 0, L->stream>>>((const unsigned*)in_dev, plan->n_before, ppe, plan->route, w); break;
