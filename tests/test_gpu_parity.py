@@ -542,7 +542,15 @@ def test_op_bracket_return_data_and_timing(ob):
     assert np.array_equal(out, init + 10.0) and fired == [1]
     ms = C.c_float()
     _capi.check(L.onk_op_elapsed_ms(op, C.byref(ms)))
-    assert ms.value >= 0.0
+    assert ms.value > 0.0                                      # timed bracket: two events around copies + kernel
+    # ONK_OP_NO_TIMING (flag 2; 1 = reset counters): same data protocol, no events, elapsed reports 0
+    out2 = np.zeros(2)
+    _capi.check(L.onk_op_begin(op, 2, init.ctypes.data, 16, 1 | 2))
+    _capi.check(L.onk_value_add_f64(scratch.value + 64, 1, 2, 20.0, 2))
+    _capi.check(L.onk_op_end(op, out2.ctypes.data, 16, None, None))
+    ob.lane_sync(2)
+    _capi.check(L.onk_op_elapsed_ms(op, C.byref(ms)))
+    assert np.array_equal(out2, init + 20.0) and ms.value == 0.0
     assert L.onk_op_begin(op, 2, init.ctypes.data, 2000, 0) == _capi.ERR_ARG   # > 960 B of return data is rejected
     _capi.check(L.onk_op_destroy(op))
 
