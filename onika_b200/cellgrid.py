@@ -101,6 +101,6 @@ class FieldMajorCellGrid:
         import torch
         sums = torch.empty(max(self.ncells, 1), dtype=torch.float64, device=self.device)[: self.ncells]
         total = torch.zeros(1, dtype=torch.float64, device=self.device) if with_total else None
-        check(lib().onk_cell_sum_packed_f64(ptr(self.columns[field]), ptr(self.cell_begin), self.ncells, ptr(sums),
+        check(lib().onk_cell_sum_packed_f64(ptr(self.columns[field]), self.nparticles, ptr(self.cell_begin), self.ncells, ptr(sums),
                                             ptr(total) if with_total else None, lane))
         return sums, total

@@ -23,6 +23,7 @@
 //     onk_reduce.cu (fixed order, no atomics on data);
 //   * persistent grid: CELL_CTAS_PER_SM x 148 CTAs, warps walk groups of 32 cells grid-stride.
 #include "onk_internal.cuh"
+#include <cuda.h>
 #include <cstdlib>
 
 namespace onk
@@ -493,6 +494,132 @@ namespace onk
   }
 }
 
+namespace onk
+{
+  // ---- field-major grid, TMA-staged: the tile is ONE tensor-map bulk copy ----
+  // The value column is described to the TMA unit as a 2D tensor of 16-double (128-byte) rows; a tile of NT cells is the box
+  // of BOXROWS rows starting at the row that holds the tile's first value, brought in by one cp.async.bulk.tensor issued by
+  // one thread (no per-thread copy loop, no slot arithmetic on the way in) and laid out with the 128-byte swizzle: the
+  // 16-byte chunk c of row r lands at chunk c ^ (r & 7), so cells that start a multiple of 16 values apart (uniform
+  // 16-particle cells: every thread at chunk 0 of its own row) spread over the banks.  Rows past the last full row of the
+  // column are never requested (out-of-bounds rows are zero-filled by the unit); their values, like those of tiles longer
+  // than the box, are read from global memory by the owning thread.
+  template<int CTAS, int NT, int BOXROWS>
+  __global__ void __launch_bounds__(NT, CTAS)
+  cell_sum_packed_tma_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ values, uint64_t nrows_full,
+                             const uint64_t* __restrict__ cell_begin, uint64_t ncells,
+                             double* __restrict__ cell_sum, double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ total)
+  {
+    extern __shared__ unsigned char dyn_smem[];
+    __shared__ unsigned long long s_next_tile[2];
+    __shared__ __align__(8) unsigned long long s_bar;
+    constexpr unsigned BOX_BYTES = BOXROWS * 128u;
+    const unsigned tile_smem = (smem_u32(dyn_smem) + 1023u) & ~1023u;     // the swizzle pattern is anchored at 1024-byte boundaries
+    const unsigned bar = smem_u32(&s_bar);
+    const uint64_t ntiles = (ncells + NT - 1) / NT;
+    unsigned* tile_counter = ticket + 1;
+    double thread_total = 0.0;
+    bool drawing = true;
+    if (threadIdx.x == 0)
+    {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    auto draw = [&](int slot)                                             // thread 0 only
+    {
+      unsigned long long t = ~0ull;
+      if (drawing)
+      {
+        const unsigned old = atomicAdd(tile_counter, 1u);
+        t = (unsigned long long)gridDim.x + old;
+        if (t >= ntiles) drawing = false;
+        if ((uint64_t)old + 1u == ntiles) atomicExch(tile_counter, 0u);   // the last draw of the launch
+      }
+      s_next_tile[slot] = t;
+    };
+
+    uint64_t nx_b = 0, nx_e = 0, nx_base = 0;
+    auto load_tables = [&](uint64_t tile)
+    {
+      nx_b = nx_e = nx_base = 0;
+      if (tile < ntiles)
+      {
+        const uint64_t c0 = tile * NT, c = c0 + threadIdx.x;
+        nx_base = __ldg(cell_begin + c0);
+        if (c < ncells) { nx_b = __ldg(cell_begin + c); nx_e = __ldg(cell_begin + c + 1); } else { nx_b = nx_e = nx_base; }
+      }
+    };
+
+    uint32_t pb = 0, pe = 0, cnt = 0; uint64_t row0 = 0;
+    auto issue = [&](uint64_t following)
+    {
+      row0 = nx_base >> 4;                                                // first row of the box
+      const uint64_t first = row0 << 4;
+      const uint64_t rb = nx_b - first, re = nx_e - first;
+      pb = rb < 0xffffffffull ? (uint32_t)rb : 0xffffffffu;
+      pe = re < 0xffffffffull ? (uint32_t)re : 0xffffffffu;
+      const uint64_t rows_avail = row0 < nrows_full ? nrows_full - row0 : 0;
+      cnt = (uint32_t)((rows_avail < (uint64_t)BOXROWS ? rows_avail : (uint64_t)BOXROWS) << 4);
+      if (threadIdx.x == 0)
+      {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(BOX_BYTES) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     :: "r"(tile_smem), "l"(&tmap), "r"(0), "r"((int)row0), "r"(bar) : "memory");
+      }
+      load_tables(following);
+    };
+    auto slot_addr = [&](uint32_t q) -> unsigned                          // value q of the box, swizzled
+    {
+      const uint32_t row = q >> 4;
+      return tile_smem + (row << 7) + ((((q >> 1) ^ row) & 7u) << 4) + ((q & 1u) << 3);
+    };
+
+    uint64_t cur = blockIdx.x;
+    if (threadIdx.x == 0) draw(0);
+    load_tables(cur);
+    __syncthreads();                                                      // barrier initialised, first ticket visible
+    uint64_t nxt = s_next_tile[0];
+    if (cur < ntiles) issue(nxt);
+    unsigned phase = 0;
+
+    for (int slot = 1; cur < ntiles; slot ^= 1)                           // CTA-uniform
+    {
+      unsigned landed = 0;
+      while (!landed)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(landed) : "r"(bar), "r"(phase) : "memory");
+      phase ^= 1u;
+      if (threadIdx.x == 0) draw(slot);                                   // ticket of the tile after the next one
+      const uint32_t staged_end = pe < cnt ? pe : cnt;
+      double s = 0.0;
+      if (pb < staged_end)                                                // particle order
+      {
+        uint32_t q = pb;
+        if (q & 1u) { s = __dadd_rn(s, lds64_u32(slot_addr(q))); ++q; }
+        for (; q + 2u <= staged_end; q += 2u)
+        {
+          double x0, x1; lds128_u32(slot_addr(q), x0, x1);
+          s = __dadd_rn(s, x0); s = __dadd_rn(s, x1);
+        }
+        if (q < staged_end) s = __dadd_rn(s, lds64_u32(slot_addr(q)));
+      }
+      const uint64_t c = cur * NT + threadIdx.x;
+      if (pe > cnt && c < ncells)                                         // beyond the box or in the last partial row: global memory
+      {
+        const uint64_t first = row0 << 4;
+        const uint64_t gb = first + (uint64_t)(pb > staged_end ? pb : staged_end), ge = first + (uint64_t)pe;
+        for (uint64_t g = gb; g < ge; g++) s = __dadd_rn(s, ld_stream_ro1(values + g));
+      }
+      if (c < ncells) { cell_sum[c] = s; thread_total = __dadd_rn(thread_total, s); }
+      __syncthreads();                                                    // everybody is done reading the tile; the new ticket is visible
+      cur = nxt;
+      nxt = s_next_tile[slot];
+      if (cur < ntiles) issue(nxt);
+    }
+    cell_total_finish<NT>(thread_total, partials, ticket, total);
+  }
+}
+
 using namespace onk;
 
 extern "C" {
@@ -557,7 +684,7 @@ int onk_cell_sum_f64(const void* arena_dev, const uint64_t* cell_off_dev, const 
   return ONK_OK;
 }
 
-int onk_cell_sum_packed_f64(const double* values_dev, const uint64_t* cell_begin_dev, uint64_t ncells,
+int onk_cell_sum_packed_f64(const double* values_dev, uint64_t nvalues, const uint64_t* cell_begin_dev, uint64_t ncells,
                             double* cell_sum_dev, double* total_dev, int lane)
 {
   Lane* L; if (int rc = lane_get(lane, &L)) return rc;
@@ -578,6 +705,47 @@ int onk_cell_sum_packed_f64(const double* values_dev, const uint64_t* cell_begin
     if (g > (unsigned)MAX_PARTIALS) g = MAX_PARTIALS;
     cell_sum_f64_async_kernel<true,8,3,32><<<g, THREADS, asy_smem<8,3,32>(), L->stream>>>((const uint8_t*)values_dev, cell_begin_dev, nullptr, nullptr, ncells, CellFieldParams{},
                                                                        cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev);
+    ONK_CHECK_LAUNCH(); count_launch();
+    return ONK_OK;
+  }
+  // TMA-staged kernel when the column can be described by a tensor map (16-byte aligned, at least one full 128-byte row);
+  // ONK_PK_KERNEL=ldgsts forces the cp.async kernel below (tuning / comparison)
+  static const bool allow_tma = []{ const char* e = getenv("ONK_PK_KERNEL"); return !(e && e[0] == 'l'); }();
+  const uint64_t nrows_full = nvalues / 16;
+  if (allow_tma && ((uintptr_t)values_dev & 15) == 0 && nrows_full > 0 && nrows_full < (1ull << 31))
+  {
+    typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_t encode = nullptr;
+    if (!encode)
+    {
+      void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+      ONK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+      if (!fn) { set_error("onk_cell_sum_packed_f64: cuTensorMapEncodeTiled entry point not found"); return ONK_ERR_CUDA; }
+      encode = (encode_t)fn;
+    }
+    // shape: 10 resident CTAs of 128 threads, 160-row (20 KiB) boxes for tiles of 128 rows on average.  Measured on 128^3
+    // cells (C ABI call, cold L2): 10x128x160 53.3 us, 6x192x256 53.3, 12x128x144 54.3, 8x128x192 55.3, 20x64x96 65.5,
+    // 16x64x112 66.6; L2 promotion none / 64 B / 128 B 53.2-53.3 us, 256 B 55.3 us
+    constexpr int l2p = (int)CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+#define ONK_PK_TMA_GO(C, NTH, BR) do { \
+    CUtensorMap tmap; \
+    const cuuint64_t gdim[2] = { 16, (cuuint64_t)nrows_full }; \
+    const cuuint64_t gstride[1] = { 128 }; \
+    const cuuint32_t box[2] = { 16, (cuuint32_t)BR }; \
+    const cuuint32_t estr[2] = { 1, 1 }; \
+    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)values_dev, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, \
+                              CU_TENSOR_MAP_SWIZZLE_128B, (CUtensorMapL2promotion)l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE); \
+    if (r != CUDA_SUCCESS) { set_error("onk_cell_sum_packed_f64: cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return ONK_ERR_CUDA; } \
+    constexpr size_t smem = (size_t)BR * 128 + 1024; \
+    static bool configured = false; \
+    if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_packed_tma_kernel<C, NTH, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; } \
+    unsigned grid = grid_for(ncells, NTH, C); \
+    if (grid > (unsigned)MAX_PARTIALS) grid = MAX_PARTIALS; \
+    cell_sum_packed_tma_kernel<C, NTH, BR><<<grid, NTH, smem, L->stream>>>(tmap, values_dev, nrows_full, cell_begin_dev, ncells, cell_sum_dev, \
+                                                                           L->ws.partials, L->ws.ticket, total_dev); } while (0)
+    ONK_PK_TMA_GO(10, 128, 160);
+#undef ONK_PK_TMA_GO
     ONK_CHECK_LAUNCH(); count_launch();
     return ONK_OK;
   }

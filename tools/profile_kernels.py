@@ -115,7 +115,7 @@ def main():
     alg_fm = 8 * fm.nparticles + fm.ncells * 16
     timed("cells_fm", lambda: fm.cell_sum(0), alg_fm, True)
     sums_fm = torch.empty(fm.ncells, dtype=torch.float64, device="cuda")
-    timed("cells_fm_raw", lambda: _capi.check(_capi.lib().onk_cell_sum_packed_f64(ptr(fm.columns[0]), ptr(fm.cell_begin), fm.ncells, ptr(sums_fm), ptr(tot), 0)),
+    timed("cells_fm_raw", lambda: _capi.check(_capi.lib().onk_cell_sum_packed_f64(ptr(fm.columns[0]), fm.nparticles, ptr(fm.cell_begin), fm.ncells, ptr(sums_fm), ptr(tot), 0)),
           alg_fm, True)
     # a plain stream over the same number of bytes, for reference (short kernels do not reach the 2 GiB rate)
     same = torch.rand(alg_fm // 8, dtype=torch.float64, device="cuda")
