@@ -243,7 +243,7 @@ int onk_cell_sum_f64(const void* arena_dev, const uint64_t* cell_off_dev, const 
 /* the same per-cell sum over a FIELD-MAJOR grid: `values_dev` is the summed field of all cells back to back, cell c owns
  * [cell_begin[c], cell_begin[c+1]) (ncells+1 offsets).  Same per-cell bits as the loop above (particle order); the layout
  * turns the kernel into a pure stream (8 B per particle + 16 B per cell of traffic, no padding between cells). */
-int onk_cell_sum_packed_f64(const double* values_dev, uint64_t nvalues /* = cell_begin[ncells], length of the column */,
+int onk_cell_sum_packed_f64(const double* values_dev, uint64_t nvalues /* length of the column = cell_begin[ncells]; must not exceed the allocation (smaller is safe, only slower) */,
                             const uint64_t* cell_begin_dev, uint64_t ncells, double* cell_sum_dev, double* total_dev, int lane);
 
 /* ------------------------------------------------------------------------------------------------------------
