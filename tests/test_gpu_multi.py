@@ -231,3 +231,71 @@ def test_id_redistribution_two_gpus(orc):
             assert np.array_equal(out8, want8[a0:a1]) and np.array_equal(out32, want32[a0:a1]), (ci, rank)
             assert counts == sch.send_count[rank].tolist()
     assert got[0]["rejected"] and got[1]["rejected"]
+
+
+# ---------------------------------------------------------------- config C4 sharded by z-slabs: no halo, one total
+def _worker_c4(rank, world, port, side, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import onika_b200 as ob
+    from onika_b200 import distributed as D, cellgrid, _capi
+    from tests._inputs import lcg_uniform, poisson_counts
+    ob.init(rank)
+    ob.bind_lane_to_torch_stream(0)
+    counts = poisson_counts(side ** 3)
+    e = lcg_uniform(int(counts.sum()), 40, -1.0, 1.0)
+    z0, z1 = D.shard_cells_z(side, rank, world)                    # cells are ordered z-major: a slab is a contiguous cell range
+    c0, c1 = z0 * side * side, z1 * side * side
+    first = np.concatenate([[0], np.cumsum(counts, dtype=np.int64)])
+    mine_counts, mine_e = counts[c0:c1], e[first[c0]:first[c1]]
+    x = D.PeerExchange()
+    out = {}
+    # reference layout (per-cell FieldArrays blocks) and field-major layout: same per-cell bits, one fused all-reduce of both totals
+    cg = cellgrid.CellGrid(mine_counts, 64, 16, (8, 8, 8, 8), 64)
+    cg.upload(cg.host_arena_with_field(3, mine_e))
+    s_arena, t_arena = cg.cell_sum(3)
+    fm = cellgrid.FieldMajorCellGrid(mine_counts, nfields=1)
+    fm.set_field(0, mine_e)
+    s_fm, t_fm = fm.cell_sum(0)
+    totals = torch.cat([t_arena, t_fm])
+    x.allreduce(_capi.OP_SUM, totals)
+    torch.cuda.synchronize()
+    out = (c0, c1, s_arena.cpu().numpy(), s_fm.cpu().numpy(), totals.cpu().numpy())
+    q.put((rank, out))
+    dist.barrier()
+    x.close()
+    dist.destroy_process_group()
+
+
+def test_cell_grid_z_slabs_two_gpus(orc):
+    import torch
+    import torch.multiprocessing as mp
+    from tests._inputs import lcg_uniform, poisson_counts
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, side = 2, 48
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_c4, args=(r, world, port, side, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    counts = poisson_counts(side ** 3)
+    e = lcg_uniform(int(counts.sum()), 40, -1.0, 1.0)
+    begin = np.zeros(counts.size + 1, np.uint64)
+    begin[1:] = np.cumsum(counts, dtype=np.uint64)
+    want, total = orc.cell_sum_packed(e, begin)
+    for rank in range(world):
+        c0, c1, s_arena, s_fm, totals = got[rank]
+        assert np.array_equal(s_arena, want[c0:c1]) and np.array_equal(s_fm, want[c0:c1])      # per-cell sums: bit-exact, both layouts
+        assert abs(totals[0] - total) <= 1e-12 * np.abs(e).sum() and abs(totals[1] - total) <= 1e-12 * np.abs(e).sum()
+    assert np.array_equal(got[0][4], got[1][4])                                                # same bits on both ranks
+    assert got[0][1] == got[1][0] and got[0][0] == 0 and got[1][1] == side ** 3
