@@ -724,6 +724,51 @@ def test_managed_memory_prefetch_and_memcpy(ob, orc):
     _capi.check(L.onk_free(out, 8))
 
 
+def test_managed_memory_host_resident_pages_through_the_tma_kernels(ob, orc):
+    """plugins keep their data in managed memory and often touch it on the host between kernels (the reference relies on page
+    migration): the TMA-staged kernels (large reductions, field-major cell sums) must fault host-resident pages in like
+    ordinary loads do.  No prefetch here on purpose."""
+    import subprocess
+    code = r'''
+import ctypes as C, numpy as np, sys
+sys.path.insert(0, %r)
+import onika_b200 as ob
+from onika_b200 import _capi
+from tests._inputs import lcg_uniform, poisson_counts
+import oracle
+L = _capi.lib()
+ob.init(0)
+n = 4_000_003                                       # > 2 TMA tiles per SM: reduce_f64_tma_kernel
+p = C.c_void_p(); _capi.check(L.onk_alloc(n * 8, 256, _capi.MEM_MANAGED, C.byref(p)))
+a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n,))
+d = lcg_uniform(n, 32, -1, 1)
+a[:] = d                                            # pages now live in host memory
+out = C.c_void_p(); _capi.check(L.onk_alloc(64, 64, _capi.MEM_PINNED, C.byref(out)))
+res = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_double)), shape=(8,))
+_capi.check(L.onk_reduce_f64(_capi.OP_MIN, p, n, out, 3)); _capi.check(L.onk_lane_sync(3))
+assert res[0] == oracle.orc.reduce_min(d), "min"
+a[12345] = -7.0                                     # host write migrates that page back
+_capi.check(L.onk_reduce_f64(_capi.OP_MIN, p, n, out, 3)); _capi.check(L.onk_lane_sync(3))
+assert res[0] == -7.0, "min after host write"
+# field-major cell sums over managed columns (cell_sum_packed_tma_kernel)
+counts = poisson_counts(20000, 16.0, 42, 0, 64)
+begin = np.zeros(counts.size + 1, np.uint64); begin[1:] = np.cumsum(counts, dtype=np.uint64)
+m = int(begin[-1])
+pv = C.c_void_p(); _capi.check(L.onk_alloc(m * 8, 256, _capi.MEM_MANAGED, C.byref(pv)))
+pb = C.c_void_p(); _capi.check(L.onk_alloc(begin.size * 8, 256, _capi.MEM_MANAGED, C.byref(pb)))
+ps = C.c_void_p(); _capi.check(L.onk_alloc(counts.size * 8, 256, _capi.MEM_MANAGED, C.byref(ps)))
+v = np.ctypeslib.as_array(C.cast(pv, C.POINTER(C.c_double)), shape=(m,)); v[:] = d[:m]
+b = np.ctypeslib.as_array(C.cast(pb, C.POINTER(C.c_uint64)), shape=(begin.size,)); b[:] = begin
+_capi.check(L.onk_cell_sum_packed_f64(pv, m, pb, counts.size, ps, None, 3)); _capi.check(L.onk_lane_sync(3))
+sums = np.ctypeslib.as_array(C.cast(ps, C.POINTER(C.c_double)), shape=(counts.size,))
+want, _ = oracle.orc.cell_sum_packed(d[:m], begin)
+assert np.array_equal(sums, want), "cell sums"
+print("managed ok")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "managed ok" in r.stdout, (r.returncode, r.stdout[-800:], r.stderr[-1500:])
+
+
 def test_finalize_and_reinitialise(orc):
     """onk_finalize tears lanes/scratch down; the next call re-creates them (runs in a subprocess: the other tests share one runtime)."""
     import subprocess
