@@ -763,6 +763,11 @@ _capi.check(L.onk_cell_sum_packed_f64(pv, m, pb, counts.size, ps, None, 3)); _ca
 sums = np.ctypeslib.as_array(C.cast(ps, C.POINTER(C.c_double)), shape=(counts.size,))
 want, _ = oracle.orc.cell_sum_packed(d[:m], begin)
 assert np.array_equal(sums, want), "cell sums"
+# pinned (mapped) host memory read in place by the kernel, over PCIe
+ph = C.c_void_p(); _capi.check(L.onk_alloc(n * 8, 256, _capi.MEM_PINNED, C.byref(ph)))
+h = np.ctypeslib.as_array(C.cast(ph, C.POINTER(C.c_double)), shape=(n,)); h[:] = d; h[777] = -9.0
+_capi.check(L.onk_reduce_f64(_capi.OP_MIN, ph, n, out, 3)); _capi.check(L.onk_lane_sync(3))
+assert res[0] == -9.0, "min over pinned host memory"
 print("managed ok")
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
