@@ -469,6 +469,76 @@ static int scenario_graph(Out& out, size_t rows, size_t cols, int replays, int n
   return pq.empty() ? 0 : 3;
 }
 
+// config C4 through the GENERIC functor path, the way an application writes it: one block per cell, ONIKA_CU_BLOCK_SIMD_FOR over
+// the cell's particles, block reduction, thread 0 stores.  Times block sizes 128 (reference default: 12.5 % of the lanes busy
+// with 16 particles per cell) and 32 (opts.max_block_size) on a field-major column; prints microseconds per sweep.
+template<int BS>
+struct GenericCellSumFunctor
+{
+  const double * __restrict__ values; const uint64_t * __restrict__ cell_begin; double * __restrict__ cell_sum;
+  ONIKA_HOST_DEVICE_FUNC inline void operator () ( size_t c ) const
+  {
+    const uint64_t b = cell_begin[c], e = cell_begin[c+1];
+    double s = 0.0;
+    ONIKA_CU_BLOCK_SIMD_FOR(uint64_t, p, b, e) { s += values[p]; }
+    s = onika::cuda::block_reduce_add( s , onika::IntConst<BS>{} );
+    if( ONIKA_CU_THREAD_IDX == 0 ) cell_sum[c] = s;
+  }
+};
+namespace onika { namespace parallel { template<int BS> struct BlockParallelForFunctorTraits< GenericCellSumFunctor<BS> > { static inline constexpr bool CudaCompatible = true; }; } }
+
+static int scenario_cells_generic_perf(Out& out, size_t ncells)
+{
+  std::vector<uint64_t> begin(ncells+1,0);
+  for(size_t c=0;c<ncells;c++) begin[c+1] = begin[c] + uint64_t( lcg(c,42,8.0,25.0) );     // ~16 particles per cell
+  const size_t np = begin[ncells];
+  void *pv=nullptr, *pb=nullptr, *ps=nullptr;
+  ONIKA_B200_CHECK( onk_alloc( np*8 , 256 , ONK_MEM_DEVICE , &pv ) ); ONIKA_B200_CHECK( onk_alloc( (ncells+1)*8 , 256 , ONK_MEM_DEVICE , &pb ) );
+  ONIKA_B200_CHECK( onk_alloc( ncells*8 , 256 , ONK_MEM_DEVICE , &ps ) );
+  { std::vector<double> v(np); for(size_t i=0;i<np;i++) v[i] = lcg(i,40,-1.0,1.0);
+    ONIKA_B200_CHECK( onk_memcpy( pv , v.data() , np*8 , 0 ) ); ONIKA_B200_CHECK( onk_memcpy( pb , begin.data() , (ncells+1)*8 , 0 ) ); ONIKA_B200_CHECK( onk_lane_sync(0) ); }
+  auto & pq = ParallelExecutionQueue::default_queue();
+  void* stream = nullptr; ONIKA_B200_CHECK( onk_lane_stream( 0 , &stream ) );
+  cudaEvent_t e0, e1; ONIKA_CU_CHECK_ERRORS( cudaEventCreate(&e0) ); ONIKA_CU_CHECK_ERRORS( cudaEventCreate(&e1) );
+  double us[3] = {0,0,0};
+  auto timeit = [&](int slot, auto make_op)
+  {
+    for(int i=0;i<2;i++) pq << set_lane(0) << make_op();
+    pq << flush << synchronize;
+    ONIKA_CU_CHECK_ERRORS( cudaEventRecord( e0 , (cudaStream_t) stream ) );
+    for(int i=0;i<5;i++) pq << set_lane(0) << make_op();
+    pq << flush;
+    ONIKA_CU_CHECK_ERRORS( cudaEventRecord( e1 , (cudaStream_t) stream ) );
+    pq << synchronize;
+    float ms = 0; ONIKA_CU_CHECK_ERRORS( cudaEventElapsedTime( &ms , e0 , e1 ) );
+    us[slot] = ms * 1e3 / 5;
+  };
+  ParallelExecutionContext::s_gpu_timing = false;
+  GenericCellSumFunctor<128> f128 = { (const double*)pv , (const uint64_t*)pb , (double*)ps };
+  GenericCellSumFunctor<32>  f32  = { (const double*)pv , (const uint64_t*)pb , (double*)ps };
+  BlockParallelForOptions o32; o32.max_block_size = 32;
+  timeit( 0 , [&]{ return block_parallel_for( ncells , f128 , parallel_execution_context("cells","bs128") ); } );
+  std::vector<double> r128(ncells); ONIKA_B200_CHECK( onk_memcpy( r128.data() , ps , ncells*8 , 0 ) ); ONIKA_B200_CHECK( onk_lane_sync(0) );
+  timeit( 1 , [&]{ return block_parallel_for( ncells , f32 , parallel_execution_context("cells","bs32") , o32 ); } );
+  std::vector<double> r32(ncells); ONIKA_B200_CHECK( onk_memcpy( r32.data() , ps , ncells*8 , 0 ) ); ONIKA_B200_CHECK( onk_lane_sync(0) );
+  { // typed field-major kernel on the same data
+    for(int i=0;i<2;i++) ONIKA_B200_CHECK( onk_cell_sum_packed_f64( (const double*)pv , np , (const uint64_t*)pb , ncells , (double*)ps , nullptr , 0 ) );
+    ONIKA_CU_CHECK_ERRORS( cudaEventRecord( e0 , (cudaStream_t) stream ) );
+    for(int i=0;i<5;i++) ONIKA_B200_CHECK( onk_cell_sum_packed_f64( (const double*)pv , np , (const uint64_t*)pb , ncells , (double*)ps , nullptr , 0 ) );
+    ONIKA_CU_CHECK_ERRORS( cudaEventRecord( e1 , (cudaStream_t) stream ) );
+    ONIKA_B200_CHECK( onk_lane_sync(0) );
+    float ms = 0; ONIKA_CU_CHECK_ERRORS( cudaEventElapsedTime( &ms , e0 , e1 ) ); us[2] = ms * 1e3 / 5;
+  }
+  ParallelExecutionContext::s_gpu_timing = true;
+  std::vector<double> rt(ncells); ONIKA_B200_CHECK( onk_memcpy( rt.data() , ps , ncells*8 , 0 ) ); ONIKA_B200_CHECK( onk_lane_sync(0) );
+  std::printf("cells_generic_perf ncells=%zu particles=%zu : generic block 128 %.1f us , generic block 32 %.1f us , typed field-major %.1f us\n", ncells, np, us[0], us[1], us[2]);
+  out.doubles( us , 3 );
+  out.doubles( rt.data() , ncells );            // in-order sums (typed kernel): the reference result
+  out.doubles( r128.data() , ncells ); out.doubles( r32.data() , ncells );   // tree sums of the generic functor: equal within rounding
+  onk_free( pv , np*8 ); onk_free( pb , (ncells+1)*8 ); onk_free( ps , ncells*8 );
+  return pq.empty() ? 0 : 3;
+}
+
 static int scenario_grid3d(Out& out)
 {
   { // which cells of a second 2D sweep must wait for a first one, given a cross-shaped conflict stencil (host logic)
@@ -736,6 +806,7 @@ int main(int argc, char* argv[])
   else if( sc == "autolanes" ) rc = scenario_autolanes( out , arg(3,64) , arg(4,4096) , int(arg(5,2000)) );
   else if( sc == "autolanes_perf" ) rc = scenario_autolanes_perf( out , arg(3,4) , arg(4,8192) , int(arg(5,20000)) );
   else if( sc == "graph" ) rc = scenario_graph( out , arg(3,128) , arg(4,512) , int(arg(5,3)) , int(arg(6,200)) );
+  else if( sc == "cells_generic_perf" ) rc = scenario_cells_generic_perf( out , arg(3,1<<18) );
   else if( sc == "grid3d" ) rc = scenario_grid3d( out );
   else if( sc == "reduce" ) rc = scenario_reduce( out , arg(3,777) , arg(4,1001) );
   else if( sc == "cells" ) rc = scenario_cells( out , arg(3,4096) );
