@@ -68,7 +68,17 @@ def test_cxx_front_end_compiles_in_a_host_only_translation_unit(tmp_path):
 #include <onika/cuda/memcpy.h>
 #include <onika/soatl/field_arrays.h>
 #include <onika/soatl/compute.h>
+#include <onika/soatl/copy.h>
+#include <onika/soatl/field_tuple.h>
+#include <onika/soatl/field_pointer_tuple.h>
+#include <onika/soatl/field_combiner.h>
+#include <onika/soatl/pretty_print.h>
+#include <onika/soatl/field_id_tuple_utils.h>
+#include <onika/parallel/parallel_execution_graph.h>
+#include <onika/parallel/reduction.h>
+#include <onika/cuda/stl_adaptors.h>
 #include <onika/scg/operator.h>
+#include <onika/app/api.h>
 struct tag_x {}; struct tag_i {};
 namespace onika { namespace soatl {
   template<> struct FieldId<tag_x> { using value_type = double; using Id = tag_x; static const char* name() { return "x"; } };
@@ -79,6 +89,17 @@ static_assert( sizeof(parallel::ParallelDataAccess) == 64 );
 static_assert( sizeof(parallel::HostKernelExecutionScratch) == 1024 && sizeof(parallel::GPUKernelExecutionScratch) == 1024 );
 static_assert( ! parallel::functor_gpu_support_v< extras::BlockParallelValueAddFunctor<true> > , "host-only TU: no device target" );
 static_assert( soatl::find_index_of_id_v<tag_i,tag_x,tag_i> == 1 );
+// value tuples are plain host objects: zero by default, field-wise conversion, equality
+int tuple_probe()
+{
+  soatl::FieldTuple<tag_x,tag_i> t;                       // zeroed
+  soatl::FieldTuple<tag_i> only_i( 7 );
+  t.copy_existing_fields( only_i );
+  soatl::FieldTuple<tag_i,tag_x> swapped( t );             // conversion by field, not by position
+  const double sorted[4] = { 1.0 , 2.0 , 4.0 , 8.0 };
+  return ( t[soatl::FieldId<tag_x>{}] == 0.0 && swapped[soatl::FieldId<tag_i>{}] == 7 && swapped == swapped
+           && onika::cuda::lower_bound( sorted , sorted+4 , 3.0 ) == sorted+2 ) ? 0 : 1;
+}
 int layout_probe()
 {
   // pure layout arithmetic of FieldArrays<64,16,x,i>: column offsets for a capacity (host only, no allocation)
