@@ -202,7 +202,10 @@ namespace onika { namespace parallel {
     static inline onikaDim3_t s_gpu_block_dims = { 8 , 8 , 4 };
     static inline int parallel_task_core_mult() { return s_parallel_task_core_mult; }
     static inline int parallel_task_core_add() { return s_parallel_task_core_add; }
-    static inline int gpu_sm_mult() { return ( s_gpu_sm_mult >= 0 ) ? s_gpu_sm_mult : parallel_task_core_mult(); }
+    // fixed grids (work stealing) have gpu_sm_mult x SMs + gpu_sm_add blocks.  Unset, the reference falls back to the CPU task
+    // multiplier (4): 4 x 128 threads per SM leave a B200 three quarters empty (value-add rows through the generic work-stealing
+    // kernel: 2250 GB/s at 4, 3858 at 8, 5086 at 16 and 32), so the default here fills the SM: 2048 / 128 = 16
+    static inline int gpu_sm_mult() { return ( s_gpu_sm_mult >= 0 ) ? s_gpu_sm_mult : int( 2048 / ONIKA_CU_MAX_THREADS_PER_BLOCK ); }
     static inline int gpu_sm_add() { return ( s_gpu_sm_add >= 0 ) ? s_gpu_sm_add : parallel_task_core_add(); }
     static inline int gpu_block_size() { return s_gpu_block_size; }
     static inline onikaDim3_t gpu_block_dims() { return s_gpu_block_dims; }

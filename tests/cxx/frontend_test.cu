@@ -788,6 +788,13 @@ static int scenario_perf(Out&, size_t n)
     bench( "block_parallel_for value-add rows" , 16.0*rows*cols , [&]{ return block_parallel_for( rows , f , parallel_execution_context("vadd") ); } );
     BlockParallelForOptions ws; ws.fixed_gpu_grid_size = true;
     bench( "block_parallel_for value-add rows, work-stealing (generic)" , 16.0*rows*cols , [&]{ return block_parallel_for( rows , f , parallel_execution_context("vadd") , ws ); } );
+    for(int mult : { 8 , 16 , 32 })
+    {
+      ParallelExecutionContext::s_gpu_sm_mult = mult;
+      char name[96]; std::snprintf( name , sizeof(name) , "  same, gpu_sm_mult = %d (grid = %d CTAs)" , mult , 148*mult );
+      bench( name , 16.0*rows*cols , [&]{ return block_parallel_for( rows , f , parallel_execution_context("vadd") , ws ); } );
+    }
+    ParallelExecutionContext::s_gpu_sm_mult = -1;
   }
   return 0;
 }
