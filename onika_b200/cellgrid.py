@@ -3,7 +3,7 @@ packed back to back in one HBM arena with offset/size/capacity tables."""
 from __future__ import annotations
 
 import ctypes as C
-from typing import Sequence, Tuple
+from typing import Sequence
 
 import numpy as np
 

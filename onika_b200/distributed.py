@@ -9,7 +9,7 @@ counterpart of the reference's mpi::all_reduce_multi (include/onika/mpi/all_redu
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import Sequence, Tuple
 
 from ._capi import OP_MIN, OP_MAX, OP_SUM
 

@@ -11,7 +11,7 @@ reference: an operation that is not pushed onto a queue executes synchronously w
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Any, Callable, List, Optional
 
 from . import _capi

@@ -9,7 +9,7 @@ on it runs in libonika_b200.so.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import numpy as np
 

@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from tests._inputs import lcg_uniform, unhx
+from tests._inputs import lcg_uniform
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")

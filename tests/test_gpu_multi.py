@@ -150,7 +150,6 @@ def test_config_c5_lane_sequence_sharded_over_two_gpus(orc):
 
 # ---------------------------------------------------------------- id-based redistribution over peer memory
 def _worker_xs(rank, world, port, cases, q):
-    import time
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"

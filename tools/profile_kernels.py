@@ -17,7 +17,6 @@ def main():
     ap.add_argument("--only", default="")
     args = ap.parse_args()
     only = set(filter(None, args.only.split(",")))
-    import numpy as np
     import torch
     import onika_b200 as ob
     from onika_b200 import parallel as P, soatl, cellgrid
