@@ -309,6 +309,53 @@ __global__ void __launch_bounds__(T, C) k_reduce_tma(const double* __restrict__ 
   if ((tid & 31) == 0 && m < 0.0) out[blockIdx.x] = m;
 }
 
+// read side through TMA (bulk tiles into a 2-stage ring), update in registers, 256-bit stores straight from registers
+template<int T, int ST, int TB, int C>
+__global__ void __launch_bounds__(T, C) k_rmw_tmaload(double* __restrict__ a, uint64_t ntiles, double s, double c)
+{
+  extern __shared__ __align__(128) unsigned char rsm[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rsm + (size_t)ST * TB);
+  const unsigned tid = threadIdx.x;
+  if (tid == 0)
+  {
+    for (int k = 0; k < ST; k++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(bars + k)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint64_t mine = (blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto issue = [&](uint64_t k)
+  {
+    const int st_ = (int)(k % ST);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + st_);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(rsm + (size_t)st_ * TB);
+    const uint64_t tile = blockIdx.x + k * gridDim.x;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((unsigned)TB) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(a + tile * (TB / 8)), "r"((unsigned)TB), "r"(bar) : "memory");
+  };
+  if (tid == 0) for (uint64_t k = 0; k < (uint64_t)ST && k < mine; k++) issue(k);
+  for (uint64_t k = 0; k < mine; k++)
+  {
+    const int st_ = (int)(k % ST);
+    const unsigned phase = (unsigned)((k / ST) & 1);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + st_);
+    unsigned done = 0;
+    while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+    const unsigned base = (unsigned)__cvta_generic_to_shared(rsm + (size_t)st_ * TB) + tid * 32u;
+    double* out = a + (blockIdx.x + k * gridDim.x) * (TB / 8) + tid * 4;
+#pragma unroll
+    for (int i = 0; i < TB / (T * 32); i++)
+    {
+      d4 v;
+      asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.a), "=d"(v.b) : "r"(base + i * (T * 32u)) : "memory");
+      asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.c), "=d"(v.d) : "r"(base + i * (T * 32u) + 16u) : "memory");
+      v.a = v.a * s + c; v.b = v.b * s + c; v.c = v.c * s + c; v.d = v.d * s + c;
+      st<0>(out + i * (T * 4), v);
+    }
+    __syncthreads();
+    if (tid == 0 && k + ST < mine) issue(k + ST);
+  }
+}
+
 int main(int argc, char** argv)
 {
   const uint64_t n = 1ull<<28;
@@ -320,6 +367,16 @@ int main(int argc, char** argv)
   int sms; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   printf("SMs %d\n", sms);
 #define RTMA(T,ST,TB,C) { const uint64_t nt = (n*8)/TB; size_t sm = (size_t)ST*TB + 128; CK(cudaFuncSetAttribute(k_reduce_tma<T,ST,TB,C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); double t = timeit([&]{ k_reduce_tma<T,ST,TB,C><<<sms*C,T,sm>>>(a,nt,out); }); printf("reduce_tma T=%d stages=%d tile=%d C=%d : %8.1f GB/s\n",T,ST,TB,C, n*8/t/1e9); }
+#define RTL(T,ST,TB,C) { const uint64_t nt = (n*8)/TB; size_t sm = (size_t)ST*TB + 128; CK(cudaFuncSetAttribute(k_rmw_tmaload<T,ST,TB,C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); double t = timeit([&]{ k_rmw_tmaload<T,ST,TB,C><<<sms*C,T,sm>>>(a,nt,1.0,0.0); }, 10); printf("rmw_tmaload T=%d stages=%d tile=%d C=%d : %8.1f GB/s\n",T,ST,TB,C, 2*n*8/t/1e9); }
+  if (argc > 1 && argv[1][0] == 'w')
+  {
+    for (int rep = 0; rep < 2; rep++)
+    {
+      { const uint64_t nt = n/(256*1*4); double t = timeit([&]{ k_rmw<256,1,8,9,0><<<sms*8,256>>>(a,nt,1.0,0.0); }, 10); printf("rmw T=256 U=1 C=8 (product shape) : %8.1f GB/s\n", 2*n*8/t/1e9); }
+      RTL(256,2,65536,1) RTL(512,2,65536,1) RTL(256,2,32768,2) RTL(256,4,32768,1) RTL(512,4,32768,1) RTL(256,2,32768,3) RTL(256,3,32768,2) RTL(128,2,16384,4) RTL(256,2,16384,4)
+    }
+    return 0;
+  }
   if (argc > 1 && argv[1][0] == 'r')
   {
     for (int rep = 0; rep < 2; rep++)
