@@ -133,6 +133,23 @@ def test_queue_capture_and_replay(prog, tmp_path):
     assert graph_ms < direct_ms, (direct_ms, graph_ms)
 
 
+def test_cell_sums_through_the_generic_functor_path(prog, tmp_path, orc):
+    """config C4 written the application way (one block per cell, ONIKA_CU_BLOCK_SIMD_FOR + block_reduce_add) with 128- and
+    32-thread blocks, next to the typed field-major kernel on the same column: typed sums are the in-order sums bit for
+    bit, the functor's tree sums agree within rounding"""
+    ncells = 20000
+    d = run(prog, tmp_path, "cells_generic_perf", ncells).view(np.float64)
+    sizes = np.floor(lcg_uniform(ncells, 42, 8.0, 25.0)).astype(np.uint64)
+    begin = np.zeros(ncells + 1, np.uint64)
+    begin[1:] = np.cumsum(sizes, dtype=np.uint64)
+    values = lcg_uniform(int(begin[-1]), 40, -1.0, 1.0)
+    want, _ = orc.cell_sum_packed(values, begin)
+    typed, g128, g32 = d[3:3 + ncells], d[3 + ncells:3 + 2 * ncells], d[3 + 2 * ncells:]
+    assert np.array_equal(typed, want)
+    mag = np.add.reduceat(np.abs(values), begin[:-1].astype(np.int64))
+    assert np.all(np.abs(g128 - want) <= SUM_RTOL * mag) and np.all(np.abs(g32 - want) <= SUM_RTOL * mag)
+
+
 def test_3d_spaces(prog, tmp_path, orc, gold):
     d = run(prog, tmp_path, "grid3d").view(np.float64)
     assert np.array_equal(d[:64], np.ones(64))          # block_parallel_for over {0..4}^3: every cell once
