@@ -392,14 +392,19 @@ def run_ours(args) -> int:
     value = world * n * 8 / (ms_per_step * 1e-3) / 1e9
 
     # ---- roofline of the dominant kernel (reduce_f64_kernel): device time of the kernel alone, measured live ----
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    k0.record()
-    for k in range(K):
-        functor.launch(n, 0)
-    k1.record()
-    torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / K
+    if world == 1:
+        # the timed region above IS K launches of this kernel and nothing else: same events, same number
+        kernel_ms = ms_per_step
+    else:
+        # N > 1: a step is the kernel plus the cross-GPU combine; time the local kernel alone the same way
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        k0.record()
+        for k in range(K):
+            functor.launch(n, 0)
+        k1.record()
+        torch.cuda.synchronize()
+        kernel_ms = k0.elapsed_time(k1) / K
     # per-launch spread, from a separate short pass with an event between launches (the events cost ~1 % themselves)
     Ks = min(K, 50)
     kev = [torch.cuda.Event(enable_timing=True) for _ in range(Ks + 1)]
