@@ -50,7 +50,44 @@ class ClockSampler:
     def __init__(self, device: int):
         self.device, self.proc, self.lines = device, None, []
 
+    def _start_nvml(self) -> bool:
+        """same counters straight from NVML (what nvidia-smi reads), polled every 2 ms: a 60 ms timed region gets ~30 samples
+        instead of the 1-4 a 50 ms nvidia-smi loop delivers"""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indexes physical devices: honour CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.device
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.device])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = (("hw_slowdown", pynvml.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", pynvml.nvmlClocksEventReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", pynvml.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", pynvml.nvmlClocksEventReasonSwPowerCap))
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)          # probe once: any failure falls back to nvidia-smi
+        except Exception:
+            return False
+        self.nvml_rows, self.nvml_stop, self.nvml_max = [], threading.Event(), mx
+
+        def poll():
+            while not self.nvml_stop.is_set():
+                try:
+                    sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    self.nvml_rows.append((time.time(), sm, pw, [n for n, b in bits if mask & b]))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+        self.t = threading.Thread(target=poll, daemon=True)
+        self.t.start()
+        return True
+
     def start(self):
+        self.nvml = self._start_nvml()
+        if self.nvml:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -64,6 +101,16 @@ class ClockSampler:
             self.lines.append((time.time(), line.strip()))
 
     def stop(self, t0: float, t1: float) -> dict:
+        if getattr(self, "nvml", False):
+            time.sleep(0.01)
+            self.nvml_stop.set()
+            self.t.join(timeout=1.0)
+            sel = [r for r in self.nvml_rows if t0 <= r[0] <= t1] or self.nvml_rows
+            if sel:
+                sm = sorted(r[1] for r in sel)
+                return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.nvml_max, "power_w_max": round(max(r[2] for r in sel), 2),
+                        "samples": len(sel), "reasons": sorted({n for r in sel for n in r[3]}), "source": "NVML, 2 ms period"}
+            return {"sm_mhz": None, "sm_max_mhz": self.nvml_max, "reasons": ["no samples"]}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
