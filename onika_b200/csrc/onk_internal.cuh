@@ -43,6 +43,7 @@ namespace onk
     cudaStream_t  stream = nullptr;
     bool          created = false;   // stream exists
     bool          owned = false;     // we created it (destroy at finalize)
+    cudaEvent_t   edge = nullptr;    // re-used by onk_lane_wait_lane: 'what this lane holds now' for another lane to wait on
     LaneWorkspace ws;
   };
 

@@ -115,6 +115,7 @@ int onk_finalize(void)
     if (L.ws.partials) cudaFree(L.ws.partials);
     if (L.ws.ticket) cudaFree(L.ws.ticket);
     if (L.ws.result) cudaFree(L.ws.result);
+    if (L.edge) cudaEventDestroy(L.edge);
     if (L.created && L.owned) cudaStreamDestroy(L.stream);
     L = Lane{};
   }
@@ -210,11 +211,10 @@ int onk_lane_wait_lane(int lane, int other_lane)
   if (int rc = lane_get(lane, &A)) return rc;
   if (int rc = lane_get(other_lane, &B)) return rc;
   if (A->stream == B->stream) return ONK_OK;
-  cudaEvent_t e;
-  ONK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  ONK_CUDA(cudaEventRecord(e, B->stream));
-  ONK_CUDA(cudaStreamWaitEvent(A->stream, e, 0));
-  ONK_CUDA(cudaEventDestroy(e));   // destruction is deferred until the event completes
+  // one event per source lane, re-recorded at every edge: a wait already queued keeps referring to the record it saw
+  if (B->edge == nullptr) ONK_CUDA(cudaEventCreateWithFlags(&B->edge, cudaEventDisableTiming));
+  ONK_CUDA(cudaEventRecord(B->edge, B->stream));
+  ONK_CUDA(cudaStreamWaitEvent(A->stream, B->edge, 0));
   return ONK_OK;
 }
 
