@@ -107,3 +107,52 @@ int layout_probe()
 }
 ''')
     subprocess.check_call(["g++", "-std=c++20", "-fopenmp", "-Wall", "-c", f"-I{INC}", str(src), "-o", str(tmp_path / "host_tu.o")], env=_env())
+
+
+def test_host_side_logic_of_the_front_end_runs_without_a_gpu(tmp_path):
+    """pure host logic of the C++ front end, executed here: data-access conflict tests and conflict maps, the split of an
+    execution space into dependent / independent elements, coordinate-range helpers, value tuples"""
+    from onika_b200 import _build
+    lib = _build.build()
+    src = tmp_path / "host_logic.cpp"
+    src.write_text(r'''
+#include <onika/parallel/parallel_data_access.h>
+#include <onika/parallel/parallel_execution_space.h>
+#include <onika/soatl/field_tuple.h>
+#include <cstdio>
+#include <vector>
+using namespace onika; using namespace onika::parallel;
+struct tag_a {}; struct tag_b {};
+namespace onika { namespace soatl {
+  template<> struct FieldId<tag_a> { using value_type = double; using Id = tag_a; static const char* name() { return "a"; } };
+  template<> struct FieldId<tag_b> { using value_type = int; using Id = tag_b; static const char* name() { return "b"; } };
+} }
+int main()
+{
+  double x[4], y[4];
+  ParallelDataAccessVector rw_x, ro_x, rw_y, cross_x;
+  rw_x.push_back( local_access( x , 2 , AccessStencilElement::RW , "x" ) );
+  ro_x.push_back( local_access( x , 2 , AccessStencilElement::RO , "x" ) );
+  rw_y.push_back( local_access( y , 2 , AccessStencilElement::RW , "y" ) );
+  cross_x.push_back( access_cross_2d( x , AccessStencilElement::RW , AccessStencilElement::RO , "xc" ) );
+  AccessConflictMap cm;
+  concurrent_data_access_conflict_map( rw_x , cross_x , cm );
+  std::printf("%d %d %d %d\n", int(concurrent_data_access(rw_x,ro_x)), int(concurrent_data_access(rw_x,rw_y)), int(concurrent_data_access(cross_x,rw_x)), int(cm.size()));
+  using C2 = oarray_t<ssize_t,2>;
+  const ParallelExecutionSpace<2> first = { {0,0} , {4,4} } , second = { {3,0} , {7,2} };
+  std::vector<C2> stencil = { C2{0,0} , C2{-1,0} , C2{1,0} , C2{0,-1} , C2{0,1} } , dep , rem;
+  concurrent_execution_space_elements( first , second , std::span<C2>( stencil ) , dep , rem );
+  std::printf("%zu %zu %zu %zu\n", dep.size(), rem.size(), coord_range_size( C2{0,0} , C2{4,4} ), coord_range_size( ssize_t(3) , ssize_t(1) ));
+  soatl::FieldTuple<tag_a,tag_b> t;  t[soatl::FieldId<tag_b>{}] = 5;
+  soatl::FieldTuple<tag_b,tag_a> u( t );
+  std::printf("%g %d %d\n", u[soatl::FieldId<tag_a>{}], u[soatl::FieldId<tag_b>{}], int( u == u ));
+  return 0;
+}
+''')
+    exe = tmp_path / "host_logic"
+    subprocess.check_call(["g++", "-std=c++20", "-fopenmp", f"-I{INC}", str(src), "-o", str(exe), f"-L{os.path.dirname(lib)}", "-lonika_b200",
+                           f"-Wl,-rpath,{os.path.dirname(lib)}"], env=_env())
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[0].split()[:3] == ["1", "0", "1"] and int(out[0].split()[3]) == 5     # x vs x conflicts, x vs y does not; RW centre against the 5-point cross
+    assert out[1] == "4 4 16 0"
+    assert out[2] == "0 5 1"
