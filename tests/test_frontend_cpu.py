@@ -156,3 +156,66 @@ int main()
     assert out[0].split()[:3] == ["1", "0", "1"] and int(out[0].split()[3]) == 5     # x vs x conflicts, x vs y does not; RW centre against the 5-point cross
     assert out[1] == "4 4 16 0"
     assert out[2] == "0 5 1"
+
+
+def test_lane_dag_placement_is_pure_host_logic(tmp_path):
+    """pre_process_queue (any_lane + declared accesses -> lanes and cross-lane edges) needs no GPU: run it here on queued,
+    never scheduled operations and check the placement the GPU test relies on"""
+    from onika_b200 import _build
+    lib = _build.build()
+    src = tmp_path / "lane_dag.cpp"
+    src.write_text(r'''
+#include <onika/parallel/block_parallel_for.h>
+#include <onika/parallel/parallel_execution_context_allocator.h>
+#include <onika/parallel/parallel_execution_queue.h>
+#include <onika/parallel/parallel_execution_operators.h>
+#include <cstdio>
+using namespace onika; using namespace onika::parallel;
+struct HostOnly { inline void operator () ( size_t ) const {} };
+int main()
+{
+  onika::cuda::CudaContext::set_global_gpu_enable( false );          // no device in this process
+  ParallelExecutionQueue owner;                                       // default queue of the contexts; never flushed
+  ParallelExecutionContextAllocator peca;
+  auto ctx = [&](const char* tag) { return peca.create( tag , "" , &owner , nullptr ); };
+  double A[1], B[1], C[1];
+  const auto a_rw = local_access( A , 2 , AccessStencilElement::RW , "a" ), a_ro = local_access( A , 2 , AccessStencilElement::RO , "a" );
+  const auto b_rw = local_access( B , 2 , AccessStencilElement::RW , "b" ), c_rw = local_access( C , 2 , AccessStencilElement::RW , "c" );
+  ParallelExecutionContext* pec[7] = { ctx("a1") , ctx("b1") , ctx("a2") , ctx("ab") , ctx("a3") , ctx("c1") , ctx("free") };
+  ParallelExecutionQueueBase q;
+  q << any_lane(4)
+    << a_rw << block_parallel_for( 8 , HostOnly{} , pec[0] )
+    << b_rw << block_parallel_for( 8 , HostOnly{} , pec[1] )
+    << a_rw << block_parallel_for( 8 , HostOnly{} , pec[2] )
+    << a_ro << b_rw << block_parallel_for( 8 , HostOnly{} , pec[3] )
+    << a_rw << block_parallel_for( 8 , HostOnly{} , pec[4] )
+    << c_rw << block_parallel_for( 8 , HostOnly{} , pec[5] )
+    << block_parallel_for( 8 , HostOnly{} , pec[6] );                 // no declared access: round robin like the reference
+  q.pre_process_queue( q.m_queue_list );
+  for(int k=0;k<7;k++)
+  {
+    int nw = 0; for(int l=0;l<256;l++) if( pec[k]->depends_on_lane(l) ) ++nw;
+    std::printf("%d:%d ", int(pec[k]->m_lane), nw);
+  }
+  std::printf("\n");
+  // hand the never-scheduled operations back: destroy the type-erased functor, run the finalize callback (returns the context)
+  while( q.m_queue_list != nullptr )
+  {
+    auto* p = q.m_queue_list; q.m_queue_list = p->m_next; p->m_next = nullptr;
+    auto fin = p->m_finalize;
+    reinterpret_cast<BlockParallelForHostFunctor*>( p->m_host_scratch.functor_data ) -> ~BlockParallelForHostFunctor();
+    if( fin.m_func != nullptr ) ( * fin.m_func )( p , fin.m_data );
+  }
+  return 0;
+}
+''')
+    exe = tmp_path / "lane_dag"
+    subprocess.check_call(["g++", "-std=c++20", "-fopenmp", f"-I{INC}", str(src), "-o", str(exe), f"-L{os.path.dirname(lib)}", "-lonika_b200",
+                           f"-Wl,-rpath,{os.path.dirname(lib)}"], env=_env())
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    lanes = [int(x.split(":")[0]) for x in out]
+    waits = [int(x.split(":")[1]) for x in out]
+    assert lanes[6] == 0                                             # phase 1: the undeclared operation takes the first lane of the cycle
+    assert lanes[0] == lanes[2] == lanes[3] == lanes[4]              # the chain on A (reads of A included) stays on one lane
+    assert lanes[1] != lanes[0] and lanes[5] not in (lanes[0], lanes[1])
+    assert waits == [0, 0, 0, 1, 0, 0, 0]                            # only "B += A" waits for another lane
