@@ -357,7 +357,7 @@ def test_reference_plugins_from_msp_batch_connected_slots(tmp_path):
 def test_reference_plugins_from_msp_example_shape(tmp_path):
     """the layout of data/exemples/concurrent_block_parallel.msp (comments, flow maps, a second operator re-using the
     arrays of the first through the connected array1/array2 slots)"""
-    out, stdout = _run_msp(tmp_path, os.path.join(MSP_DIR, "concurrent_lanes.msp"), "run_test", "dump:array2=@OUT")
+    out, stdout = _run_msp(tmp_path, os.path.join(MSP_DIR, "concurrent_lanes.msp"), "lanes_then_auto", "dump:array2=@OUT")
     assert stdout.count("All operations have terminated") == 2
     x = _chain(np.zeros((4, 256)), 2.3, 2) + 2.3           # concurrent_block_parallel
     x = _chain(x, 0.5, 1) + 0.5                            # automatic_concurrent_parallel on the same arrays
