@@ -201,6 +201,9 @@ int onk_xs_plan_build(onk_xs_plan* plan, const uint64_t* ids_before_dev, uint64_
                       const uint64_t* ids_after_dev, uint64_t n_after, int lane, int* status);
 int onk_xs_plan_send_counts(onk_xs_plan* plan, uint64_t* send_count_host /* world entries: the reference's send_count */);
 int onk_xs_move(onk_xs_plan* plan, onk_window* out, uint64_t elem_bytes, const void* in_dev, int lane);
+/* the same for several arrays that move with the same ids (the fields of a particle): one barrier before, one after, one
+ * scatter kernel per array -- what the reference does by calling data_move once per array with the same tables */
+int onk_xs_move_fields(onk_xs_plan* plan, int nfields, onk_window* const* outs, const uint64_t* elem_bytes, const void* const* ins_dev, int lane);
 int onk_xs_plan_destroy(onk_xs_plan* plan);
 
 /* parallel_for(N, y[i] += a*x[i])   include/onika/parallel/parallel_for.h:91-112 (config C1) */

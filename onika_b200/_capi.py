@@ -76,6 +76,7 @@ PROTOTYPES = {
     "onk_xs_plan_build": (i32, [vp, vp, u64, vp, u64, i32, C.POINTER(i32)]),
     "onk_xs_plan_send_counts": (i32, [vp, C.POINTER(u64)]),
     "onk_xs_move": (i32, [vp, vp, u64, vp, i32]),
+    "onk_xs_move_fields": (i32, [vp, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), i32]),
     "onk_xs_plan_destroy": (i32, [vp]),
     "onk_axpy_f64": (i32, [vp, vp, dbl, u64, i32]),
     "onk_parallel_memset": (i32, [vp, u64, u64, i32, i32]),

@@ -355,36 +355,56 @@ int onk_xs_plan_send_counts(onk_xs_plan* plan, uint64_t* send_count_host)
   return ONK_OK;
 }
 
-int onk_xs_move(onk_xs_plan* plan, onk_window* out, uint64_t elem_bytes, const void* in_dev, int lane)
+// argument checks and the scatter launch of one array (no barriers)
+static int xs_check_one(onk_xs_plan* plan, onk_window* out, uint64_t elem_bytes, const void* in_dev)
 {
-  ONK_REQUIRE(plan != nullptr && plan->built, "onk_xs_move: plan was not built");
   ONK_REQUIRE(out != nullptr && out->connected && out->world == plan->geo.world && out->rank == plan->geo.rank, "onk_xs_move: output window is not connected to the plan's ranks");
   ONK_REQUIRE(elem_bytes > 0 && (plan->n_before == 0 || in_dev != nullptr), "onk_xs_move: bad element size or null input");
   ONK_REQUIRE(out->bytes >= plan->n_after * elem_bytes, "onk_xs_move: output window too small (%zu < %llu)", out->bytes, (unsigned long long)(plan->n_after * elem_bytes));
-  Lane* L; if (int rc = lane_get(lane, &L)) return rc;
+  return ONK_OK;
+}
+
+static int xs_scatter_one(onk_xs_plan* plan, onk_window* out, uint64_t elem_bytes, const void* in_dev, Lane* L)
+{
+  if (plan->n_before == 0) return ONK_OK;
   XsWindows w{};
   for (int r = 0; r < plan->geo.world; r++) w.out[r] = (unsigned char*)out->peer[r];
+  const uintptr_t a = (uintptr_t)in_dev;
+  const unsigned piece = (elem_bytes % 32 == 0 && a % 32 == 0) ? 32u : (elem_bytes % 16 == 0 && a % 16 == 0) ? 16u
+                       : (elem_bytes % 8 == 0 && a % 8 == 0) ? 8u : (elem_bytes % 4 == 0 && a % 4 == 0) ? 4u : 1u;
+  const unsigned ppe = (unsigned)(elem_bytes / piece);
+  const unsigned grid = grid_for(plan->n_before * ppe, 256 * XS_UNROLL, 8);
+  switch (piece)
+  {
+    case 32: xs_scatter_kernel<XsPiece32><<<grid, 256, 0, L->stream>>>((const XsPiece32*)in_dev, plan->n_before, ppe, plan->route, w); break;
+    case 16: xs_scatter_kernel<uint4><<<grid, 256, 0, L->stream>>>((const uint4*)in_dev, plan->n_before, ppe, plan->route, w); break;
+    case 8:  xs_scatter_kernel<unsigned long long><<<grid, 256, 0, L->stream>>>((const unsigned long long*)in_dev, plan->n_before, ppe, plan->route, w); break;
+    case 4:  xs_scatter_kernel<unsigned><<<grid, 256, 0, L->stream>>>((const unsigned*)in_dev, plan->n_before, ppe, plan->route, w); break;
+    default: xs_scatter_kernel<unsigned char><<<grid, 256, 0, L->stream>>>((const unsigned char*)in_dev, plan->n_before, ppe, plan->route, w); break;
+  }
+  ONK_CHECK_LAUNCH(); count_launch();
+  return ONK_OK;
+}
+
+int onk_xs_move_fields(onk_xs_plan* plan, int nfields, onk_window* const* outs, const uint64_t* elem_bytes, const void* const* ins_dev, int lane)
+{
+  ONK_REQUIRE(plan != nullptr && plan->built, "onk_xs_move: plan was not built");
+  ONK_REQUIRE(nfields >= 1 && outs != nullptr && elem_bytes != nullptr && ins_dev != nullptr, "onk_xs_move_fields: null argument");
+  // every argument is checked before the first collective step: a rank that rejects its arguments must not leave the others at a barrier
+  for (int k = 0; k < nfields; k++) if (int rc = xs_check_one(plan, outs[k], elem_bytes[k], ins_dev[k])) return rc;
+  Lane* L; if (int rc = lane_get(lane, &L)) return rc;
   // the peers' windows may still be read by what they queued before this call
   if (int rc = onk_xchg_barrier(plan->x, lane)) return rc;
-  if (plan->n_before > 0)
-  {
-    const uintptr_t a = (uintptr_t)in_dev;
-    const unsigned piece = (elem_bytes % 32 == 0 && a % 32 == 0) ? 32u : (elem_bytes % 16 == 0 && a % 16 == 0) ? 16u
-                         : (elem_bytes % 8 == 0 && a % 8 == 0) ? 8u : (elem_bytes % 4 == 0 && a % 4 == 0) ? 4u : 1u;
-    const unsigned ppe = (unsigned)(elem_bytes / piece);
-    const unsigned grid = grid_for(plan->n_before * ppe, 256 * XS_UNROLL, 8);
-    switch (piece)
-    {
-      case 32: xs_scatter_kernel<XsPiece32><<<grid, 256, 0, L->stream>>>((const XsPiece32*)in_dev, plan->n_before, ppe, plan->route, w); break;
-      case 16: xs_scatter_kernel<uint4><<<grid, 256, 0, L->stream>>>((const uint4*)in_dev, plan->n_before, ppe, plan->route, w); break;
-      case 8:  xs_scatter_kernel<unsigned long long><<<grid, 256, 0, L->stream>>>((const unsigned long long*)in_dev, plan->n_before, ppe, plan->route, w); break;
-      case 4:  xs_scatter_kernel<unsigned><<<grid, 256, 0, L->stream>>>((const unsigned*)in_dev, plan->n_before, ppe, plan->route, w); break;
-      default: xs_scatter_kernel<unsigned char><<<grid, 256, 0, L->stream>>>((const unsigned char*)in_dev, plan->n_before, ppe, plan->route, w); break;
-    }
-    ONK_CHECK_LAUNCH(); count_launch();
-  }
+  for (int k = 0; k < nfields; k++) if (int rc = xs_scatter_one(plan, outs[k], elem_bytes[k], ins_dev[k], L)) return rc;
   // everything every rank sent has landed when the lane continues
   return onk_xchg_barrier(plan->x, lane);
+}
+
+int onk_xs_move(onk_xs_plan* plan, onk_window* out, uint64_t elem_bytes, const void* in_dev, int lane)
+{
+  onk_window* outs[1] = { out };
+  const void* ins[1] = { in_dev };
+  return onk_xs_move_fields(plan, 1, outs, &elem_bytes, ins, lane);
 }
 
 int onk_xs_plan_destroy(onk_xs_plan* plan)

@@ -218,6 +218,23 @@ class IdRedistribution:
         elem = values.element_size() * (values.numel() // max(values.shape[0], 1)) if values.shape[0] else values.element_size()
         self._check(self._lib.onk_xs_move(self.handle, out.handle, elem, ptr(values), lane))
 
+    def move_fields(self, values_list, outs, lane: int = -1) -> None:
+        """several arrays that travel with the same ids (onk_xs_move_fields): one pair of barriers for all of them"""
+        from .runtime import ptr
+        C = self._C
+        k = len(values_list)
+        if k == 0 or k != len(outs):
+            raise ValueError("one output window per array")
+        elems = []
+        for v in values_list:
+            if v.shape[0] != self.n_before or not v.is_contiguous():
+                raise ValueError("values must be contiguous with one row per local element before")
+            elems.append(v.element_size() * (v.numel() // max(v.shape[0], 1)) if v.shape[0] else v.element_size())
+        c_outs = (C.c_void_p * k)(*[o.handle for o in outs])
+        c_elems = (C.c_uint64 * k)(*elems)
+        c_ins = (C.c_void_p * k)(*[ptr(v) for v in values_list])
+        self._check(self._lib.onk_xs_move_fields(self.handle, k, c_outs, c_elems, c_ins, lane))
+
     def close(self):
         if self.handle:
             self._check(self._lib.onk_xs_plan_destroy(self.handle))

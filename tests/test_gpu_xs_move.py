@@ -96,3 +96,27 @@ def test_single_rank_allreduce_and_barrier_are_identities(xch):
         assert torch.equal(w, v)
     with pytest.raises(Exception):
         xch.allreduce(_capi.OP_SUM, torch.zeros(9, dtype=torch.float64, device="cuda"), lane=0)      # more than 8 values
+
+
+def test_several_fields_move_with_one_pair_of_barriers(xch, orc):
+    """onk_xs_move_fields: the fields of a particle (positions as 24-byte records, an 8-byte id, a 1-byte type) travel with the
+    same plan in one call; each must equal the oracle's data_move of that array"""
+    import torch
+    from onika_b200.distributed import IdRedistribution, PeerWindow
+    id_min, id_max, before, after = xs_random_case(1, 9, 50000, 20000)
+    sch = orc.xs_comm_scheme(id_min, id_max, before, after)
+    n = before[0].size
+    rs = np.random.RandomState(5)
+    fields = [rs.rand(n, 3), before[0].astype(np.int64), rs.randint(0, 256, n).astype(np.uint8)]
+    mv = IdRedistribution(xch, id_min, id_max)
+    mv.plan(torch.from_numpy(before[0].astype(np.int64)).cuda(), torch.from_numpy(after[0].astype(np.int64)).cuda(), lane=0)
+    wins = [PeerWindow(after[0].size * f[0:1].nbytes, xch) for f in fields]
+    mv.move_fields([torch.from_numpy(f).cuda() for f in fields], wins, lane=0)
+    torch.cuda.synchronize()
+    for f, w in zip(fields, wins):
+        got = w.tensor(torch.uint8).cpu().numpy()[:after[0].size * f[0:1].nbytes].view(f.dtype).reshape((after[0].size,) + f.shape[1:])
+        assert np.array_equal(got, orc.xs_data_move(sch, f))
+    assert np.array_equal(wins[1].tensor(torch.int64).cpu().numpy()[:after[0].size], after[0].astype(np.int64))   # ids onto ids
+    mv.close()
+    for w in wins:
+        w.close()
