@@ -219,3 +219,47 @@ int main()
     assert lanes[0] == lanes[2] == lanes[3] == lanes[4]              # the chain on A (reads of A included) stays on one lane
     assert lanes[1] != lanes[0] and lanes[5] not in (lanes[0], lanes[1])
     assert waits == [0, 0, 0, 1, 0, 0, 0]                            # only "B += A" waits for another lane
+
+
+def test_msp_flat_batch_reader(tmp_path):
+    """the .msp subset reader of tests/cxx/run_operator.cu (comments, flow maps, bare operator names, task_group / name keys,
+    errors with file:line) on the committed batch files and on malformed input"""
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = tmp_path / "msp_probe.cpp"
+    src.write_text(r'''
+#include "msp_reader.h"
+int main(int argc, char* argv[])
+{
+  std::vector<msp::BatchSpec> b;
+  if( ! msp::parse_msp( argv[1] , b ) ) return 3;
+  for(const auto& s : b)
+  {
+    std::printf("%s|%s|%d|", s.key.c_str(), s.name.c_str(), int(s.task_group));
+    for(const auto& it : s.body) { std::printf("%s(", it.op.c_str()); for(const auto& kv : it.values) std::printf("%s=%s;", kv.first.c_str(), kv.second.c_str()); std::printf(")"); }
+    std::printf("\n");
+  }
+  return 0;
+}
+''')
+    exe = tmp_path / "msp_probe"
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", f"-I{os.path.join(here, 'cxx')}", str(src), "-o", str(exe)], env=_env())
+
+    def parse(path):
+        r = subprocess.run([str(exe), str(path)], capture_output=True, text=True)
+        return r.returncode, r.stdout.splitlines(), r.stderr
+
+    rc, out, _ = parse(os.path.join(here, "cxx", "msp", "tutorial_chain.msp"))
+    assert rc == 0 and out == ["tutorial_chain|tutorial_chain_test|1|synchronous_block_parallel(my_value=1.1;)async_block_parallel(my_value=1.2;)"
+                               "synchronous_block_parallel(my_value=1.3;)"]
+    rc, out, _ = parse(os.path.join(here, "cxx", "msp", "concurrent_lanes.msp"))
+    assert rc == 0 and out == ["lanes_then_auto|lane_operators_back_to_back|1|concurrent_block_parallel(rows=4;columns=256;value=2.3;iter_count=2;)"
+                               "automatic_concurrent_parallel(iter_count=1;value=0.5;)"]
+    ok = tmp_path / "ok.msp"
+    ok.write_text("a:\n  body:\n    - nop\n    - op2: { s: \"quoted text\" }   # trailing comment\nb:\n  task_group: false\n  body:\n    - x: { k: 1 }\n")
+    rc, out, _ = parse(ok)
+    assert rc == 0 and out == ["a|a|0|nop()op2(s=quoted text;)", "b|b|0|x(k=1;)"]
+    for bad, where in (("a:\n  body:\n    - op: { k 1 }\n", ":3:"), ("- op\n", ":1:"), ("a:\n  - op\n", ":2:"), ("a:\n  colour: red\n", ":2:")):
+        f = tmp_path / "bad.msp"
+        f.write_text(bad)
+        rc, out, err = parse(f)
+        assert rc == 3 and where in err, (bad, err)
