@@ -138,3 +138,22 @@ def test_queue_semantics_lanes_fifo_and_delay_queues(monkeypatch):
     with pytest.raises(ValueError):
         q << P.flush
     q.m_queue_list.clear()
+
+
+def test_ctypes_prototypes_have_the_arity_of_the_header_declarations():
+    """a parameter added to a C declaration (e.g. the column length of onk_cell_sum_packed_f64) must show up in the ctypes
+    table too: compare argument counts, and pointer-ness argument by argument"""
+    import ctypes as C
+    import re
+    with open(_capi.HEADER) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    decls = dict(re.findall(r"\b(onk_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text))
+    assert set(decls) == set(_capi.PROTOTYPES)
+    for name, params in decls.items():
+        plist = [] if params.strip() in ("", "void") else [p.strip() for p in params.split(",")]
+        res, args = _capi.PROTOTYPES[name]
+        assert len(plist) == len(args), (name, plist, args)
+        for p, a in zip(plist, args):
+            is_ptr_c = ("*" in p) or ("[" in p)
+            is_ptr_py = a in (C.c_void_p, C.c_char_p) or hasattr(a, "contents") or (isinstance(a, type) and issubclass(a, C._Pointer))
+            assert is_ptr_c == is_ptr_py, (name, p, a)
