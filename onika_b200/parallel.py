@@ -178,7 +178,7 @@ class ParallelExecutionQueueBase:
         elif isinstance(item, set_lane):
             self.set_lane(item.lane, item.cycle)
         elif isinstance(item, ParallelExecutionQueueBase):
-            while item.m_queue_list:              # splice, keeping each operation's lane (operators.h:78-89)
+            while item.m_queue_list:              # splice, keeping each operation's lane (parallel_execution_operators.h:78-89)
                 self.enqueue(item.m_queue_list.pop(0), from_other_queue=True)
         else:
             raise TypeError(f"cannot push {type(item)} onto a parallel execution queue")
@@ -255,7 +255,7 @@ class ParallelExecutionQueue(ParallelExecutionQueueBase):
     def __lshift__(self, item):
         if item is flush:
             self.schedule_all()
-            self.set_lane(DEFAULT_EXECUTION_LANE)   # operators.h:107-112
+            self.set_lane(DEFAULT_EXECUTION_LANE)   # parallel_execution_operators.h:107-112
             return self
         if item is synchronize:
             self.wait()

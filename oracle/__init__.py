@@ -428,7 +428,7 @@ _Reference.xs_data_move = _ref_xs_data_move
 
 
 def _ref_run_unit_tests(self):
-    """runs the reference's own ONIKA_UNIT_TESTs compiled into oracle/_ref (xs_data_move_range_utils.h:103-150); (run, failed)"""
+    """runs the reference's own ONIKA_UNIT_TESTs compiled into oracle/_ref (xs_data_move_range_utils.h:96-129); (run, failed)"""
     n = C.c_int(0)
     failed = self.lib.ref_run_unit_tests(C.byref(n))
     return n.value, failed

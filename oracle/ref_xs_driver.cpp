@@ -49,7 +49,7 @@ extern "C" void ref_xs_data_move(int world, uint64_t id_min, uint64_t id_max,
   ref_mpi_run( world, rank_main, &j );
 }
 
-// The range utilities register the reference's own unit tests (xs_data_move_range_utils.h:103-150) at load time through
+// The range utilities register the reference's own unit tests (xs_data_move_range_utils.h:96-129) at load time through
 // onika::UnitTest / plugin_db_register, whose definitions live in src/core/unit_test.cpp + src/core/plugin.cpp (dlopen,
 // plugin database: not needed here).  These minimal definitions keep the registered tests so they can be run below.
 namespace onika

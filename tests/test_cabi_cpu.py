@@ -95,7 +95,7 @@ class _Rec:
 
 
 def test_queue_semantics_lanes_fifo_and_delay_queues(monkeypatch):
-    """ordering rules of the reference queue (parallel_execution_queue.cpp:94-111,242-271; operators.h:62-112),
+    """ordering rules of the reference queue (parallel_execution_queue.cpp:94-111,242-271; parallel_execution_operators.h:62-112),
     checked on the host logic alone (launches are recorded instead of executed)."""
     monkeypatch.setattr(parallel.ParallelExecutionQueue, "wait", lambda self, lane=-2: self.m_exec_list.clear())
     P = parallel

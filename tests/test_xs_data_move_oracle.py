@@ -50,7 +50,7 @@ def test_random_grid_moves_before_ids_onto_after_ids(orc, world, seed, count, pe
 
 
 def test_range_utils(orc):
-    """include/onika/mpi/xs_data_move_range_utils.h:109-121 (the reference's unit test of the id -> rendezvous rank map)"""
+    """include/onika/mpi/xs_data_move_range_utils.h:96-108 (the reference's unit test of the id -> rendezvous rank map)"""
     lo, hi = 5, 1000
     for nprocs in range(1, 16):
         starts = [orc.xs_range_start(r, nprocs, lo, hi) for r in range(nprocs)] + [hi]
