@@ -517,6 +517,15 @@ def test_field_major_cell_sum_config_c4_full_size(ob):
     s0, t0 = empty.cell_sum(0)
     ob.lane_sync()
     assert s0.numel() == 0 and host(t0)[0] == 0.0
+    hollow = cellgrid.FieldMajorCellGrid(np.zeros(1000, np.uint32), nfields=1)          # cells without a single particle
+    s1, t1 = hollow.cell_sum(0)
+    ob.lane_sync()
+    assert np.array_equal(host(s1), np.zeros(1000)) and host(t1)[0] == 0.0
+    tiny = cellgrid.FieldMajorCellGrid(np.array([3, 0, 5], np.uint32), nfields=1)          # fewer values than one 16-value row
+    tiny.set_field(0, np.arange(8, dtype=np.float64))
+    s2, t2 = tiny.cell_sum(0)
+    ob.lane_sync()
+    assert host(s2).tolist() == [3.0, 0.0, 25.0] and host(t2)[0] == 28.0
 
 
 # ---------------------------------------------------------------- op bracket, host-buffer paths, errors
