@@ -96,6 +96,15 @@ def test_single_rank_allreduce_and_barrier_are_identities(xch):
         assert torch.equal(w, v)
     with pytest.raises(Exception):
         xch.allreduce(_capi.OP_SUM, torch.zeros(9, dtype=torch.float64, device="cuda"), lane=0)      # more than 8 values
+    import ctypes as C
+    L = _capi.lib()
+    rank, world = C.c_int(-1), C.c_int(-1)
+    _capi.check(L.onk_xchg_info(xch.handle, C.byref(rank), C.byref(world)))
+    assert (rank.value, world.value) == (0, 1)
+    _capi.check(L.onk_device_sync())                      # everything queued on every lane has completed
+    idle = C.c_int(0)
+    _capi.check(L.onk_lane_query(_capi.LANE_ALL, C.byref(idle)))
+    assert idle.value == 1
 
 
 def test_several_fields_move_with_one_pair_of_barriers(xch, orc):
