@@ -15,6 +15,11 @@
 
 namespace onika { namespace soatl {
 
+  // A functor CLASS whose call operator is ONIKA_HOST_DEVICE_FUNC can declare itself runnable on the device (extended lambdas
+  // are recognised by the compiler; named types are not), in the style of parallel::BlockParallelForFunctorTraits:
+  //   namespace onika { namespace soatl { template<> struct ApplyFunctorTraits<MyOp> { static constexpr bool CudaCompatible = true; }; } }
+  template<class OperatorT> struct ApplyFunctorTraits { static inline constexpr bool CudaCompatible = false; };
+
   namespace compute_details
   {
 #   if defined(__CUDACC__)
@@ -25,10 +30,9 @@ namespace onika { namespace soatl {
     }
     template<class OperatorT> static inline constexpr bool device_callable_v =
 #     if defined(__CUDACC_EXTENDED_LAMBDA__)
-      __nv_is_extended_host_device_lambda_closure_type(OperatorT) || __nv_is_extended_device_lambda_closure_type(OperatorT);
-#     else
-      false;
+      __nv_is_extended_host_device_lambda_closure_type(OperatorT) || __nv_is_extended_device_lambda_closure_type(OperatorT) ||
 #     endif
+      ApplyFunctorTraits<OperatorT>::CudaCompatible;
     template<class OperatorT, class... T>
     static inline bool try_device_apply( const OperatorT& f , size_t n , T* ... cols )
     {

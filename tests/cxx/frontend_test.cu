@@ -631,6 +631,19 @@ static int scenario_listed(Out& out)
 }
 
 // SOATL: layout, resize policy, tuple access, serialisation, device parallel_apply_simd
+struct DistFunctor
+{
+  double ax, ay, az;
+  ONIKA_HOST_DEVICE_FUNC inline void operator () ( double& d, double x, double y, double z ) const
+  {
+    x = x - ax; y = y - ay; z = z - az;
+    d = sqrt( x*x + y*y + z*z );
+    x /= d; y /= d; z /= d;
+    d += x/(y*z);
+  }
+};
+namespace onika { namespace soatl { template<> struct ApplyFunctorTraits<DistFunctor> { static inline constexpr bool CudaCompatible = true; }; } }
+
 static int scenario_soatl(Out& out, size_t n)
 {
   using namespace onika::soatl;
@@ -717,6 +730,10 @@ static int scenario_soatl(Out& out, size_t n)
         x /= d; y /= d; z /= d;
         d += x/(y*z);
       } , arrays , particle_e , particle_rx , particle_ry , particle_rz );
+    out.doubles( arrays[particle_e] , n );
+    // the same sweep by a named functor type that declares itself device-compatible (ApplyFunctorTraits)
+    for(size_t i=0;i<arrays.capacity();i++) arrays[particle_e][i] = 0.0;
+    parallel_apply_simd( DistFunctor{ ax , ay , az } , arrays , particle_e , particle_rx , particle_ry , particle_rz );
     out.doubles( arrays[particle_e] , n );
     arrays.clear();
   }

@@ -258,15 +258,16 @@ def test_soatl_container_layout_serialize_and_device_apply(prog, tmp_path, orc, 
     g = gold["soatl_serialize"]
     assert raw[pos:pos + wire_size].tobytes().hex() == g["packed_hex"]      # byte-identical to the reference's wire format
     pos += wire_size
-    e = raw[pos:].view(np.float64)
+    e, e_named = raw[pos:pos + 8 * n].view(np.float64), raw[pos + 8 * n:].view(np.float64)
     want = orc.soatl_dist(lcg_uniform(n, 10, 0, 1), lcg_uniform(n, 11, 0, 1), lcg_uniform(n, 12, 0, 1))
-    assert np.isnan(e[0]) and np.array_equal(e, want, equal_nan=True)
+    assert np.isnan(e[0]) and np.array_equal(e, want, equal_nan=True) and np.array_equal(e_named, want, equal_nan=True)
     # a larger sweep of the device lambda
     n = 100_003
     raw = run(prog, tmp_path, "soatl", n)
-    e = raw[-8 * n:].view(np.float64)
+    e, e_named = raw[-16 * n:-8 * n].view(np.float64), raw[-8 * n:].view(np.float64)
     want = orc.soatl_dist(lcg_uniform(n, 10, 0, 1), lcg_uniform(n, 11, 0, 1), lcg_uniform(n, 12, 0, 1))
-    assert np.array_equal(e, want, equal_nan=True)
+    assert np.array_equal(e, want, equal_nan=True)              # extended lambda on the device
+    assert np.array_equal(e_named, want, equal_nan=True)        # named functor type with ApplyFunctorTraits::CudaCompatible
 
 
 # ---------------------------------------------------------------- the reference's own tutorial plugins, compiled unchanged
