@@ -3,9 +3,13 @@
 
 Metric (BASELINE.json): block_parallel_for & reduce HBM GB/s.  Workload at every N: BASELINE configs[1], the fp64
 reduce-min of tests/gpu_reduce_min_fp64.cu over 2^28 doubles (2 GiB) PER GPU (weak scaling: the element range is
-sharded, the only exchange is the all-reduce of one 8-byte partial per step).
+sharded, the only exchange is the all-reduce of one 8-byte partial per step).  At N > 1 the same line also carries
+`strong` (fixed totals 2^28 and 2^31 doubles: T(1) on rank 0 alone vs T(N) sharded), `C5` (the two-lane kernel
+sequence of tests/parallel_queue_lane.cu at 16384^2 with rows sharded and fused min + sum, BASELINE configs[4]) and
+`checks` (multi-GPU parity against the oracle, outside every timed region; a mismatch fails the run).
 
   python bench.py --gpus N --steps K --warmup W            this repo (CUDA path through the C ABI)
+  python bench.py --gpus N --scaling strong ...            headline workload = 2^28 doubles in TOTAL, sharded over N
   python bench.py --impl reference --gpus N --steps K ...  the reference's own OpenMP path on the host cores
 
 One JSON line on stdout (rank 0).  See the task contract for the keys; `roofline`, `cpu_baseline`, `e2e`, `clocks`
@@ -30,7 +34,16 @@ SEED = 1234
 METRIC = "block_parallel_for & reduce HBM GB/s (reduce_min fp64, 2^28 doubles per GPU)"
 UNIT = "GB/s"
 WORKLOAD = "reduce_min_f64_2^28 (BASELINE configs[1]; tests/gpu_reduce_min_fp64.cu shape)"
-CPU_SAMPLE_ELEMS = 1 << 27             # 1 GiB sample of the same workload for the host-core baseline
+CPU_SAMPLE_ELEMS = N_ELEMS              # the host-core baseline runs the same 2^28 elements (one GPU's share of the workload)
+L2_NOTE = "inputs larger than L2 (2 GiB per pass vs 126 MB)"
+
+
+def bench_config(scaling: str = "weak") -> dict:
+    """`config` of the JSON line: identical in both arms (the driver compares them)"""
+    c = {"workload": WORKLOAD, "elements_per_gpu": N_ELEMS, "bytes_per_gpu": N_ELEMS * 8, "l2": L2_NOTE}
+    if scaling == "strong":
+        c = {"workload": WORKLOAD + ", fixed total", "elements_total": N_ELEMS, "bytes_total": N_ELEMS * 8, "l2": "flushed between timed iterations when the shard fits L2, else larger than L2"}
+    return c
 
 
 def read_json(path):
@@ -139,9 +152,10 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------ reference arm
 def cpu_reduce_min_baseline(min_seconds: float, steps: int | None = None, warmup: int = 1):
-    """The reference's CPU implementation of the path on the host cores: cpu_compute of tests/gpu_reduce_min_fp64.cu
-    (through oracle/_ref, N = 2^20 per call as the reference hard-codes it) and the single-region restatement
-    (oracle port).  Returns (best GB/s, kind, cores, sample text, seconds per pass)."""
+    """The reference's CPU implementation of the path on the host cores, over the same 2^28 doubles one GPU gets:
+    `reference` = cpu_compute of tests/gpu_reduce_min_fp64.cu compiled from the reference tree (oracle/_ref; 2^20 elements per
+    call as the reference hard-codes it), `port` = the single-region restatement (oracle/oracle.c).
+    Returns a dict: value (GB/s of `kind`), kind, cores, sample, ref_gbs, port_gbs, seconds per pass, passes."""
     import numpy as np
     import oracle
     orc = oracle.orc
@@ -155,7 +169,7 @@ def cpu_reduce_min_baseline(min_seconds: float, steps: int | None = None, warmup
     d = np.empty(n, dtype=np.float64)
     orc.fill_lcg(d, SEED)                     # parallel first touch, like cpu_init (tests/gpu_reduce_min_fp64.cu:30-44)
     cores = orc.num_threads()
-    want = float(d.min())
+    want = orc.reduce_min(d)
 
     def run(fn):
         for _ in range(warmup):
@@ -169,18 +183,17 @@ def cpu_reduce_min_baseline(min_seconds: float, steps: int | None = None, warmup
             assert r == want
         return ts
 
-    res = {}
-    res["port"] = run(lambda: orc.reduce_min(d))
+    res = {"port": run(lambda: orc.reduce_min(d))}
     if oracle.ref.available():
         res["reference"] = run(lambda: oracle.ref.reduce_min_chunks(d)[0])
-    best_kind = min(res, key=lambda k: sorted(res[k])[len(res[k]) // 2])
-    ts = sorted(res[best_kind])
+    kind = "reference" if "reference" in res else "port"      # the line's value is the reference's own code whenever it was built
+    ts = sorted(res[kind])
     med = ts[len(ts) // 2]
     gbs = {k: n * 8 / sorted(v)[len(v) // 2] / 1e9 for k, v in res.items()}
-    sample = (f"reduce_min over a {n * 8 >> 20} MiB sample (2^27 doubles) of the workload, median of {len(ts)} passes, OpenMP {cores} threads; "
-              + ", ".join(f"{k}={v:.1f} GB/s" for k, v in gbs.items())
-              + " (reference = cpu_compute from the reference tree, 2^20 elements per call; port = oracle/oracle.c single region)")
-    return gbs[best_kind], best_kind, cores, sample, med, len(ts)
+    sample = (f"reduce_min over {n * 8 >> 20} MiB (2^28 doubles, one GPU's share), median of {len(ts)} passes, OpenMP {cores} threads; "
+              "reference = cpu_compute compiled from the reference tree (2^20 elements per call); port = oracle/oracle.c, one region")
+    return {"value": gbs[kind], "kind": kind, "cores": cores, "sample": sample, "ref_gbs": gbs.get("reference"), "port_gbs": gbs["port"],
+            "seconds": med, "passes": len(ts)}
 
 
 def cpu_secondary_baselines(budget_s: float = 2.0) -> dict:
@@ -230,17 +243,25 @@ def cpu_secondary_baselines(budget_s: float = 2.0) -> dict:
     return out
 
 
+def _cpu_baseline_object(b: dict) -> dict:
+    r = lambda v: None if v is None else round(v, 3)
+    return {"value": r(b["value"]), "unit": UNIT, "cores": b["cores"], "kind": b["kind"], "sample": b["sample"],
+            "ref_gbs": r(b["ref_gbs"]), "port_gbs": r(b["port_gbs"])}
+
+
 def run_reference_arm(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    gbs, kind, cores, sample, med, nsteps = cpu_reduce_min_baseline(0.0, steps=max(1, args.steps), warmup=max(1, args.warmup))
+    b = cpu_reduce_min_baseline(0.0, steps=max(1, args.steps), warmup=max(1, args.warmup))
+    gbs = b["value"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": nsteps,
-        "warmup": max(1, args.warmup), "ms_per_step": round(med * 1e3, 4), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": b["passes"],
+        "warmup": max(1, args.warmup), "ms_per_step": round(b["seconds"] * 1e3, 4), "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "each step = one pass over a 1 GiB sample of the workload on the host cores; no GPU involved"},
-        "cpu_baseline": {"value": round(gbs, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "config": bench_config(args.scaling),
+        "method": "each step = one pass of the reference's OpenMP reduce-min over 2^28 doubles in host memory on the box's host cores (rank 0 only); no GPU involved",
+        "cpu_baseline": _cpu_baseline_object(b),
         "e2e": {"value": round(gbs, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "elements_per_s": round(gbs * 1e9 / 8, 1),
     }
@@ -345,6 +366,345 @@ def secondary_kernels(ob, torch):
     return out
 
 
+def _max_over_ranks(torch, dist, world, v: float) -> float:
+    if world == 1:
+        return v
+    t = torch.tensor([v], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _gather_floats(torch, dist, world, v: float):
+    if world == 1:
+        return [v]
+    t = torch.tensor([v], dtype=torch.float64, device="cuda")
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [float(o.item()) for o in out]
+
+
+class _L2Flush:
+    """READS 1 GiB of other data (clean lines: a write-flush would leave dirty lines whose eviction is billed to the next kernel)"""
+
+    def __init__(self, torch, ob, P):
+        self.buf = torch.ones(1 << 27, dtype=torch.float64, device="cuda")
+        self.out = torch.empty(1, dtype=torch.float64, device="cuda")
+        self.f = P.ReduceFunctor(ob.OP_MIN, self.buf, self.out)
+
+    def __call__(self):
+        self.f.launch(self.buf.numel(), 0)
+
+
+def strong_scaling(K, W, world, rank, torch, dist, ob, P, D, xchg):
+    """scaling = T(1)/T(G) at FIXED total size.  T(1): rank 0 alone reduces the whole input (the others wait at a
+    barrier); T(N): every rank reduces its contiguous shard and the partials are combined inside the kernel.  Both timed with
+    CUDA events over K back-to-back steps (max over ranks).  2^28 is BASELINE C2; 2^31 doubles (16 GiB) is the largest
+    power of two that fits one GPU next to the other buffers."""
+    out = {}
+    errors = []                                                  # raised at the very end: every rank goes through every collective
+    for label, total in (("2^28", 1 << 28), ("2^31", 1 << 31)):
+        b, e = D.shard_range(total, rank, world)
+        n_loc = e - b
+        n_alloc = total if rank == 0 else n_loc                 # rank 0 also holds the whole input for T(1)
+        data = torch.empty(n_alloc, dtype=torch.float64, device="cuda")
+        data.uniform_(1e-3, 1.0, generator=torch.Generator(device="cuda").manual_seed(SEED + 17 * rank))
+        res = torch.empty(1, dtype=torch.float64, device="cuda")
+        shard = data[:n_loc]
+        want = shard.min()
+        if world > 1:
+            dist.all_reduce(want, op=dist.ReduceOp.MIN)
+
+        def step_n():
+            if xchg is not None:
+                xchg.reduce(ob.OP_MIN, shard, n=n_loc, out=res, lane=0)
+            else:
+                P.ReduceFunctor(ob.OP_MIN, shard, res).launch(n_loc, 0)
+                if world > 1:
+                    D.combine_across_ranks(ob.OP_MIN, res)
+
+        def timed(fn, k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(k):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / k
+
+        for _ in range(W):
+            step_n()
+        torch.cuda.synchronize()
+        if float(res.item()) != float(want.item()):
+            errors.append(f"strong scaling {label}: sharded reduce_min differs from the check value")
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        tn = _max_over_ranks(torch, dist, world, timed(step_n, K))
+        t1 = 0.0
+        if rank == 0:
+            f1 = P.ReduceFunctor(ob.OP_MIN, data, res)
+            for _ in range(W):
+                f1.launch(total, 0)
+            torch.cuda.synchronize()
+            t1 = timed(lambda: f1.launch(total, 0), K)
+        t1 = _max_over_ranks(torch, dist, world, t1)
+        out[label] = {"elements_total": total, "T1_ms": round(t1, 5), "TN_ms": round(tn, 5), "speedup": round(t1 / tn, 3),
+                      "GBps_1": round(total * 8 / t1 / 1e6, 1), "GBps_N": round(total * 8 / tn / 1e6, 1)}
+        del data, shard
+        torch.cuda.empty_cache()
+    assert not errors, "; ".join(errors)
+    out["definition"] = "T(1)/T(N) at fixed total size; T(1) = rank 0 alone on the whole input in this same run, T(N) = sharded, partials combined inside the reduction kernel; K back-to-back steps between two CUDA events, max over ranks"
+    return out
+
+
+def c5_lane_sequence(K, W, world, rank, torch, dist, ob, P, D, xchgs):
+    """BASELINE configs[4] (tests/parallel_queue_lane.cu:58-108 at 16384 x 16384): two arrays, kernel1 -> kernel2 -> min -> sum
+    per array on two lanes, rows sharded contiguously over the ranks; the min and the sum of each array are combined across the
+    GPUs inside the reduction kernels (one exchange per lane).  Timed from a fork on lane 0 to the join on lane 0, K steps
+    between two CUDA events, max over ranks; T(1) = rank 0 alone on the whole arrays."""
+    import ctypes as C
+    from onika_b200 import _capi
+    L = _capi.lib()
+    rows_total = cols = 1 << 14
+    b, e = D.shard_range(rows_total, rank, world)
+    rows = e - b
+    rows_alloc = rows_total if rank == 0 else rows
+    arrs = [torch.empty(rows_alloc * cols, dtype=torch.float64, device="cuda") for _ in range(2)]
+    for k, a in enumerate(arrs):
+        a.uniform_(0.0, 1.0, generator=torch.Generator(device="cuda").manual_seed(SEED + 31 * rank + k))
+    res = torch.zeros(4, dtype=torch.float64, device="cuda")
+    adds = ((1.1, 1.2), (1.3, 1.4))
+    lanes = (1, 2)
+
+    def step(nrows, fused):
+        for k in range(2):
+            _capi.check(L.onk_lane_wait_lane(lanes[k], 0))          # fork: both lanes start after what lane 0 holds (the start event)
+            p = arrs[k].data_ptr()
+            _capi.check(L.onk_value_add_f64(p, nrows, cols, adds[k][0], lanes[k]))
+            _capi.check(L.onk_value_add_f64(p, nrows, cols, adds[k][1], lanes[k]))
+            for j, op in enumerate((ob.OP_MIN, ob.OP_SUM)):
+                o = res[2 * k + j:].data_ptr()
+                if fused:
+                    _capi.check(L.onk_reduce_xchg_f64(op, p, nrows * cols, o, xchgs[k].handle, lanes[k]))
+                else:
+                    _capi.check(L.onk_reduce_f64(op, p, nrows * cols, o, lanes[k]))
+        for k in range(2):
+            _capi.check(L.onk_lane_wait_lane(0, lanes[k]))          # join
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
+    fused = world > 1 and xchgs is not None
+    if world > 1 and not fused:
+        return {"skipped": "C5 on N GPUs needs the peer exchange (CUDA IPC / peer access unavailable on this box)"}
+    # expected minimum: x -> fl(fl(x + v1) + v2) is monotone, so the minimum of the array follows the same recurrence exactly
+    mins = [a[:rows * cols].min() for a in arrs]
+    if world > 1:
+        for m in mins:
+            dist.all_reduce(m, op=dist.ReduceOp.MIN)
+    mins = [float(m.item()) for m in mins]
+    nsteps = W + K
+    for _ in range(W):
+        step(rows, fused)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    tn = _max_over_ranks(torch, dist, world, timed(lambda: step(rows, fused), K))
+    for k in range(2):
+        for _ in range(nsteps):
+            mins[k] = (mins[k] + adds[k][0]) + adds[k][1]
+    got = res.cpu().numpy().tolist()
+    errors = []                                                  # raised at the very end: every rank goes through every collective
+    if not (got[0] == mins[0] and got[2] == mins[1]):
+        errors.append(f"C5: minima {got[0]!r}, {got[2]!r} differ from the expected {mins!r}")
+    sums = [a[:rows * cols].sum() for a in arrs]
+    mags = [a[:rows * cols].abs().sum() for a in arrs]
+    if world > 1:
+        for t in sums + mags:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    for k in range(2):
+        if not abs(got[2 * k + 1] - float(sums[k].item())) <= 1e-12 * float(mags[k].item()):
+            errors.append(f"C5: sum of array {k} outside 1e-12")
+    if world > 1:
+        g = [torch.empty_like(res) for _ in range(world)]
+        dist.all_gather(g, res)
+        if not all(torch.equal(x.view(torch.int64), g[0].view(torch.int64)) for x in g):
+            errors.append("C5: reductions differ between ranks")
+    t1 = tn
+    if world > 1:
+        t1 = 0.0
+        if rank == 0:
+            for _ in range(W):
+                step(rows_total, False)
+            torch.cuda.synchronize()
+            t1 = timed(lambda: step(rows_total, False), K)
+        t1 = _max_over_ranks(torch, dist, world, t1)
+    nbytes = 2 * (2 * 16 + 2 * 8) * rows_total * cols
+    out = {"rows_x_cols": [rows_total, cols], "arrays": 2, "lanes": 2, "kernels_per_step_per_rank": 8, "algorithmic_bytes": nbytes,
+           "T1_ms": round(t1, 5), "TN_ms": round(tn, 5), "speedup": round(t1 / tn, 3), "GBps_N": round(nbytes / tn / 1e6, 1),
+           "checks": "min bit-exact (monotone recurrence), sum <= 1e-12, same bits on all ranks",
+           "sequence": "per array: value_add(v1) -> value_add(v2) -> reduce min -> reduce sum on its own lane; fork/join on lane 0 every step"}
+    del arrs
+    torch.cuda.empty_cache()
+    assert not errors, "; ".join(errors)
+    return out
+
+
+def h2d_peak(torch, dist, world, nbytes=1 << 30):
+    """measured host->device copy rate of this box: every rank copies `nbytes` from its own pinned buffer at the same time
+    (cudaMemcpyAsync), best of 3; returns (per-rank GB/s list, aggregate GB/s)"""
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    best = 0.0
+    for _ in range(4):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, nbytes / e0.elapsed_time(e1) / 1e6)
+    per_rank = _gather_floats(torch, dist, world, best)
+    del src, dst
+    return [round(v, 2) for v in per_rank], round(sum(per_rank), 2)
+
+
+def e2e_measure(K, world, rank, torch, dist, ob, P, data, n):
+    """the plugin-facing host-buffer call onk_host_reduce_f64 on PINNED and on PAGEABLE host input (host -> device copies
+    inside the timed region), next to the measured H2D copy rate of the same box"""
+    per_rank_peak, agg_peak = h2d_peak(torch, dist, world)
+    want = float(data.min().item())
+    Ke = max(2, min(K, 10))
+
+    def run(hostbuf):
+        for _ in range(2):
+            r = P.host_reduce(ob.OP_MIN, hostbuf)
+        assert r == want
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            r = P.host_reduce(ob.OP_MIN, hostbuf)   # synchronous: returns the host result (8 bytes D2H)
+            if world > 1:
+                rt = torch.tensor([r], dtype=torch.float64, device="cuda")
+                dist.all_reduce(rt, op=dist.ReduceOp.MIN)
+                r = float(rt.item())
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / Ke
+        per_rank = _gather_floats(torch, dist, world, n * 8 / dt / 1e9)
+        return _max_over_ranks(torch, dist, world, dt), per_rank
+
+    pinned = torch.empty(n, dtype=torch.float64).pin_memory()
+    pinned.copy_(data)
+    torch.cuda.synchronize()
+    dt, per_rank = run(pinned)
+    e2e = {"value": round(world * n * 8 / dt / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": 8,
+           "ms_per_step": round(dt * 1e3, 3), "steps": Ke, "call": "onk_host_reduce_f64 (pinned host input, chunked H2D overlapped with the kernel)",
+           "per_rank_GBps": [round(v, 2) for v in per_rank],
+           "h2d_peak_GBps": agg_peak, "h2d_peak_per_rank_GBps": per_rank_peak,
+           "h2d_peak_how": "1 GiB cudaMemcpyAsync from pinned memory on every rank at the same time, best of 4",
+           "frac_of_pcie": round(world * n * 8 / dt / 1e9 / agg_peak, 4) if agg_peak else None}
+    pageable = torch.empty(n, dtype=torch.float64)
+    pageable.copy_(pinned)
+    del pinned
+    dtp, per_rank_p = run(pageable)
+    e2e["pageable"] = {"value": round(world * n * 8 / dtp / 1e9, 3), "ms_per_step": round(dtp * 1e3, 3),
+                       "per_rank_GBps": [round(v, 2) for v in per_rank_p],
+                       "call": "onk_host_reduce_f64 on ordinary (pageable) host memory: staged through pinned buffers by the library"}
+    del pageable
+    return e2e
+
+
+def e2e_multipass(K, world, rank, torch, dist, ob, D):
+    """e2e of a MULTI-PASS workload, where a transfer is amortised: the C5 sequence on HOST-resident arrays -- each rank's two
+    row shards cross PCIe once (pinned host -> device, on the two lanes), then kernel1, kernel2, min and sum run on the
+    device and 32 bytes of results come back; the updated arrays stay device-resident, as the reference's managed arrays do."""
+    import ctypes as C
+    import numpy as np
+    from onika_b200 import _capi
+    L = _capi.lib()
+    rows_total = cols = 1 << 14
+    b, e = D.shard_range(rows_total, rank, world)
+    rows = e - b
+    n = rows * cols
+    host = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2)]
+    dev = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(2)]
+    for k, h in enumerate(host):
+        dev[k].uniform_(0.0, 1.0)
+        h.copy_(dev[k])                       # the step's input lives in pinned host memory
+    torch.cuda.synchronize()
+    res = torch.zeros(4, dtype=torch.float64, device="cuda")
+    res_host = torch.zeros(4, dtype=torch.float64).pin_memory()
+    adds = ((1.1, 1.2), (1.3, 1.4))
+    lanes = (1, 2)
+
+    def once():
+        for k in range(2):
+            _capi.check(L.onk_memcpy(dev[k].data_ptr(), host[k].data_ptr(), n * 8, lanes[k]))
+            _capi.check(L.onk_value_add_f64(dev[k].data_ptr(), rows, cols, adds[k][0], lanes[k]))
+            _capi.check(L.onk_value_add_f64(dev[k].data_ptr(), rows, cols, adds[k][1], lanes[k]))
+            _capi.check(L.onk_reduce_f64(ob.OP_MIN, dev[k].data_ptr(), n, res[2 * k:].data_ptr(), lanes[k]))
+            _capi.check(L.onk_reduce_f64(ob.OP_SUM, dev[k].data_ptr(), n, res[2 * k + 1:].data_ptr(), lanes[k]))
+            _capi.check(L.onk_memcpy(res_host[2 * k:].data_ptr(), res[2 * k:].data_ptr(), 16, lanes[k]))
+        for k in range(2):
+            _capi.check(L.onk_lane_sync(lanes[k]))
+        return res_host.clone()
+
+    once()
+    if world > 1:
+        dist.barrier()
+    Ke = max(2, min(K, 5))
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        r = once()
+        if world > 1:
+            rt = r.cuda()
+            dist.all_reduce(rt, op=dist.ReduceOp.MIN)     # (stand-in for the combine; 32 bytes)
+    torch.cuda.synchronize()
+    dt = _max_over_ranks(torch, dist, world, (time.perf_counter() - t0) / Ke)
+    want_min = [(float(h.min().item()) + a[0]) + a[1] for h, a in zip(host, adds)]
+    assert [float(r[0]), float(r[2])] == want_min, "multi-pass e2e: minima differ"
+    nbytes = 2 * (2 * 16 + 2 * 8) * rows_total * cols
+    return {"workload": "C5 lane sequence, 2 x 16384^2 fp64 in pinned HOST memory, rows sharded; 4 passes per transferred byte",
+            "value": round(nbytes / dt / 1e9, 3), "unit": UNIT, "ms_per_step": round(dt * 1e3, 3), "steps": Ke,
+            "h2d_bytes_per_step": 2 * n * 8, "d2h_bytes_per_step": 32, "algorithmic_bytes": nbytes}
+
+
+def cpu_multipass_baseline(budget_s: float = 6.0) -> dict:
+    """the same C5 sequence by the reference's OpenMP path on the host cores (oracle/_ref lane_sequence; port otherwise) on a
+    4096 x 4096 sample per array, plus min and sum by the oracle: GB/s of the same algorithmic bytes"""
+    import numpy as np
+    import oracle
+    orc = oracle.orc
+    rows = cols = 4096
+    a1 = np.empty((rows, cols)); a2 = np.empty((rows, cols))
+    orc.fill_lcg(a1.reshape(-1), 3, 0.0, 1.0); orc.fill_lcg(a2.reshape(-1), 4, 0.0, 1.0)
+    use_ref = oracle.ref.available()
+    ts = []
+    t_end = time.perf_counter() + budget_s
+    while time.perf_counter() < t_end and len(ts) < 9:
+        t0 = time.perf_counter()
+        if use_ref:
+            oracle.ref.lane_sequence(a1, a2, 1.1, 1.2, 1.3, 1.4)
+        else:
+            orc.lane_sequence(a1, a2, 1.1, 1.2, 1.3, 1.4)
+        for a in (a1, a2):
+            orc.reduce_min(a.reshape(-1)); orc.reduce_sum(a.reshape(-1), orc.num_threads())
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    nbytes = 2 * (2 * 16 + 2 * 8) * rows * cols
+    return {"value": round(nbytes / ts[len(ts) // 2] / 1e9, 2), "unit": UNIT, "cores": orc.num_threads(), "kind": "reference" if use_ref else "port",
+            "sample": f"2 x {rows}x{cols} fp64 in host memory, median of {len(ts)} passes"}
+
+
 def run_ours(args) -> int:
     import numpy as np
     import torch
@@ -364,7 +724,10 @@ def run_ours(args) -> int:
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    n = N_ELEMS
+    strong = args.scaling == "strong"
+    n_total = N_ELEMS * (1 if strong else world)
+    b0, e0 = D.shard_range(n_total, rank, world)
+    n = e0 - b0                               # weak: 2^28 per GPU; strong: 2^28 / N per GPU
     # synthetic shard of this rank: uniform(1e-3, 1), seeded per rank; NaN-free, no signed-zero mix
     g = torch.Generator(device="cuda").manual_seed(SEED + rank)
     data = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * (1.0 - 1e-3) + 1e-3
@@ -374,9 +737,11 @@ def run_ours(args) -> int:
     # N > 1: the path's only exchange is one fp64 partial per rank.  Default: fused into the reduction kernel over NVLink
     # peer memory (onk_reduce_xchg_f64).  --exchange nccl: separate NCCL all-reduce(MIN) after the kernel.
     xchg = None
+    xchg_lanes = None
     if world > 1 and args.exchange == "fused":
         try:
             xchg = D.PeerExchange()
+            xchg_lanes = (D.PeerExchange(), D.PeerExchange())     # one exchange per lane for the C5 sequence
             ok = 1
         except Exception as ex:   # no peer access / CUDA IPC on this box: every rank must take the same path
             print(f"[bench] rank {rank}: fused exchange unavailable ({str(ex)[:120]}); using NCCL", file=sys.stderr)
@@ -386,13 +751,15 @@ def run_ours(args) -> int:
         if int(flag.item()) == 0:
             if xchg is not None:
                 xchg.close()
-            xchg = None
+            xchg = xchg_lanes = None
+
+    flush = _L2Flush(torch, ob, P) if n * 8 < (512 << 20) else None   # strong scaling at large N: the shard may fit L2
 
     def step():
         if xchg is not None:
             xchg.reduce(ob.OP_MIN, data, n=n, out=result, lane=0)   # ONE kernel: local reduce + cross-GPU combine
         else:
-            functor.launch(n, 0)              # one pass of the hot path over this rank's 2 GiB shard
+            functor.launch(n, 0)              # one pass of the hot path over this rank's shard
             if world > 1:
                 D.combine_across_ranks(ob.OP_MIN, result)
 
@@ -415,31 +782,40 @@ def run_ours(args) -> int:
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = ob.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
-    ev0.record()                              # exactly K steps between the two events, nothing else in the stream
-    for k in range(K):
-        step()
-    ev1.record()
-    torch.cuda.synchronize()
+    if flush is None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()                              # exactly K steps between the two events, nothing else in the stream
+        for k in range(K):
+            step()
+        ev1.record()
+        torch.cuda.synchronize()
+        total_ms = ev0.elapsed_time(ev1)
+        flush_launches = 0
+    else:
+        # small shards: L2 flushed (by a read of 1 GiB) before every timed step, one event pair per step
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for k in range(K):
+            flush()
+            evs[k][0].record(); step(); evs[k][1].record()
+        torch.cuda.synchronize()
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        flush_launches = K
     if world > 1:
         dist.barrier()
     t_wall1 = time.time()
-    launches = ob.launch_count() - launches0
-    total_ms = ev0.elapsed_time(ev1)
+    launches = ob.launch_count() - launches0 - flush_launches
     if world > 1:
-        tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms = float(tt.item())
+        total_ms = _max_over_ranks(torch, dist, world, total_ms)
         tl = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(tl, op=dist.ReduceOp.SUM)
         launches = int(tl.item())
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     ms_per_step = total_ms / K
-    value = world * n * 8 / (ms_per_step * 1e-3) / 1e9
+    value = n_total * 8 / (ms_per_step * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel (reduce_f64_kernel): device time of the kernel alone, measured live ----
-    if world == 1:
+    # ---- roofline of the dominant kernel: device time of the kernel alone, measured live ----
+    if world == 1 and flush is None:
         # the timed region above IS K launches of this kernel and nothing else: same events, same number
         kernel_ms = ms_per_step
     else:
@@ -466,81 +842,105 @@ def run_ours(args) -> int:
         else (6650.0, "fallback (B200_PROFILING.md)")
     achieved = n * 8 / (kernel_ms * 1e-3) / 1e9
     traffic = read_json(os.path.join(ROOT, "profiles", "roofline_traffic.json"))
-    roofline = {"bound": "hbm", "kernel": "onk::reduce_f64_tma_kernel<MIN>", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+    big = n >= (1 << 26)
+    roofline = {"bound": "hbm", "kernel": "onk::reduce_f64_tma_kernel<MIN>" if big else "onk::reduce_f64_kernel<MIN>", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": n * 8, "kernel_ms": round(kernel_ms, 5),
-                "traffic": (traffic or {}).get("reduce_f64_kernel_dram_bytes_per_launch")}
+                "traffic": (traffic or {}).get("reduce_f64_kernel_dram_bytes_per_launch") if n == N_ELEMS else None,
+                "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this size (profiles/roofline_traffic.json), not measured in this run"}
 
     # ---- e2e: the plugin-facing host-buffer call (host -> device copies inside the timed region) ----
     e2e = None
-    try:
-        if args.profile_mode:
-            raise RuntimeError("skipped (--profile-mode)")
-        hostbuf = torch.empty(n, dtype=torch.float64).pin_memory()
-        hostbuf.copy_(data)                   # the step's input lives in pinned host memory
-        torch.cuda.synchronize()
-        Ke = max(2, min(K, 10))
-        for _ in range(2):
-            r = P.host_reduce(ob.OP_MIN, hostbuf)
-        assert r == float(data.min().item())
+    e2e_mp = None
+    if not args.profile_mode:
+        try:
+            e2e = e2e_measure(K, world, rank, torch, dist, ob, P, data, n)
+        except Exception as ex:  # pragma: no cover
+            e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+    del data, functor
+    torch.cuda.empty_cache()
+
+    # ---- fixed-size scaling, the C5 sequence on N GPUs, multi-GPU parity (all outside the headline's timed region) ----
+    strong_obj = c5 = checks = None
+    failures = []
+
+    def section(fn):
+        # a failed check is recorded and the run goes on: every rank walks through the same collectives, then all fail together
+        try:
+            return fn()
+        except AssertionError as ex:
+            failures.append(str(ex)[:300])
+            print(f"[bench] CHECK FAILED on rank {rank}: {ex}", file=sys.stderr)
+            return {"failed": str(ex)[:300]}
+
+    if not args.profile_mode and not args.no_extras:
         if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(Ke):
-            r = P.host_reduce(ob.OP_MIN, hostbuf)   # synchronous: returns the host result (8 bytes D2H)
-            if world > 1:
-                rt = torch.tensor([r], dtype=torch.float64, device="cuda")
-                dist.all_reduce(rt, op=dist.ReduceOp.MIN)
-                r = float(rt.item())
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / Ke
-        if world > 1:
-            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        e2e = {"value": round(world * n * 8 / dt / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": 8,
-               "ms_per_step": round(dt * 1e3, 3), "steps": Ke, "call": "onk_host_reduce_f64 (pinned host input, chunked H2D overlapped with the kernel)"}
-        del hostbuf
-    except Exception as ex:  # pragma: no cover
-        e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+            strong_obj = section(lambda: strong_scaling(min(K, 50), 3, world, rank, torch, dist, ob, P, D, xchg))
+        c5 = section(lambda: c5_lane_sequence(min(K, 10), 3, world, rank, torch, dist, ob, P, D, xchg_lanes))
+        e2e_mp = section(lambda: e2e_multipass(K, world, rank, torch, dist, ob, D))
+        if world > 1 and xchg is not None:
+            from tests import _multigpu_checks
+            checks = _multigpu_checks.run_checks(rank, world)        # never raises: {name: "ok" | message}
+            failures += [f"{k}: {v}" for k, v in checks.items() if v != "ok"]
+    failed = "; ".join(failures) if failures else None
+    if world > 1:
+        bad = torch.tensor([1 if failed else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()) and not failed:
+            failed = "a check failed on another rank"
 
     cpu_baseline = None
     kernels = None
-    if rank == 0 and world == 1 and not args.profile_mode:
-        del data
-        torch.cuda.empty_cache()
-        if not args.no_extras:
+    if rank == 0 and not args.profile_mode:
+        if world == 1 and not args.no_extras:
             try:
                 kernels = secondary_kernels(ob, torch)
             except Exception as ex:  # pragma: no cover
                 kernels = {"error": str(ex)[:200]}
-        try:
-            gbs, kind, cores, sample, _, _ = cpu_reduce_min_baseline(args.cpu_seconds)
-            cpu_baseline = {"value": round(gbs, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
-            if kernels is not None and "error" not in kernels:
-                kernels["cpu_reference_same_box"] = cpu_secondary_baselines()
-        except Exception as ex:  # pragma: no cover
-            cpu_baseline = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+        if world == 1:
+            try:
+                cpu_baseline = _cpu_baseline_object(cpu_reduce_min_baseline(args.cpu_seconds))
+                if kernels is not None and "error" not in kernels:
+                    kernels["cpu_reference_same_box"] = cpu_secondary_baselines()
+                if e2e_mp is not None:
+                    e2e_mp["cpu_baseline"] = cpu_multipass_baseline()
+            except Exception as ex:  # pragma: no cover
+                cpu_baseline = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
 
     if rank == 0:
+        method = {"sharding": (f"element range x{world}; one fp64 partial per rank and step, combined " + ("inside the reduction kernel over NVLink peer memory (rank order)" if xchg is not None else "by an NCCL all-reduce(min)")) if world > 1 else "single GPU",
+                  "timing": "CUDA events on the launching stream, max over ranks"}
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "elements_per_gpu": n, "bytes_per_gpu": n * 8, "sharding": (f"element range x{world}; one fp64 partial per rank and step, combined " + ("inside the reduction kernel over NVLink peer memory (rank order)" if xchg is not None else "by an NCCL all-reduce(min)")) if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2 (2 GiB per pass vs 126 MB)", "timing": "CUDA events on the launching stream, max over ranks"},
+            "config": bench_config(args.scaling), "method": method,
             "elements_per_s": round(value * 1e9 / 8, 1),
             "frac_of_nominal_8TBs_per_gpu": round(value / world / 8000.0, 4),
             "kernel_launch_ms_min_median_max": [round(per_step[0], 5), round(per_step[len(per_step) // 2], 5), round(per_step[-1], 5)],
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks, "gpu_launches": launches,
         }
+        if strong_obj is not None:
+            line["strong"] = strong_obj
+        if c5 is not None:
+            line["C5"] = c5
+        if e2e_mp is not None:
+            line["e2e_multipass"] = e2e_mp
+        if checks is not None:
+            line["checks"] = checks
+        if failed:
+            line["checks_failed"] = failed
         if kernels is not None:
             line["kernels"] = kernels
         emit_json(line)
+    if xchg is not None:
+        torch.cuda.synchronize()
+        dist.barrier()                            # no peer is still storing into this rank's buffers
+        xchg.close(); xchg_lanes[0].close(); xchg_lanes[1].close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return 3 if failed else 0
 
 
 class _OnlyJsonOnStdout:
@@ -580,6 +980,7 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: 2^28 doubles per GPU (default, the driver's efficiency arithmetic); strong: 2^28 doubles in total")
     ap.add_argument("--cpu-seconds", type=float, default=6.0, help="wall budget per CPU-baseline variant")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="N>1: cross-GPU combine inside the kernel (NVLink peer stores) or a separate NCCL all-reduce")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary per-config kernel timings")

@@ -117,22 +117,45 @@ namespace onika
 #  define ONIKA_CU_BLOCK_SHARED        __shared__
 #  define ONIKA_CU_GLOBAL_VARIABLE     __managed__
 
+// A CTA is either ONE block of the reference's launch (the usual case) or -- when the runtime packs small items, see
+// block_parallel_for_adapter.h "sub-block items" -- blockDim.y independent SUB-BLOCKS of blockDim.x <= 32 threads, each of which
+// stands for one block: the block vocabulary below then speaks about the calling thread's sub-block (size blockDim.x, thread
+// index threadIdx.x, barrier = the sub-block's lanes of the warp).  Such CTAs are launched as explicit one-CTA clusters
+// (onk_launch_ex, ONK_LAUNCH_SUB_BLOCKS), which device code reads from a launch constant: one uniform predicate, no memory.
+namespace onika { namespace cuda {
+  __device__ __forceinline__ bool sub_block_cta()
+  { unsigned int r; asm("{\n\t.reg .pred p;\n\tmov.pred p, %%is_explicit_cluster;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(r)); return r != 0u; }
+  __device__ __forceinline__ unsigned int lane_id() { unsigned int r; asm("mov.u32 %0, %%laneid;" : "=r"(r)); return r; }
+  // lanes of the calling thread's group of `n` consecutive lanes (n a power of two <= 32)
+  __device__ __forceinline__ unsigned int lane_group_mask(unsigned int n)
+  { return ( n >= 32u ) ? 0xffffffffu : ( ( ( 1u << n ) - 1u ) << ( lane_id() & ~( n - 1u ) ) ); }
+  __device__ __forceinline__ unsigned int block_size()  { return sub_block_cta() ? blockDim.x : ( blockDim.x * blockDim.y * blockDim.z ); }
+  __device__ __forceinline__ unsigned int thread_idx()  { return sub_block_cta() ? threadIdx.x : ( ( ( threadIdx.z * blockDim.y ) + threadIdx.y ) * blockDim.x + threadIdx.x ); }
+  __device__ __forceinline__ unsigned int block_idx()   { const unsigned int b = ( ( blockIdx.z * gridDim.y ) + blockIdx.y ) * gridDim.x + blockIdx.x; return sub_block_cta() ? ( b * blockDim.y + threadIdx.y ) : b; }
+  __device__ __forceinline__ unsigned int grid_size()   { const unsigned int g = gridDim.x * gridDim.y * gridDim.z; return sub_block_cta() ? ( g * blockDim.y ) : g; }
+  __device__ __forceinline__ dim3 block_dims()          { return sub_block_cta() ? dim3( blockDim.x , 1 , 1 ) : dim3( blockDim.x , blockDim.y , blockDim.z ); }
+  __device__ __forceinline__ dim3 thread_coord()        { return sub_block_cta() ? dim3( threadIdx.x , 0 , 0 ) : dim3( threadIdx.x , threadIdx.y , threadIdx.z ); }
+  __device__ __forceinline__ void block_sync()          { if( sub_block_cta() ) __syncwarp( lane_group_mask( blockDim.x ) ); else __syncthreads(); }
+  __device__ __forceinline__ int  block_sync_or(int p)  { return sub_block_cta() ? __any_sync( lane_group_mask( blockDim.x ) , p ) : __syncthreads_or( p ); }
+  __device__ __forceinline__ int  block_sync_and(int p) { return sub_block_cta() ? __all_sync( lane_group_mask( blockDim.x ) , p ) : __syncthreads_and( p ); }
+} }
+
 #  define ONIKA_CU_GRID_DIMS    gridDim
-#  define ONIKA_CU_GRID_SIZE    (gridDim.x*gridDim.y*gridDim.z)
+#  define ONIKA_CU_GRID_SIZE    ::onika::cuda::grid_size()
 #  define ONIKA_CU_BLOCK_COORD  blockIdx
-#  define ONIKA_CU_BLOCK_IDX    ( ( ( (blockIdx.z*gridDim.y) + blockIdx.y ) * gridDim.x ) + blockIdx.x )
-#  define ONIKA_CU_BLOCK_DIMS   blockDim
-#  define ONIKA_CU_BLOCK_SIZE   (blockDim.x*blockDim.y*blockDim.z)
-#  define ONIKA_CU_THREAD_COORD threadIdx
-#  define ONIKA_CU_THREAD_IDX   ( ( ( (threadIdx.z*blockDim.y) + threadIdx.y ) * blockDim.x ) + threadIdx.x )
+#  define ONIKA_CU_BLOCK_IDX    ::onika::cuda::block_idx()
+#  define ONIKA_CU_BLOCK_DIMS   ::onika::cuda::block_dims()
+#  define ONIKA_CU_BLOCK_SIZE   ::onika::cuda::block_size()
+#  define ONIKA_CU_THREAD_COORD ::onika::cuda::thread_coord()
+#  define ONIKA_CU_THREAD_IDX   ::onika::cuda::thread_idx()
 
 // threads of the block share the iterations [s,e)
 #  define ONIKA_CU_BLOCK_SIMD_FOR(T,i,s,e)           for(T i=(s)+ONIKA_CU_THREAD_IDX ; i<(e) ; i+=ONIKA_CU_BLOCK_SIZE )
 #  define ONIKA_CU_BLOCK_SIMD_FOR_UNGUARDED(T,i,s,e) for(T _onika_j=(s) , i=(s)+ONIKA_CU_THREAD_IDX ; _onika_j<(e) ; _onika_j+=ONIKA_CU_BLOCK_SIZE, i+=ONIKA_CU_BLOCK_SIZE )
 
-#  define ONIKA_CU_BLOCK_SYNC()        __syncthreads()
-#  define ONIKA_CU_BLOCK_SYNC_OR(p)    __syncthreads_or(p)
-#  define ONIKA_CU_BLOCK_SYNC_AND(p)   __syncthreads_and(p)
+#  define ONIKA_CU_BLOCK_SYNC()        ::onika::cuda::block_sync()
+#  define ONIKA_CU_BLOCK_SYNC_OR(p)    ::onika::cuda::block_sync_or(p)
+#  define ONIKA_CU_BLOCK_SYNC_AND(p)   ::onika::cuda::block_sync_and(p)
 #  define ONIKA_CU_BLOCK_FENCE()       __threadfence_block()
 #  define ONIKA_CU_DEVICE_FENCE()      __threadfence()
 #  define ONIKA_CU_SYSTEM_FENCE()      __threadfence_system()

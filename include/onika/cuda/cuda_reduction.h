@@ -21,8 +21,21 @@ namespace onika { namespace cuda {
     ONIKA_HOST_DEVICE_FUNC static inline T block_reduce(const T& x)
     {
 #     if defined(__CUDA_ARCH__)
-      static_assert( BlockSize % 32 == 0 && BlockSize <= 1024 , "block size must be a multiple of the warp size" );
       static_assert( sizeof(T) <= 8 && std::is_trivially_copyable_v<T> , "shuffle based reduction needs a <= 8 byte trivially copyable type" );
+      if constexpr ( BlockSize <= 32 )
+      {
+        // a block (or a sub-block of a CTA that packs several small items) inside one warp: butterfly over its own lanes
+        // only -- no shared memory, no barrier, and the other lanes of the warp may be anywhere else in the code
+        static_assert( BlockSize >= 1 && ( BlockSize & ( BlockSize - 1 ) ) == 0 , "a block smaller than a warp must be a power of two" );
+        const unsigned int lanes = lane_group_mask( BlockSize );
+        T v = x;
+#       pragma unroll
+        for(int o=BlockSize/2;o>0;o>>=1) v = Op::apply( v , __shfl_xor_sync( lanes , v , o ) );
+        return v;
+      }
+      else
+      {
+      static_assert( BlockSize % 32 == 0 && BlockSize <= 1024 , "block size must be a multiple of the warp size" );
       constexpr int NW = BlockSize / 32;
       __shared__ alignas(8) unsigned char s_raw[ ( NW + 1 ) * sizeof(T) ];
       T* s_part = reinterpret_cast<T*>( s_raw );
@@ -45,6 +58,7 @@ namespace onika { namespace cuda {
       const T result = s_part[NW];
       __syncthreads();                                       // s_raw may be reused by the next call
       return result;
+      }
 #     else
       return x;
 #     endif

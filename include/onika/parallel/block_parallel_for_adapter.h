@@ -4,6 +4,12 @@
 //   * bpf_items_kernel      persistent item loop: grid = min(N, occupancy x 148 SMs), CTA b runs items b, b+grid, ...
 //                           (no 2M-block launches for cell-sized items; one barrier between items keeps functors that
 //                           use block-shared scratch correct)
+//   * bpf_sub_items_kernel  "sub-block items": for functors whose traits declare SubBlockItems and whose block is <= 32 threads
+//                           (opts.max_block_size), a CTA of 256 threads holds 256/bs independent sub-blocks, each running the
+//                           item loop on its own -- a cell of ~16 particles occupies 16 lanes instead of a 128-thread block,
+//                           and an SM keeps 2048/bs items in flight instead of 16-32.  The ONIKA_CU_* block vocabulary means
+//                           the sub-block inside such a CTA (include/onika/cuda/cuda.h), so functor sources do not change;
+//                           opt-in because function-scope ONIKA_CU_BLOCK_SHARED variables would be shared by the sub-blocks.
 //   * bpf_box_kernel        same for 2D/3D boxes: items are box coordinates, first coordinate fastest
 //   * bpf_worksteal_kernel  fixed grid + atomic ticket (opts.fixed_gpu_grid_size), 1D only, as in the reference
 // Kernels live in the plugin's translation unit (device code for user functors never enters the runtime library);
@@ -42,6 +48,21 @@ namespace onika { namespace parallel {
         if constexpr ( ! Indexed ) func( start + ssize_t(i) );
         else func( idx[ start + ssize_t(i) ] );
         if( i + gridDim.x < n ) __syncthreads();
+      }
+    }
+
+    // CTA = blockDim.y sub-blocks of blockDim.x <= 32 threads; sub-block w of W runs items w, w+W, ... (neighbouring lanes of
+    // a warp work on neighbouring items: their index / offset loads share cache lines)
+    template<bool Indexed, class ElementListT, class FuncT>
+    __global__ void __launch_bounds__(256)
+    bpf_sub_items_kernel( const ElementListT idx , __grid_constant__ const FuncT func , const ssize_t start , const unsigned long long n )
+    {
+      const unsigned long long W = (unsigned long long) gridDim.x * blockDim.y;
+      for(unsigned long long i = (unsigned long long) blockIdx.x * blockDim.y + threadIdx.y; i < n; i += W)
+      {
+        if constexpr ( ! Indexed ) func( start + ssize_t(i) );
+        else func( idx[ start + ssize_t(i) ] );
+        ONIKA_CU_BLOCK_SYNC();
       }
     }
 
@@ -99,13 +120,13 @@ namespace onika { namespace parallel {
     }
 
     template<class KernelT>
-    inline void launch( KernelT kernel , unsigned int grid , onikaDim3_t block , int lane , void** args )
+    inline void launch( KernelT kernel , unsigned int grid , onikaDim3_t block , int lane , void** args , int flags = 0 )
     {
       static thread_local KernelT s_kernel = nullptr;
       static thread_local cudaFunction_t s_func = nullptr;
       if( s_kernel != kernel ) { ONIKA_CU_CHECK_ERRORS( cudaGetFuncBySymbol( & s_func , (const void*) kernel ) ); s_kernel = kernel; }
       const unsigned g[3] = { grid , 1 , 1 } , b[3] = { block.x , block.y , block.z };
-      ONIKA_B200_CHECK( onk_launch( (void*) s_func , g , b , 0 , lane , args ) );
+      ONIKA_B200_CHECK( onk_launch_ex( (void*) s_func , g , b , 0 , lane , args , flags ) );
     }
   }
 #endif
@@ -193,9 +214,25 @@ namespace onika { namespace parallel {
           }
           else
           {
-            auto kernel = b200::bpf_items_kernel<(ElemND>=1),ElementListT,FuncT>;
-            void* args[] = { &elements , (void*) &m_func , &start , &n };
-            b200::launch( kernel , b200::persistent_grid( kernel , threads , n , sms ) , pec->m_block_size , pec->m_lane , args );
+            bool packed = false;
+            if constexpr ( functor_sub_block_items_v<FuncT> )
+            {
+              if( threads <= 32 && ( threads & ( threads - 1 ) ) == 0 )
+              {
+                auto kernel = b200::bpf_sub_items_kernel<(ElemND>=1),ElementListT,FuncT>;
+                const onikaDim3_t cta = { threads , 256u / threads , 1 };
+                const unsigned long long nctas = ( n + cta.y - 1 ) / cta.y;
+                void* args[] = { &elements , (void*) &m_func , &start , &n };
+                b200::launch( kernel , b200::persistent_grid( kernel , 256 , nctas , sms ) , cta , pec->m_lane , args , ONK_LAUNCH_SUB_BLOCKS );
+                packed = true;
+              }
+            }
+            if( ! packed )
+            {
+              auto kernel = b200::bpf_items_kernel<(ElemND>=1),ElementListT,FuncT>;
+              void* args[] = { &elements , (void*) &m_func , &start , &n };
+              b200::launch( kernel , b200::persistent_grid( kernel , threads , n , sms ) , pec->m_block_size , pec->m_lane , args );
+            }
           }
         }
         else

@@ -12,6 +12,14 @@ namespace onika { namespace parallel {
   // specialise with CudaCompatible = true for functors whose call operator may run on the device
   template<class FuncT> struct BlockParallelForFunctorTraits { static inline constexpr bool CudaCompatible = false; };
 
+  // optional member of a traits specialisation: `static inline constexpr bool SubBlockItems = true;` lets the runtime pack
+  // several small items into one CTA (block_parallel_for_adapter.h, bpf_sub_items_kernel) when the operation's block size is
+  // <= 32 threads.  Declare it for functors that keep no function-scope ONIKA_CU_BLOCK_SHARED state and synchronise only
+  // through the ONIKA_CU_* vocabulary.
+  template<class FuncT> static inline constexpr bool functor_sub_block_items_v = []{
+      if constexpr ( requires { BlockParallelForFunctorTraits<FuncT>::SubBlockItems; } ) return bool( BlockParallelForFunctorTraits<FuncT>::SubBlockItems );
+      else return false; }();
+
   template<class FuncT> struct FunctorNeedsGPUSupport : public
 # if defined(__CUDACC__)
     std::integral_constant<bool,BlockParallelForFunctorTraits<FuncT>::CudaCompatible>

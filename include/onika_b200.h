@@ -120,6 +120,12 @@ int onk_op_elapsed_ms(onk_op* op, float* ms);                /* valid after the 
  *                        (cudaGetFuncBySymbol in the plugin's translation unit), so device code for user functors
  *                        stays in the plugin, as in the reference. */
 int onk_launch(void* cu_function, const unsigned grid[3], const unsigned block[3], size_t shared_bytes, int lane, void** args);
+/* the same with launch flags.  ONK_LAUNCH_SUB_BLOCKS: the CTA is block[0] x block[1] threads and holds block[1] independent
+ * sub-blocks of block[0] threads, each standing for one "block" of the reference's one-block-per-item launch
+ * (block_parallel_for_adapter.h:81-93); the kernel is launched as an explicit 1-CTA cluster, which is how device code
+ * (the ONIKA_CU_* vocabulary, include/onika/cuda/cuda.h) tells the two kinds of CTA apart. */
+#define ONK_LAUNCH_SUB_BLOCKS      1
+int onk_launch_ex(void* cu_function, const unsigned grid[3], const unsigned block[3], size_t shared_bytes, int lane, void** args, int flags);
 int onk_launch_count(uint64_t* n);          /* kernels launched by this library since onk_init (all entry points) */
 
 /* lane sequence capture  CUDA-graph capture of everything queued on a set of lanes between begin and end
@@ -148,14 +154,17 @@ int onk_combine_f64(int op, const double* partials_dev, uint32_t count, double* 
 /* ---- fused reduction + cross-GPU combine over NVLink peer memory ----
  * The counterpart of "reduce locally, then mpi::all_reduce_multi" (include/onika/mpi/all_reduce_multi.h:30-37) as ONE
  * kernel per rank: the last CTA of the local reduction stores its partial into every peer's exchange buffer (peer
- * stores over NVLink/NVSwitch), publishes it with a release flag, waits for the peers' flags and folds the `world`
- * partials in RANK ORDER -- every rank gets the same bits, sums are reproducible, no collective library call.
+ * stores over NVLink/NVSwitch) as a flagged 16-byte packet (payload and call epoch in the same words: no fences), polls its
+ * own buffer for the peers' packets and folds the `world` partials in RANK ORDER -- every rank gets the same bits, sums are
+ * reproducible, no collective library call.
  * Exchange buffers are ONK_XCHG_BYTES of device memory per rank (onk_xchg_create), shared between the processes of one
  * node through CUDA IPC: export the local handle, all-gather the handles with any host-side transport, open the peers.
- * All ranks must issue the same sequence of calls on an exchange (reductions, all-reduces, barriers: the call count is the
- * flag epoch), and all calls on one exchange must go to the same lane (they complete in issue order); use one exchange per
- * lane for independent sequences. */
-#define ONK_XCHG_BYTES      4096
+ * All ranks must issue the same sequence of calls on an exchange (reductions, all-reduces, barriers: the call count, kept
+ * on the device, is the packet epoch, so a captured lane sequence can be replayed), and all calls on one exchange must go
+ * to the same lane (they complete in issue order); use one exchange per lane for independent sequences.
+ * A peer that does not show up within ~10 s makes the call's results NaN and the exchange unusable: onk_xchg_status
+ * reports the failed call once the lane was synchronised, every later call on the exchange returns ONK_ERR_STATE. */
+#define ONK_XCHG_BYTES      8192
 #define ONK_XCHG_MAX_WORLD    16
 #define ONK_XCHG_MAX_VALUES    8
 #define ONK_IPC_HANDLE_BYTES  64
@@ -170,6 +179,7 @@ int onk_reduce_xchg_f64(int op, const double* in_dev, uint64_t n, double* out_de
  * per rank, no collective library call.  Collective, counts as one epoch. */
 int onk_xchg_allreduce_f64(onk_xchg* x, int op, double* values_dev, int count, int lane);
 int onk_xchg_info(onk_xchg* x, int* rank, int* world);
+int onk_xchg_status(onk_xchg* x, uint64_t* failed_call);   /* 0 = healthy; else the 1-based call in which a peer timed out */
 /* device-side barrier between the ranks' lanes (same flag exchange, no payload): what every rank queued on `lane` before
  * it, peer stores included, is complete and visible once it has passed on any rank.  Collective, counts as one epoch. */
 int onk_xchg_barrier(onk_xchg* x, int lane);

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "onk_op_end": (i32, [vp, vp, sz, vp, vp]),
     "onk_op_elapsed_ms": (i32, [vp, P(C.c_float)]),
     "onk_launch": (i32, [vp, P(C.c_uint), P(C.c_uint), sz, i32, P(vp)]),
+    "onk_launch_ex": (i32, [vp, P(C.c_uint), P(C.c_uint), sz, i32, P(vp), i32]),
     "onk_launch_count": (i32, [P(u64)]),
     "onk_graph_begin": (i32, [i32, P(i32), i32]),
     "onk_graph_end": (i32, [P(vp)]),
@@ -65,6 +66,7 @@ PROTOTYPES = {
     "onk_xchg_allreduce_f64": (i32, [vp, i32, vp, i32, i32]),
     "onk_xchg_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
     "onk_xchg_barrier": (i32, [vp, i32]),
+    "onk_xchg_status": (i32, [vp, P(u64)]),
     "onk_window_create": (i32, [C.c_size_t, i32, i32, C.POINTER(vp)]),
     "onk_window_export": (i32, [vp, C.c_char_p]),
     "onk_window_connect": (i32, [vp, C.c_char_p]),

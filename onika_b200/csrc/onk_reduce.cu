@@ -21,58 +21,95 @@ namespace onk
   constexpr unsigned RED_CTAS_PER_SM = 4;
 
   // ---- cross-GPU exchange (fused into the finish of the reduction kernel) ----
-  // one buffer per rank, mapped into every peer process: [parity][rank] values and epoch flags
+  // One buffer per rank, mapped into every peer process.  Values travel in FLAGGED PACKETS (the "LL" idea of collective
+  // libraries): a double is sent as two 8-byte words, each carrying 32 payload bits and the 32-bit call epoch, written with
+  // one 16-byte peer store.  An 8-byte word is never torn, so a reader that sees the epoch in both words holds the value:
+  // no release fence on the producer, no acquire on the consumer, one NVLink round per exchange.  The epoch is a call
+  // counter kept in the rank's own buffer (device-resident, so a captured CUDA graph replays correctly) and slots are
+  // double-buffered by its parity: a rank can be at most one call ahead of the slowest peer.
+  struct alignas(16) XchgPacket { unsigned long long lo, hi; };
   struct XchgBuffer
   {
-    double             val[2][ONK_XCHG_MAX_WORLD][ONK_XCHG_MAX_VALUES];   // [parity][source rank][value]
-    unsigned long long flag[2][ONK_XCHG_MAX_WORLD];
-    unsigned long long error;                      // set when a peer did not show up in time
+    XchgPacket         slot[2][ONK_XCHG_MAX_WORLD][ONK_XCHG_MAX_VALUES];   // [parity][source rank][value]
+    unsigned long long epoch;                      // calls completed on this exchange (only this rank's kernels touch it)
   };
   static_assert(sizeof(XchgBuffer) <= ONK_XCHG_BYTES, "exchange buffer layout");
   struct XchgParams
   {
     XchgBuffer* peer[ONK_XCHG_MAX_WORLD];          // peer[r] = rank r's buffer as seen from this device (peer[rank] is local)
+    unsigned long long* error_host;                // mapped pinned word: epoch of the first call in which a peer did not show up
     int rank, world;
-    unsigned long long epoch;                      // strictly increasing, identical on all ranks for matching calls
   };
 
-  __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
-  { asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
-  __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
-  { unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+  constexpr long long XCHG_TIMEOUT_CLOCKS = 20000000000ll;          // ~10 s: a peer is missing; fail instead of hanging the device
 
-  // called by the last CTA with the rank-local result in thread 0; returns the global result in thread 0
+  __device__ __forceinline__ void xchg_send(XchgPacket* dst, double v, unsigned epoch32)
+  {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), e = (unsigned long long)epoch32 << 32;
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" :: "l"(dst), "l"((b & 0xffffffffull) | e), "l"((b >> 32) | e) : "memory");
+  }
+  // spins without backing off first (the peers are usually a few microseconds apart), then sleeps between polls
+  __device__ __forceinline__ bool xchg_recv(const XchgPacket* src, unsigned epoch32, double* v)
+  {
+    unsigned long long lo, hi;
+    long long t0 = 0;
+    for (unsigned spins = 0;; spins++)
+    {
+      asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+      if ((unsigned)(lo >> 32) == epoch32 && (unsigned)(hi >> 32) == epoch32) break;
+      if (spins == 2048u) t0 = clock64();
+      if (spins > 2048u)
+      {
+        __nanosleep(128);
+        if (clock64() - t0 > XCHG_TIMEOUT_CLOCKS) { *v = __longlong_as_double(0x7ff8000000000000ll); return false; }
+      }
+    }
+    *v = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+    return true;
+  }
+  __device__ __forceinline__ void xchg_fail(const XchgParams& xp, unsigned long long epoch)
+  {
+    if (*reinterpret_cast<volatile unsigned long long*>(xp.error_host) == 0ull) *reinterpret_cast<volatile unsigned long long*>(xp.error_host) = epoch;
+    __threadfence_system();
+  }
+  // next epoch of this rank's exchange; call from ONE thread
+  __device__ __forceinline__ unsigned long long xchg_next_epoch(const XchgParams& xp)
+  {
+    XchgBuffer* mine = xp.peer[xp.rank];
+    const unsigned long long e = mine->epoch + 1ull;
+    mine->epoch = e;
+    return e;
+  }
+
+  // called by ONE CTA with the rank-local result in thread 0; returns the global result in thread 0.  A peer that does not
+  // show up makes the result NaN for every operator and records the epoch in the exchange's host-visible error word.
   template<int OP>
   __device__ __forceinline__ double xchg_combine(double local, const XchgParams& xp)
   {
     using R = Red<OP>;
     __shared__ double s_local;
+    __shared__ unsigned long long s_epoch;
     __shared__ double s_vals[ONK_XCHG_MAX_WORLD];
-    if (threadIdx.x == 0) s_local = local;
+    __shared__ int s_failed;
+    if (threadIdx.x == 0) { s_local = local; s_epoch = xchg_next_epoch(xp); s_failed = 0; }
     __syncthreads();
-    const int par = (int)(xp.epoch & 1ull);
+    const unsigned long long epoch = s_epoch;
+    const int par = (int)(epoch & 1ull);
     if ((int)threadIdx.x < xp.world)
     {
       const int peer = (int)threadIdx.x;
-      // publish: value first, then the flag with release semantics at system scope (peer stores travel over NVLink)
-      XchgBuffer* pb = xp.peer[peer];
-      *reinterpret_cast<volatile double*>(&pb->val[par][xp.rank][0]) = s_local;
-      st_release_sys(&pb->flag[par][xp.rank], xp.epoch);
-      // gather: wait for rank `peer`'s flag in MY buffer
-      XchgBuffer* mine = xp.peer[xp.rank];
-      const long long t0 = clock64();
-      bool ok = true;
-      while (ld_acquire_sys(&mine->flag[par][peer]) < xp.epoch)
-      {
-        if (clock64() - t0 > 20000000000ll) { ok = false; break; }        // ~10 s: a peer is missing; do not hang the device
-        __nanosleep(64);
-      }
-      s_vals[peer] = ok ? *reinterpret_cast<volatile double*>(&mine->val[par][peer][0]) : __longlong_as_double(0x7ff8000000000000ll);
-      if (!ok) mine->error = xp.epoch;
+      xchg_send(&xp.peer[peer]->slot[par][xp.rank][0], s_local, (unsigned)epoch);            // my value into rank `peer`'s buffer
+      double v;
+      if (!xchg_recv(&xp.peer[xp.rank]->slot[par][peer][0], (unsigned)epoch, &v)) { s_failed = 1; xchg_fail(xp, epoch); }
+      s_vals[peer] = v;
     }
     __syncthreads();
     double r = R::identity();
-    if (threadIdx.x == 0) for (int i = 0; i < xp.world; i++) r = R::apply(r, s_vals[i]);     // rank order
+    if (threadIdx.x == 0)
+    {
+      for (int i = 0; i < xp.world; i++) r = R::apply(r, s_vals[i]);                          // rank order
+      if (s_failed) r = __longlong_as_double(0x7ff8000000000000ll);
+    }
     return r;
   }
 
@@ -291,47 +328,45 @@ using namespace onk;
 
 namespace onk
 {
-  // device-side barrier between the ranks' lanes: everything queued before it on every rank's lane (peer stores
-  // included: a kernel's writes are performed before a later kernel of the same stream publishes its release flag)
-  // is complete and visible when it returns on any rank
   // all-reduce of `count` <= ONK_XCHG_MAX_VALUES doubles held by every rank, in place, same operator for all values:
-  // thread p publishes this rank's values into rank p's buffer and waits for rank p's; values are folded in rank order
+  // thread (p,k) sends this rank's value k into rank p's buffer and receives rank p's value k; values are folded in rank order
   template<int OP>
-  __global__ void xchg_allreduce_kernel(double* __restrict__ values, int count, const __grid_constant__ XchgParams xp)
+  __global__ void __launch_bounds__(ONK_XCHG_MAX_WORLD * ONK_XCHG_MAX_VALUES)
+  xchg_allreduce_kernel(double* __restrict__ values, int count, const __grid_constant__ XchgParams xp)
   {
     using R = Red<OP>;
     __shared__ double s_vals[ONK_XCHG_MAX_WORLD][ONK_XCHG_MAX_VALUES];
-    const int par = (int)(xp.epoch & 1ull);
-    if ((int)threadIdx.x < xp.world)
+    __shared__ unsigned long long s_epoch;
+    __shared__ int s_failed;
+    if (threadIdx.x == 0) { s_epoch = xchg_next_epoch(xp); s_failed = 0; }
+    __syncthreads();
+    const unsigned long long epoch = s_epoch;
+    const int par = (int)(epoch & 1ull);
+    const int peer = (int)threadIdx.x / ONK_XCHG_MAX_VALUES, k = (int)threadIdx.x % ONK_XCHG_MAX_VALUES;
+    if (peer < xp.world && k < count)
     {
-      const int peer = (int)threadIdx.x;
-      XchgBuffer* pb = xp.peer[peer];
-      for (int k = 0; k < count; k++) *reinterpret_cast<volatile double*>(&pb->val[par][xp.rank][k]) = values[k];
-      st_release_sys(&pb->flag[par][xp.rank], xp.epoch);
-      XchgBuffer* mine = xp.peer[xp.rank];
-      const long long t0 = clock64();
-      bool ok = true;
-      while (ld_acquire_sys(&mine->flag[par][peer]) < xp.epoch)
-      {
-        if (clock64() - t0 > 20000000000ll) { ok = false; break; }
-        __nanosleep(64);
-      }
-      for (int k = 0; k < count; k++)
-        s_vals[peer][k] = ok ? *reinterpret_cast<volatile double*>(&mine->val[par][peer][k]) : __longlong_as_double(0x7ff8000000000000ll);
-      if (!ok) mine->error = xp.epoch;
+      xchg_send(&xp.peer[peer]->slot[par][xp.rank][k], values[k], (unsigned)epoch);
+      double v;
+      if (!xchg_recv(&xp.peer[xp.rank]->slot[par][peer][k], (unsigned)epoch, &v)) { s_failed = 1; xchg_fail(xp, epoch); }
+      s_vals[peer][k] = v;
     }
     __syncthreads();
     if ((int)threadIdx.x < count)
     {
       double r = R::identity();
       for (int p = 0; p < xp.world; p++) r = R::apply(r, s_vals[p][threadIdx.x]);
-      values[threadIdx.x] = r;
+      values[threadIdx.x] = s_failed ? __longlong_as_double(0x7ff8000000000000ll) : r;
     }
   }
 
+  // device-side barrier between the ranks' lanes: everything queued before it on every rank's lane, peer stores included, is
+  // complete and visible when it returns on any rank.  The earlier kernels of the lane have completed when this one starts;
+  // the system-scope fences order their (peer) writes before the packet and the packet before what follows.
   __global__ void xchg_barrier_kernel(const __grid_constant__ XchgParams xp)
   {
+    __threadfence_system();
     (void) xchg_combine<ONK_OP_MIN>(0.0, xp);
+    __threadfence_system();
   }
 }
 
@@ -341,7 +376,20 @@ struct onk_xchg
   XchgParams  params{};
   bool        connected = false;
   void*       opened[ONK_XCHG_MAX_WORLD] = {};
+  unsigned long long* error_host = nullptr;      // pinned + mapped: written by the kernels on a timeout, read by the host
 };
+
+namespace onk
+{
+  // sticky failure: once a peer did not show up in a call, every later call on the exchange is refused
+  static int xchg_usable(onk_xchg* x, const char* who)
+  {
+    if (x == nullptr || !x->connected) { set_error("%s: exchange is not connected", who); return ONK_ERR_ARG; }
+    const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(x->error_host);
+    if (e != 0ull) { set_error("%s: the exchange failed in call %llu (a peer rank did not show up within the timeout)", who, e); return ONK_ERR_STATE; }
+    return ONK_OK;
+  }
+}
 
 extern "C" {
 
@@ -353,9 +401,12 @@ int onk_xchg_create(int rank, int world, onk_xchg** x)
   onk_xchg* h = new onk_xchg();
   cudaError_t e = cudaMalloc((void**)&h->local, ONK_XCHG_BYTES);      // plain cudaMalloc: exportable through CUDA IPC
   if (e == cudaSuccess) e = cudaMemset(h->local, 0, ONK_XCHG_BYTES);
-  if (e != cudaSuccess) { delete h; ONK_CUDA(e); }
-  h->params.rank = rank; h->params.world = world; h->params.epoch = 0;
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->error_host, 64, cudaHostAllocMapped | cudaHostAllocPortable);
+  if (e != cudaSuccess) { if (h->local) cudaFree(h->local); delete h; ONK_CUDA(e); }
+  *h->error_host = 0ull;
+  h->params.rank = rank; h->params.world = world;
   h->params.peer[rank] = h->local;
+  h->params.error_host = h->error_host;          // unified addressing: the mapped host pointer is valid on the device
   h->connected = (world == 1);
   *x = h;
   return ONK_OK;
@@ -394,7 +445,15 @@ int onk_xchg_destroy(onk_xchg* x)
   cudaDeviceSynchronize();
   for (int r = 0; r < ONK_XCHG_MAX_WORLD; r++) if (x->opened[r]) cudaIpcCloseMemHandle(x->opened[r]);
   if (x->local) cudaFree(x->local);
+  if (x->error_host) cudaFreeHost(x->error_host);
   delete x;
+  return ONK_OK;
+}
+
+int onk_xchg_status(onk_xchg* x, uint64_t* failed_call)
+{
+  ONK_REQUIRE(x != nullptr && failed_call != nullptr, "onk_xchg_status: null argument");
+  *failed_call = *reinterpret_cast<volatile unsigned long long*>(x->error_host);
   return ONK_OK;
 }
 
@@ -408,9 +467,8 @@ int onk_xchg_info(onk_xchg* x, int* rank, int* world)
 
 int onk_xchg_barrier(onk_xchg* x, int lane)
 {
-  ONK_REQUIRE(x != nullptr && x->connected, "onk_xchg_barrier: exchange is not connected");
+  if (int rc = xchg_usable(x, "onk_xchg_barrier")) return rc;
   Lane* L; if (int rc = lane_get(lane, &L)) return rc;
-  x->params.epoch += 1;
   xchg_barrier_kernel<<<1, 32, 0, L->stream>>>(x->params);
   ONK_CHECK_LAUNCH();
   count_launch();
@@ -419,16 +477,16 @@ int onk_xchg_barrier(onk_xchg* x, int lane)
 
 int onk_xchg_allreduce_f64(onk_xchg* x, int op, double* values_dev, int count, int lane)
 {
-  ONK_REQUIRE(x != nullptr && x->connected, "onk_xchg_allreduce_f64: exchange is not connected");
+  if (int rc = xchg_usable(x, "onk_xchg_allreduce_f64")) return rc;
   ONK_REQUIRE(values_dev != nullptr && count >= 1 && count <= ONK_XCHG_MAX_VALUES, "onk_xchg_allreduce_f64: 1..%d values", ONK_XCHG_MAX_VALUES);
   ONK_REQUIRE(op == ONK_OP_MIN || op == ONK_OP_MAX || op == ONK_OP_SUM, "onk_xchg_allreduce_f64: unknown op %d", op);
   Lane* L; if (int rc = lane_get(lane, &L)) return rc;
-  x->params.epoch += 1;
+  constexpr unsigned T = ONK_XCHG_MAX_WORLD * ONK_XCHG_MAX_VALUES;
   switch (op)
   {
-    case ONK_OP_MIN: xchg_allreduce_kernel<ONK_OP_MIN><<<1, 32, 0, L->stream>>>(values_dev, count, x->params); break;
-    case ONK_OP_MAX: xchg_allreduce_kernel<ONK_OP_MAX><<<1, 32, 0, L->stream>>>(values_dev, count, x->params); break;
-    default:         xchg_allreduce_kernel<ONK_OP_SUM><<<1, 32, 0, L->stream>>>(values_dev, count, x->params); break;
+    case ONK_OP_MIN: xchg_allreduce_kernel<ONK_OP_MIN><<<1, T, 0, L->stream>>>(values_dev, count, x->params); break;
+    case ONK_OP_MAX: xchg_allreduce_kernel<ONK_OP_MAX><<<1, T, 0, L->stream>>>(values_dev, count, x->params); break;
+    default:         xchg_allreduce_kernel<ONK_OP_SUM><<<1, T, 0, L->stream>>>(values_dev, count, x->params); break;
   }
   ONK_CHECK_LAUNCH();
   count_launch();
@@ -437,12 +495,11 @@ int onk_xchg_allreduce_f64(onk_xchg* x, int op, double* values_dev, int count, i
 
 int onk_reduce_xchg_f64(int op, const double* in_dev, uint64_t n, double* out_dev, onk_xchg* x, int lane)
 {
-  ONK_REQUIRE(x != nullptr && x->connected, "onk_reduce_xchg_f64: exchange is not connected");
+  if (int rc = xchg_usable(x, "onk_reduce_xchg_f64")) return rc;
   ONK_REQUIRE(out_dev != nullptr && (n == 0 || in_dev != nullptr), "onk_reduce_xchg_f64: null pointer");
   ONK_REQUIRE(((uintptr_t)in_dev & 7) == 0, "onk_reduce_xchg_f64: input is not 8-byte aligned");
   ONK_REQUIRE(op == ONK_OP_MIN || op == ONK_OP_MAX || op == ONK_OP_SUM, "onk_reduce_xchg_f64: unknown op %d", op);
   Lane* L; if (int rc = lane_get(lane, &L)) return rc;
-  x->params.epoch += 1;
   switch (op)
   {
     case ONK_OP_MIN: return launch_reduce<ONK_OP_MIN>(in_dev, n, out_dev, L, &x->params);

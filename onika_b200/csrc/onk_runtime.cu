@@ -56,10 +56,20 @@ namespace onk
     }
     if (L.ws.partials == nullptr)
     {
-      ONK_CUDA(cudaMalloc(&L.ws.partials, sizeof(double) * MAX_PARTIALS));
-      ONK_CUDA(cudaMalloc(&L.ws.ticket, 256));
-      ONK_CUDA(cudaMemset(L.ws.ticket, 0, 256));
-      ONK_CUDA(cudaMalloc(&L.ws.result, 256));
+      // all or nothing: a half-built workspace must never be seen by a later call
+      LaneWorkspace w;
+      cudaError_t e = cudaMalloc(&w.partials, sizeof(double) * MAX_PARTIALS);
+      if (e == cudaSuccess) e = cudaMalloc(&w.ticket, 256);
+      if (e == cudaSuccess) e = cudaMemset(w.ticket, 0, 256);
+      if (e == cudaSuccess) e = cudaMalloc(&w.result, 256);
+      if (e != cudaSuccess)
+      {
+        if (w.partials) cudaFree(w.partials);
+        if (w.ticket) cudaFree(w.ticket);
+        if (w.result) cudaFree(w.result);
+        ONK_CUDA(e);
+      }
+      L.ws = w;
     }
     *out = &L;
     return ONK_OK;
@@ -415,27 +425,48 @@ int onk_op_elapsed_ms(onk_op* op, float* ms)
 
 /* ---------------------------------------------- generic launch ---------------------------------------------- */
 
-typedef CUresult (*cuLaunchKernel_t)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**);
+typedef CUresult (*cuLaunchKernelEx_t)(const CUlaunchConfig*, CUfunction, void**, void**);
 
-int onk_launch(void* cu_function, const unsigned grid[3], const unsigned block[3], size_t shared_bytes, int lane, void** args)
+int onk_launch_ex(void* cu_function, const unsigned grid[3], const unsigned block[3], size_t shared_bytes, int lane, void** args, int flags)
 {
   ONK_REQUIRE(cu_function != nullptr && grid != nullptr && block != nullptr, "onk_launch: null argument");
+  ONK_REQUIRE((flags & ~ONK_LAUNCH_SUB_BLOCKS) == 0, "onk_launch_ex: unknown flags %d", flags);
   Lane* L; if (int rc = lane_get(lane, &L)) return rc;
   if ((uint64_t)grid[0] * grid[1] * grid[2] == 0) return ONK_OK;   // empty execution space: nothing to run
-  static cuLaunchKernel_t launch = nullptr;
+  static std::atomic<cuLaunchKernelEx_t> s_launch{nullptr};
+  cuLaunchKernelEx_t launch = s_launch.load(std::memory_order_acquire);
   if (!launch)
   {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
-    ONK_CUDA(cudaGetDriverEntryPoint("cuLaunchKernel", &fn, cudaEnableDefault, &q));
-    if (!fn) { set_error("onk_launch: cuLaunchKernel entry point not found"); return ONK_ERR_CUDA; }
-    launch = (cuLaunchKernel_t)fn;
+    ONK_CUDA(cudaGetDriverEntryPoint("cuLaunchKernelEx", &fn, cudaEnableDefault, &q));
+    if (!fn) { set_error("onk_launch: cuLaunchKernelEx entry point not found"); return ONK_ERR_CUDA; }
+    launch = (cuLaunchKernelEx_t)fn;
+    s_launch.store(launch, std::memory_order_release);
   }
-  CUresult r = launch((CUfunction)cu_function, grid[0], grid[1], grid[2], block[0], block[1], block[2],
-                      (unsigned)shared_bytes, (CUstream)L->stream, args, nullptr);
-  if (r != CUDA_SUCCESS) { set_error("onk_launch: cuLaunchKernel failed with CUresult %d", (int)r); return ONK_ERR_CUDA; }
+  CUlaunchConfig cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDimX = grid[0]; cfg.gridDimY = grid[1]; cfg.gridDimZ = grid[2];
+  cfg.blockDimX = block[0]; cfg.blockDimY = block[1]; cfg.blockDimZ = block[2];
+  cfg.sharedMemBytes = (unsigned)shared_bytes;
+  cfg.hStream = (CUstream)L->stream;
+  CUlaunchAttribute attr[1];
+  if (flags & ONK_LAUNCH_SUB_BLOCKS)
+  {
+    // explicit cluster of one CTA: %is_explicit_cluster is how the ONIKA_CU_* macros recognise a CTA of sub-blocks
+    attr[0].id = CU_LAUNCH_ATTRIBUTE_CLUSTER_DIMENSION;
+    attr[0].value.clusterDim.x = 1; attr[0].value.clusterDim.y = 1; attr[0].value.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  CUresult r = launch(&cfg, (CUfunction)cu_function, args, nullptr);
+  if (r != CUDA_SUCCESS) { set_error("onk_launch: cuLaunchKernelEx failed with CUresult %d", (int)r); return ONK_ERR_CUDA; }
   count_launch();
   return ONK_OK;
+}
+
+int onk_launch(void* cu_function, const unsigned grid[3], const unsigned block[3], size_t shared_bytes, int lane, void** args)
+{
+  return onk_launch_ex(cu_function, grid, block, shared_bytes, lane, args, 0);
 }
 
 int onk_launch_count(uint64_t* n)
@@ -449,43 +480,58 @@ int onk_launch_count(uint64_t* n)
 
 struct onk_graph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; };
 
-static struct { bool active = false; cudaStream_t origin = nullptr; std::vector<cudaStream_t> others; uint64_t launches0 = 0; } g_capture;
+static struct { bool active = false; cudaStream_t origin = nullptr; std::vector<cudaStream_t> others; uint64_t launches0 = 0; } g_capture;   // guarded by rt().mutex
+
+// leaves every lane of a failed capture out of capture mode and forgets it
+static void capture_abort(cudaStream_t origin)
+{
+  cudaGraph_t g = nullptr;
+  cudaStreamEndCapture(origin, &g);             // invalidates the capture on all forked streams as well
+  if (g) cudaGraphDestroy(g);
+  cudaGetLastError();
+  g_capture.active = false; g_capture.origin = nullptr; g_capture.others.clear();
+}
 
 int onk_graph_begin(int origin_lane, const int* other_lanes, int n_other)
 {
-  ONK_REQUIRE(!g_capture.active, "onk_graph_begin: a capture is already active");
   ONK_REQUIRE(n_other == 0 || other_lanes != nullptr, "onk_graph_begin: null lane list");
   Lane* O; if (int rc = lane_get(origin_lane, &O)) return rc;
   ONK_REQUIRE(O->stream != nullptr && O->stream != cudaStreamLegacy,
               "onk_graph_begin: lane %d runs on the legacy default stream, which cannot be captured", origin_lane);
   std::vector<cudaStream_t> others;
   for (int i = 0; i < n_other; i++) { Lane* L; if (int rc = lane_get(other_lanes[i], &L)) return rc; if (L->stream != O->stream) others.push_back(L->stream); }
+  std::lock_guard<std::mutex> lk(rt().mutex);
+  ONK_REQUIRE(!g_capture.active, "onk_graph_begin: a capture is already active");
   ONK_CUDA(cudaStreamBeginCapture(O->stream, cudaStreamCaptureModeThreadLocal));
   // fork: every other lane joins the capture by waiting on an event recorded in the origin lane
-  cudaEvent_t fork;
-  ONK_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-  ONK_CUDA(cudaEventRecord(fork, O->stream));
-  for (cudaStream_t s : others) ONK_CUDA(cudaStreamWaitEvent(s, fork, 0));
-  ONK_CUDA(cudaEventDestroy(fork));
+  cudaEvent_t fork = nullptr;
+  cudaError_t e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventRecord(fork, O->stream);
+  for (size_t i = 0; e == cudaSuccess && i < others.size(); i++) e = cudaStreamWaitEvent(others[i], fork, 0);
+  if (fork) cudaEventDestroy(fork);
+  if (e != cudaSuccess) { capture_abort(O->stream); ONK_CUDA(e); }
   g_capture.active = true; g_capture.origin = O->stream; g_capture.others = others; g_capture.launches0 = rt().launches.load();
   return ONK_OK;
 }
 
 int onk_graph_end(onk_graph** graph)
 {
+  std::lock_guard<std::mutex> lk(rt().mutex);
   ONK_REQUIRE(graph != nullptr && g_capture.active, "onk_graph_end: no active capture");
-  g_capture.active = false;
   // join: the origin lane waits for every other lane
-  for (cudaStream_t s : g_capture.others)
+  cudaError_t e = cudaSuccess;
+  for (size_t i = 0; e == cudaSuccess && i < g_capture.others.size(); i++)
   {
-    cudaEvent_t j;
-    ONK_CUDA(cudaEventCreateWithFlags(&j, cudaEventDisableTiming));
-    ONK_CUDA(cudaEventRecord(j, s));
-    ONK_CUDA(cudaStreamWaitEvent(g_capture.origin, j, 0));
-    ONK_CUDA(cudaEventDestroy(j));
+    cudaEvent_t j = nullptr;
+    e = cudaEventCreateWithFlags(&j, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(j, g_capture.others[i]);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(g_capture.origin, j, 0);
+    if (j) cudaEventDestroy(j);
   }
+  if (e != cudaSuccess) { capture_abort(g_capture.origin); ONK_CUDA(e); }
   onk_graph* g = new onk_graph();
-  cudaError_t e = cudaStreamEndCapture(g_capture.origin, &g->graph);
+  e = cudaStreamEndCapture(g_capture.origin, &g->graph);
+  g_capture.active = false; g_capture.origin = nullptr; g_capture.others.clear();
   if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
   if (e != cudaSuccess) { if (g->graph) cudaGraphDestroy(g->graph); delete g; ONK_CUDA(e); }
   g->kernels = rt().launches.load() - g_capture.launches0;

@@ -17,3 +17,12 @@ TEST_DECLARE_FIELD(int32_t      , particle_mid   , "Particle molecule id")
 TEST_DECLARE_FIELD(float        , particle_dist  , "Particle pair distance")
 TEST_DECLARE_FIELD(int16_t      , particle_tmp1  , "Particle Temporary 1")
 TEST_DECLARE_FIELD(int8_t       , particle_tmp2  , "Particle Temporary 2")
+// config C3: eight fp64 fields swept by one read-modify-write operator
+TEST_DECLARE_FIELD(double       , bench_f0       , "C3 field 0")
+TEST_DECLARE_FIELD(double       , bench_f1       , "C3 field 1")
+TEST_DECLARE_FIELD(double       , bench_f2       , "C3 field 2")
+TEST_DECLARE_FIELD(double       , bench_f3       , "C3 field 3")
+TEST_DECLARE_FIELD(double       , bench_f4       , "C3 field 4")
+TEST_DECLARE_FIELD(double       , bench_f5       , "C3 field 5")
+TEST_DECLARE_FIELD(double       , bench_f6       , "C3 field 6")
+TEST_DECLARE_FIELD(double       , bench_f7       , "C3 field 7")

@@ -487,6 +487,11 @@ struct GenericCellSumFunctor
 };
 namespace onika { namespace parallel { template<int BS> struct BlockParallelForFunctorTraits< GenericCellSumFunctor<BS> > { static inline constexpr bool CudaCompatible = true; }; } }
 
+// the same functor source, declared safe for sub-block packing (no function-scope shared state): several cells per CTA
+template<int BS> struct PackedCellSumFunctor : public GenericCellSumFunctor<BS> {};
+namespace onika { namespace parallel { template<int BS> struct BlockParallelForFunctorTraits< PackedCellSumFunctor<BS> >
+  { static inline constexpr bool CudaCompatible = true; static inline constexpr bool SubBlockItems = true; }; } }
+
 static int scenario_cells_generic_perf(Out& out, size_t ncells)
 {
   std::vector<uint64_t> begin(ncells+1,0);
@@ -500,7 +505,7 @@ static int scenario_cells_generic_perf(Out& out, size_t ncells)
   auto & pq = ParallelExecutionQueue::default_queue();
   void* stream = nullptr; ONIKA_B200_CHECK( onk_lane_stream( 0 , &stream ) );
   cudaEvent_t e0, e1; ONIKA_CU_CHECK_ERRORS( cudaEventCreate(&e0) ); ONIKA_CU_CHECK_ERRORS( cudaEventCreate(&e1) );
-  double us[3] = {0,0,0};
+  double us[6] = {0,0,0,0,0,0};
   auto timeit = [&](int slot, auto make_op)
   {
     for(int i=0;i<2;i++) pq << set_lane(0) << make_op();
@@ -529,12 +534,26 @@ static int scenario_cells_generic_perf(Out& out, size_t ncells)
     ONIKA_B200_CHECK( onk_lane_sync(0) );
     float ms = 0; ONIKA_CU_CHECK_ERRORS( cudaEventElapsedTime( &ms , e0 , e1 ) ); us[2] = ms * 1e3 / 5;
   }
-  ParallelExecutionContext::s_gpu_timing = true;
   std::vector<double> rt(ncells); ONIKA_B200_CHECK( onk_memcpy( rt.data() , ps , ncells*8 , 0 ) ); ONIKA_B200_CHECK( onk_lane_sync(0) );
-  std::printf("cells_generic_perf ncells=%zu particles=%zu : generic block 128 %.1f us , generic block 32 %.1f us , typed field-major %.1f us\n", ncells, np, us[0], us[1], us[2]);
-  out.doubles( us , 3 );
+  // sub-block items: the same operator() in CTAs of 256/bs sub-blocks of bs threads
+  std::vector<double> rsub[3] = { std::vector<double>(ncells) , std::vector<double>(ncells) , std::vector<double>(ncells) };
+  auto sub = [&](int slot, auto functor, unsigned int bs)
+  {
+    ONIKA_B200_CHECK( onk_memset_bytes( ps , 0xff , ncells*8 , 0 ) );
+    BlockParallelForOptions o; o.max_block_size = bs;
+    timeit( 3+slot , [&]{ return block_parallel_for( ncells , functor , parallel_execution_context("cells","sub") , o ); } );
+    ONIKA_B200_CHECK( onk_memcpy( rsub[slot].data() , ps , ncells*8 , 0 ) ); ONIKA_B200_CHECK( onk_lane_sync(0) );
+  };
+  sub( 0 , PackedCellSumFunctor<32>{ { (const double*)pv , (const uint64_t*)pb , (double*)ps } } , 32 );
+  sub( 1 , PackedCellSumFunctor<16>{ { (const double*)pv , (const uint64_t*)pb , (double*)ps } } , 16 );
+  sub( 2 , PackedCellSumFunctor<8>{ { (const double*)pv , (const uint64_t*)pb , (double*)ps } } , 8 );
+  ParallelExecutionContext::s_gpu_timing = true;
+  std::printf("cells_generic_perf ncells=%zu particles=%zu : generic block 128 %.1f us , generic block 32 %.1f us , typed field-major %.1f us , sub-block items 32/16/8 threads %.1f / %.1f / %.1f us\n",
+              ncells, np, us[0], us[1], us[2], us[3], us[4], us[5]);
+  out.doubles( us , 6 );
   out.doubles( rt.data() , ncells );            // in-order sums (typed kernel): the reference result
   out.doubles( r128.data() , ncells ); out.doubles( r32.data() , ncells );   // tree sums of the generic functor: equal within rounding
+  for(int k=0;k<3;k++) out.doubles( rsub[k].data() , ncells );
   onk_free( pv , np*8 ); onk_free( pb , (ncells+1)*8 ); onk_free( ps , ncells*8 );
   return pq.empty() ? 0 : 3;
 }
@@ -740,6 +759,91 @@ static int scenario_soatl(Out& out, size_t n)
   return 0;
 }
 
+// soatl::parallel_apply_simd on the device, the two C3 kernels: the 8-field read-modify-write sweep and the
+// tests/benchmark.cpp operator, through the GENERIC vectorised kernel of soatl/compute.h, next to the typed entry points
+// of the library on the same arrays.  Small n: every element goes to the output (parity); timed = 1: prints/returns times.
+static int scenario_soatl_apply(Out& out, size_t n, bool timed)
+{
+  using namespace onika::soatl;
+  void* stream = nullptr; ONIKA_B200_CHECK( onk_lane_stream( 0 , &stream ) );
+  cudaEvent_t e0, e1; ONIKA_CU_CHECK_ERRORS( cudaEventCreate(&e0) ); ONIKA_CU_CHECK_ERRORS( cudaEventCreate(&e1) );
+  auto time_us = [&](auto launch, int reps) -> double
+  {
+    for(int i=0;i<2;i++) launch();
+    ONIKA_CU_CHECK_ERRORS( cudaEventRecord( e0 , (cudaStream_t) stream ) );
+    for(int i=0;i<reps;i++) launch();
+    ONIKA_CU_CHECK_ERRORS( cudaEventRecord( e1 , (cudaStream_t) stream ) );
+    ONIKA_B200_CHECK( onk_lane_sync(0) );
+    float ms = 0; ONIKA_CU_CHECK_ERRORS( cudaEventElapsedTime( &ms , e0 , e1 ) );
+    return ms * 1e3 / reps;
+  };
+  double us[4] = {0,0,0,0};
+  const double s = 1.0000001; const double c[8] = { 0.125 , 0.25 , 0.375 , 0.5 , 0.625 , 0.75 , 0.875 , 1.0 };
+  {
+    auto fa = make_hybrid_field_arrays( cst::align<256>() , cst::chunk<16>() , bench_f0 , bench_f1 , bench_f2 , bench_f3 , bench_f4 , bench_f5 , bench_f6 , bench_f7 );
+    fa.resize(n);
+    double* col[8] = { fa[bench_f0] , fa[bench_f1] , fa[bench_f2] , fa[bench_f3] , fa[bench_f4] , fa[bench_f5] , fa[bench_f6] , fa[bench_f7] };
+    if( ! timed ) { for(int k=0;k<8;k++) for(size_t i=0;i<fa.capacity();i++) col[k][i] = ( i < n ) ? lcg(i,20+k,0.0,1.0) : 0.5; }
+    else ONIKA_B200_CHECK( onk_memset_bytes( fa.storage_ptr() , 0 , fa.storage_size() , 0 ) );
+    ONIKA_B200_CHECK( onk_prefetch( fa.storage_ptr() , fa.storage_size() , 1 , 0 ) ); ONIKA_B200_CHECK( onk_lane_sync(0) );
+    const double c0=c[0],c1=c[1],c2=c[2],c3=c[3],c4=c[4],c5=c[5],c6=c[6],c7=c[7];
+    auto rmw = [=] ONIKA_HOST_DEVICE_FUNC (double& a0, double& a1, double& a2, double& a3, double& a4, double& a5, double& a6, double& a7)
+      { a0 = a0*s + c0; a1 = a1*s + c1; a2 = a2*s + c2; a3 = a3*s + c3; a4 = a4*s + c4; a5 = a5*s + c5; a6 = a6*s + c6; a7 = a7*s + c7; };
+    auto sweep = [&]{ parallel_apply_simd( rmw , fa , bench_f0 , bench_f1 , bench_f2 , bench_f3 , bench_f4 , bench_f5 , bench_f6 , bench_f7 ); };
+    if( ! timed )
+    {
+      sweep();                                                   // default target: lane 0, synchronous like the reference's loop
+      for(int k=0;k<8;k++) out.doubles( col[k] , n );
+    }
+    else
+    {
+      DeviceApplyScope on_lane( 0 , false );                    // caller's lane, no host synchronisation between sweeps
+      us[0] = time_us( sweep , 5 );
+      us[1] = time_us( [&]{ ONIKA_B200_CHECK( onk_soatl_rmw_f64( fa.storage_ptr() , 256 , 16 , 8 , n , fa.capacity() , s , c , 0 ) ); } , 5 );
+    }
+    fa.clear();
+  }
+  {
+    auto arrays = make_hybrid_field_arrays( cst::align<256>() , cst::chunk<16>() , particle_rx , particle_ry , particle_rz , particle_e );
+    arrays.resize(n);
+    if( ! timed )
+      for(size_t i=0;i<arrays.capacity();i++)
+      { const bool in = i < n; arrays[particle_rx][i] = in ? lcg(i,10,0,1) : 2.0; arrays[particle_ry][i] = in ? lcg(i,11,0,1) : 3.0; arrays[particle_rz][i] = in ? lcg(i,12,0,1) : 4.0; arrays[particle_e][i] = 0.0; }
+    else
+    {
+      ONIKA_B200_CHECK( onk_parallel_memset( arrays[particle_rx] , arrays.capacity() , 0x3fe0000000000000ull , 8 , 0 ) );   // 0.5
+      ONIKA_B200_CHECK( onk_parallel_memset( arrays[particle_ry] , arrays.capacity() , 0x3fd0000000000000ull , 8 , 0 ) );   // 0.25
+      ONIKA_B200_CHECK( onk_parallel_memset( arrays[particle_rz] , arrays.capacity() , 0x3fe8000000000000ull , 8 , 0 ) );   // 0.75
+    }
+    ONIKA_B200_CHECK( onk_prefetch( arrays.storage_ptr() , arrays.storage_size() , 1 , 0 ) ); ONIKA_B200_CHECK( onk_lane_sync(0) );
+    const double ax = timed ? 0.125 : arrays[particle_rx][0], ay = timed ? 0.0625 : arrays[particle_ry][0], az = timed ? 0.03125 : arrays[particle_rz][0];
+    auto dist = [ax,ay,az] ONIKA_HOST_DEVICE_FUNC (double& d, double x, double y, double z)
+      {
+        x = x - ax; y = y - ay; z = z - az;
+        d = sqrt( x*x + y*y + z*z );
+        x /= d; y /= d; z /= d;
+        d += x/(y*z);
+      };
+    auto sweep = [&]{ parallel_apply_simd( dist , arrays , particle_e , particle_rx , particle_ry , particle_rz ); };
+    if( ! timed ) { sweep(); out.doubles( arrays[particle_e] , n ); }
+    else
+    {
+      DeviceApplyScope on_lane( 0 , false );
+      us[2] = time_us( sweep , 5 );
+      const size_t npad = ( ( n + 15 ) / 16 ) * 16;
+      us[3] = time_us( [&]{ ONIKA_B200_CHECK( onk_soatl_dist_f64( arrays[particle_e] , arrays[particle_rx] , arrays[particle_ry] , arrays[particle_rz] , npad , ax , ay , az , 0 ) ); } , 5 );
+    }
+    arrays.clear();
+  }
+  if( timed )
+  {
+    std::printf("soatl_apply n=%zu : 8-field rmw generic %.1f us (%.0f GB/s) , typed %.1f us (%.0f GB/s) ; benchmark.cpp operator generic %.1f us (%.0f GB/s) , typed %.1f us (%.0f GB/s)\n",
+                n, us[0], 128.0*n/us[0]/1e3, us[1], 128.0*n/us[1]/1e3, us[2], 32.0*n/us[2]/1e3, us[3], 32.0*n/us[3]/1e3);
+    out.doubles( us , 4 );
+  }
+  return 0;
+}
+
 // reduction helpers queued on lanes together with the kernels that produce their input
 static int scenario_reduce_helpers(Out& out, size_t rows, size_t cols)
 {
@@ -836,6 +940,7 @@ int main(int argc, char* argv[])
   else if( sc == "cells" ) rc = scenario_cells( out , arg(3,4096) );
   else if( sc == "listed" ) rc = scenario_listed( out );
   else if( sc == "soatl" ) rc = scenario_soatl( out , arg(3,53) );
+  else if( sc == "soatl_apply" ) rc = scenario_soatl_apply( out , arg(3,100003) , arg(4,0) != 0 );
   else if( sc == "perf" ) rc = scenario_perf( out , arg(3,1<<27) );
   else if( sc == "helpers" ) rc = scenario_helpers( out , arg(3,333) );
   else if( sc == "reduce_helpers" ) rc = scenario_reduce_helpers( out , arg(3,513) , arg(4,1027) );

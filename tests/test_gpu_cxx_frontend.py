@@ -144,10 +144,15 @@ def test_cell_sums_through_the_generic_functor_path(prog, tmp_path, orc):
     begin[1:] = np.cumsum(sizes, dtype=np.uint64)
     values = lcg_uniform(int(begin[-1]), 40, -1.0, 1.0)
     want, _ = orc.cell_sum_packed(values, begin)
-    typed, g128, g32 = d[3:3 + ncells], d[3 + ncells:3 + 2 * ncells], d[3 + 2 * ncells:]
+    typed, g128, g32 = (d[6 + k * ncells:6 + (k + 1) * ncells] for k in range(3))
     assert np.array_equal(typed, want)
     mag = np.add.reduceat(np.abs(values), begin[:-1].astype(np.int64))
     assert np.all(np.abs(g128 - want) <= SUM_RTOL * mag) and np.all(np.abs(g32 - want) <= SUM_RTOL * mag)
+    # sub-block items (several cells per CTA, the same functor source): every cell written, same sums within rounding
+    for k in range(3, 6):
+        sub = d[6 + k * ncells:6 + (k + 1) * ncells]
+        assert sub.size == ncells and not np.isnan(sub).any()
+        assert np.all(np.abs(sub - want) <= SUM_RTOL * mag)
 
 
 def test_3d_spaces(prog, tmp_path, orc, gold):
@@ -268,6 +273,29 @@ def test_soatl_container_layout_serialize_and_device_apply(prog, tmp_path, orc, 
     want = orc.soatl_dist(lcg_uniform(n, 10, 0, 1), lcg_uniform(n, 11, 0, 1), lcg_uniform(n, 12, 0, 1))
     assert np.array_equal(e, want, equal_nan=True)              # extended lambda on the device
     assert np.array_equal(e_named, want, equal_nan=True)        # named functor type with ApplyFunctorTraits::CudaCompatible
+
+
+@pytest.mark.parametrize("n", [1, 1023, 1024, 100_003, 1 << 20])
+def test_soatl_parallel_apply_simd_vectorised_device_kernel(prog, tmp_path, orc, n):
+    """both C3 operators through the generic vectorised kernel of soatl/compute.h (256-bit accesses, 4 elements per thread,
+    scalar tail): the 8-field read-modify-write sweep and the tests/benchmark.cpp operator, bit for bit against the oracle"""
+    d = run(prog, tmp_path, "soatl_apply", n).view(np.float64)
+    assert d.size == 9 * n
+    s, c = 1.0000001, np.array([0.125 * (k + 1) for k in range(8)])
+    for k in range(8):
+        col = lcg_uniform(n, 20 + k, 0.0, 1.0)
+        assert np.array_equal(d[k * n:(k + 1) * n], col * s + c[k]), k       # one rounded multiply, one rounded add (oracle rule)
+    # the same through the oracle's packed-storage sweep (orc_soatl_rmw_f64) for one layout
+    cap = ((n + 15) // 16) * 16
+    stride = ((cap * 8 + 255) // 256) * 256
+    st = np.zeros(8 * stride, dtype=np.uint8)
+    for k in range(8):
+        st[k * stride:k * stride + 8 * n].view(np.float64)[:] = lcg_uniform(n, 20 + k, 0.0, 1.0)
+    orc.soatl_rmw(st, 256, 16, 8, n, cap, s, c)
+    for k in range(8):
+        assert np.array_equal(d[k * n:(k + 1) * n], st[k * stride:k * stride + 8 * n].view(np.float64)), k
+    want = orc.soatl_dist(lcg_uniform(n, 10, 0, 1), lcg_uniform(n, 11, 0, 1), lcg_uniform(n, 12, 0, 1))
+    assert np.array_equal(d[8 * n:], want, equal_nan=True)
 
 
 # ---------------------------------------------------------------- the reference's own tutorial plugins, compiled unchanged

@@ -298,3 +298,41 @@ def test_cell_grid_z_slabs_two_gpus(orc):
         assert abs(totals[0] - total) <= 1e-12 * np.abs(e).sum() and abs(totals[1] - total) <= 1e-12 * np.abs(e).sum()
     assert np.array_equal(got[0][4], got[1][4])                                                # same bits on both ranks
     assert got[0][1] == got[1][0] and got[0][0] == 0 and got[1][1] == side ** 3
+
+
+# ---------------------------------------------------------------- the checks bench.py reports under `checks` at N > 1
+def _worker_checks(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import onika_b200 as ob
+    from tests import _multigpu_checks
+    ob.init(rank)
+    ob.bind_lane_to_torch_stream(0)
+    q.put((rank, _multigpu_checks.run_checks(rank, world)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bench_multi_gpu_checks_two_gpus():
+    """tests/_multigpu_checks.py (what `bench.py --gpus N` runs outside its timed regions): all five checks on 2 GPUs"""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_checks, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in range(world):
+        assert len(got[rank]) == 5 and all(v == "ok" for v in got[rank].values()), got[rank]
