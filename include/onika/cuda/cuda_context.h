@@ -15,10 +15,46 @@
 #include <vector>
 #include <sys/types.h>
 
+// Device description shared by every translation unit of a plugin, whichever compiler built it: ONE layout in nvcc and in
+// host-compiler TUs (the inline default_cuda_ctx() below is the same object for both, so a type that changes with the
+// compiler would be an ODR violation).  Field names follow cudaDeviceProp for the members the reference reads
+// (src/scg-builtin-components/init_cuda.cpp:179-195, include/onika/parallel/block_parallel_for.h:124).
+struct onikaDeviceProp_t
+{
+  char   name[256] = {0};
+  int    multiProcessorCount = 0;
+  int    warpSize = 32;
+  size_t totalGlobalMem = 0;
+  size_t sharedMemPerBlock = 0;
+  size_t sharedMemPerMultiprocessor = 0;
+  int    maxThreadsPerBlock = 1024;
+  int    maxThreadsPerMultiProcessor = 2048;
+  int    major = 0, minor = 0;
+  int    clockRate = 0;                 // kHz
+  int    managedMemory = 1;
+  int    concurrentManagedAccess = 1;
+  int    persistingL2CacheMaxSize = 0;
+  int    l2CacheSize = 0;
+};
+
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
 #include <cuda_runtime_api.h>
-using onikaDeviceProp_t = cudaDeviceProp;
+// fills the layout-stable description from the runtime's own (what ONIKA_CU_GET_DEVICE_PROPERTIES means here)
+static inline cudaError_t onika_get_device_properties( onikaDeviceProp_t* p , int id )
+{
+  cudaDeviceProp q;
+  const cudaError_t e = cudaGetDeviceProperties( &q , id );
+  if( e != cudaSuccess ) return e;
+  std::snprintf( p->name , sizeof(p->name) , "%s" , q.name );
+  p->multiProcessorCount = q.multiProcessorCount; p->warpSize = q.warpSize; p->totalGlobalMem = q.totalGlobalMem;
+  p->sharedMemPerBlock = q.sharedMemPerBlock; p->sharedMemPerMultiprocessor = q.sharedMemPerMultiprocessor;
+  p->maxThreadsPerBlock = q.maxThreadsPerBlock; p->maxThreadsPerMultiProcessor = q.maxThreadsPerMultiProcessor;
+  p->major = q.major; p->minor = q.minor; p->managedMemory = q.managedMemory; p->concurrentManagedAccess = q.concurrentManagedAccess;
+  p->persistingL2CacheMaxSize = q.persistingL2CacheMaxSize; p->l2CacheSize = q.l2CacheSize;
+  int khz = 0; if( cudaDeviceGetAttribute( &khz , cudaDevAttrClockRate , id ) == cudaSuccess ) p->clockRate = khz;
+  return cudaSuccess;
+}
 using onikaStream_t     = cudaStream_t;
 using onikaEvent_t      = cudaEvent_t;
 using onikaError_t      = cudaError_t;
@@ -64,14 +100,13 @@ static inline constexpr auto onikaMemcpyHostToDevice = cudaMemcpyHostToDevice;
 #define ONIKA_CU_SET_SHARED_MEM_CONFIG(shmc)           cudaDeviceSetSharedMemConfig(shmc)
 #define ONIKA_CU_SET_LIMIT(l,v)                        cudaDeviceSetLimit(l,v)
 #define ONIKA_CU_GET_LIMIT(vptr,l)                     cudaDeviceGetLimit(vptr,l)
-#define ONIKA_CU_GET_DEVICE_PROPERTIES(propPtr,id)     cudaGetDeviceProperties(propPtr,id)
+#define ONIKA_CU_GET_DEVICE_PROPERTIES(propPtr,id)     onika_get_device_properties(propPtr,id)
 #define ONIKA_CU_GET_DEVICE_ATTRIBUTE(valPtr,attr,id)  cudaDeviceGetAttribute(valPtr,attr,id)
 #define ONIKA_CU_DEVICE_SYNCHRONIZE()                  cudaDeviceSynchronize()
 #define ONIKA_CU_GET_ERROR_STRING(c)                   cudaGetErrorString(c)
 #else
 // host-only translation units still see the handle types (opaque) so that headers parse; they cannot launch kernels
-struct onikaDeviceProp_t { char name[256] = {0}; int multiProcessorCount = 0; int warpSize = 32; size_t totalGlobalMem = 0; size_t sharedMemPerBlock = 0; int managedMemory = 1; int concurrentManagedAccess = 1; int persistingL2CacheMaxSize = 0; };
-struct onikaDim3_t { unsigned int x = 1, y = 1, z = 1; };
+struct onikaDim3_t { unsigned int x = 1, y = 1, z = 1; };      // same layout as dim3 (static_assert in the nvcc branch of CudaDevice below)
 using onikaStream_t = void*;
 using onikaEvent_t  = void*;
 using onikaError_t  = int;
@@ -94,6 +129,9 @@ namespace onika { namespace cuda {
   inline constexpr long onika_dim3_size(const onikaDim3_t& d) { return long(d.x) * d.y * d.z; }
   inline constexpr long onika_dim3_size(long d) { return d; }
 
+# if defined(__CUDACC__)
+  static_assert( sizeof(onikaDim3_t) == 3 * sizeof(unsigned int) && alignof(onikaDim3_t) == alignof(unsigned int) , "dim3 layout assumed by host-compiler translation units" );
+# endif
   struct CudaDevice
   {
     onikaDeviceProp_t m_deviceProp;
@@ -138,10 +176,9 @@ namespace onika { namespace cuda {
         auto & d = ctx->m_devices[0];
         int sms = 0; size_t mem = 0;
         ONIKA_B200_CHECK( onk_device_info( & d.device_id , & sms , & mem , d.m_deviceProp.name , sizeof(d.m_deviceProp.name) ) );
+        d.m_deviceProp.multiProcessorCount = sms; d.m_deviceProp.totalGlobalMem = mem;       // from the runtime library: any compiler
 #       if defined(__CUDACC__)
-        ONIKA_CU_CHECK_ERRORS( cudaGetDeviceProperties( & d.m_deviceProp , d.device_id ) );
-#       else
-        d.m_deviceProp.multiProcessorCount = sms; d.m_deviceProp.totalGlobalMem = mem;
+        ONIKA_CU_CHECK_ERRORS( onika_get_device_properties( & d.m_deviceProp , d.device_id ) );
 #       endif
         s_default_cuda_ctx = ctx;
       }

@@ -28,12 +28,11 @@ namespace onika
     ONIKA_HOST_DEVICE_FUNC inline T* end() { return m_data + N; }
     ONIKA_HOST_DEVICE_FUNC inline const T* end() const { return m_data + N; }
 
-    // lexicographic order with the LAST coordinate most significant (z, then y, then x): the order in which
-    // coord_range_to_list enumerates a range
+    // lexicographic order, coordinate 0 most significant (include/onika/oarray.h:49-58 in the reference); host and device
     template<class U> requires std::totally_ordered_with<T,U>
-    inline std::strong_ordering operator <=> (const oarray_t<U,N>& o) const
+    ONIKA_HOST_DEVICE_FUNC inline std::strong_ordering operator <=> (const oarray_t<U,N>& o) const
     {
-      for (size_t k = N; k-- > 0; )
+      for (size_t k = 0; k < N; k++)
       {
         if (m_data[k] < o.m_data[k]) return std::strong_ordering::less;
         if (m_data[k] > o.m_data[k]) return std::strong_ordering::greater;
@@ -41,7 +40,7 @@ namespace onika
       return std::strong_ordering::equal;
     }
     template<class U> requires std::equality_comparable_with<T,U>
-    inline bool operator == (const oarray_t<U,N>& o) const
+    ONIKA_HOST_DEVICE_FUNC inline bool operator == (const oarray_t<U,N>& o) const
     {
       for (size_t k = 0; k < N; k++) if (!(m_data[k] == o.m_data[k])) return false;
       return true;

@@ -57,12 +57,29 @@ namespace onika { namespace parallel {
   static inline constexpr size_t MAX_CONFLICT_MAP_SIZE = 128;
   using AccessConflictMap = onika::inplace_vector< oarray_t<int,3> , MAX_CONFLICT_MAP_SIZE >;
 
-  // two access sets may conflict when they name the same data and their combined access modes intersect
+  // two access sets may conflict when they name the same data and their combined access modes intersect: the reference's
+  // test (src/parallel/parallel_data_access.cpp:28-45), kept bit for bit because the reference PRINTS its outcome.  Note what
+  // it answers: with RO = 1 and WO = 2 a pure writer and a pure reader of the same data do not "conflict" while two readers
+  // do -- so it must not be used to ORDER operations; data_access_dependency() below is the ordering rule.
   inline bool concurrent_data_access(const ParallelDataAccessVector& a , const ParallelDataAccessVector& b )
   {
     auto modes = [](const ParallelDataAccess& d) { unsigned m = 0; for(auto e : d.m_stencil) m |= e.mode(); return m; };
     for(const auto & da : a) for(const auto & db : b)
       if( da.m_data_ptr == db.m_data_ptr && ( modes(da) & modes(db) ) != 0 ) return true;
+    return false;
+  }
+
+  // must operation b (queued after a) wait for a ?  Same data, both touch it, at least one writes: read-after-write,
+  // write-after-read and write-after-write all order; two readers do not.  This is the element rule of
+  // concurrent_data_access_conflict_map applied to whole access sets, and what the lane placement uses.
+  inline bool data_access_dependency(const ParallelDataAccessVector& a , const ParallelDataAccessVector& b )
+  {
+    auto modes = [](const ParallelDataAccess& d) { unsigned m = 0; for(auto e : d.m_stencil) m |= e.mode(); return m; };
+    for(const auto & da : a) for(const auto & db : b)
+    {
+      const unsigned ma = modes(da) , mb = modes(db);
+      if( da.m_data_ptr == db.m_data_ptr && ma != 0 && mb != 0 && ( ( ma | mb ) & AccessStencilElement::WO ) != 0 ) return true;
+    }
     return false;
   }
 

@@ -137,7 +137,7 @@ namespace onika { namespace parallel {
         auto visit = [&](const ParallelExecutionContext* q)
         {
           if( q->m_lane < 0 || q->m_data_access.empty() ) return;
-          if( ! concurrent_data_access( q->m_data_access , pec->m_data_access ) ) return;
+          if( ! data_access_dependency( q->m_data_access , pec->m_data_access ) ) return;
           pec->add_lane_dependency( q->m_lane );
           last_conflict_lane = q->m_lane;
         };

@@ -7,10 +7,93 @@
 // ONK_LANE_D2H); device staging is double-buffered and recycled through events.  Results are identical to the
 // device-resident entry points because the very same kernels run on the chunks (reductions: per-chunk partials are
 // combined in chunk order by onk_combine_f64).
+//
+// PAGEABLE input (ordinary malloc'ed memory, what a plugin usually holds): the copy engine cannot read it directly and the
+// driver's own bounce path runs at ~11 GB/s on this class of host.  The library stages it itself: a small pool of host
+// threads copies chunk k+1 into a ring of pinned buffers while chunk k crosses PCIe from the previous ring slot
+// (measured on the B200 box: see DESIGN.md "e2e").  Pinned / registered / managed input skips the staging.
 #include "onk_internal.cuh"
+
+#include <condition_variable>
+#include <thread>
+#include <sched.h>
 
 namespace onk
 {
+  // ---- host copy pool: memcpy of one large block split over a few persistent threads ----
+  class CopyPool
+  {
+  public:
+    static CopyPool& instance() { static CopyPool* p = new CopyPool(); return *p; }     // never destroyed: workers sleep on a condition variable
+    int threads() const { return m_nthreads; }
+    void copy(void* dst, const void* src, size_t bytes)
+    {
+      if (bytes < (1u << 20) || m_nthreads <= 1) { memcpy(dst, src, bytes); return; }
+      {
+        std::lock_guard<std::mutex> lk(m_mutex);
+        m_dst = (char*)dst; m_src = (const char*)src; m_bytes = bytes; m_pending = m_nthreads - 1; ++m_generation;
+      }
+      m_wake.notify_all();
+      slice(0, (char*)dst, (const char*)src, bytes);                                       // the caller is thread 0
+      std::unique_lock<std::mutex> lk(m_mutex);
+      m_done.wait(lk, [&]{ return m_pending == 0; });
+    }
+  private:
+    CopyPool()
+    {
+      int n = 0;
+      cpu_set_t set;
+      if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+      if (n <= 0) n = (int)std::thread::hardware_concurrency();
+      if (const char* e = getenv("ONK_HOST_COPY_THREADS")) n = atoi(e);
+      m_nthreads = n < 1 ? 1 : (n > 8 ? 8 : n);
+      for (int t = 1; t < m_nthreads; t++) std::thread([this, t]{ worker(t); }).detach();
+    }
+    void slice(int t, char* dst, const char* src, size_t bytes) const
+    {
+      const size_t per = ((bytes / m_nthreads) + 4095) & ~(size_t)4095;
+      const size_t b = (size_t)t * per;
+      if (b >= bytes) return;
+      const size_t e = (t == m_nthreads - 1 || b + per > bytes) ? bytes : b + per;
+      memcpy(dst + b, src + b, e - b);
+    }
+    void worker(int t)
+    {
+      uint64_t seen = 0;
+      for (;;)
+      {
+        char* d; const char* s; size_t n;
+        {
+          std::unique_lock<std::mutex> lk(m_mutex);
+          m_wake.wait(lk, [&]{ return m_generation != seen; });
+          seen = m_generation; d = m_dst; s = m_src; n = m_bytes;
+        }
+        slice(t, d, s, n);
+        {
+          std::lock_guard<std::mutex> lk(m_mutex);
+          if (--m_pending == 0) m_done.notify_one();
+        }
+      }
+    }
+    std::mutex m_mutex;
+    std::condition_variable m_wake, m_done;
+    char* m_dst = nullptr; const char* m_src = nullptr; size_t m_bytes = 0;
+    uint64_t m_generation = 0;
+    int m_pending = 0, m_nthreads = 1;
+  };
+
+  // pinned ring for pageable input
+  constexpr int    PIN_SLOTS = 3;
+  static void*     g_pin[PIN_SLOTS] = {nullptr, nullptr, nullptr};
+
+  // can the copy engine read this host pointer directly ?  (pinned, registered or managed memory)
+  static bool dma_readable(const void* p)
+  {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type != cudaMemoryTypeUnregistered;
+  }
+
   constexpr int LANE_H2D = ONK_MAX_LANES - 1, LANE_COMPUTE = ONK_MAX_LANES - 2, LANE_D2H = ONK_MAX_LANES - 3;
   constexpr size_t STAGE_BYTES = 64u << 20;       // per staging buffer
   constexpr int MAX_CHUNK_PARTIALS = MAX_PARTIALS;
@@ -26,6 +109,12 @@ namespace onk
       if (!r.stage_dev[i]) ONK_CUDA(cudaMalloc(&r.stage_dev[i], STAGE_BYTES));
     }
     r.stage_bytes = STAGE_BYTES;
+    return ONK_OK;
+  }
+  static int ensure_pinned_ring()
+  {
+    for (int i = 0; i < PIN_SLOTS; i++)
+      if (!g_pin[i]) ONK_CUDA(cudaHostAlloc(&g_pin[i], STAGE_BYTES, cudaHostAllocDefault));
     return ONK_OK;
   }
 
@@ -56,14 +145,29 @@ int onk_host_reduce_f64(int op, const double* in_host, uint64_t n, double* out_h
   ONK_REQUIRE(nchunks <= (uint64_t)MAX_CHUNK_PARTIALS, "onk_host_reduce_f64: input too large (%llu chunks)", (unsigned long long)nchunks);
   // per-chunk partials live in the H2D lane's partial array (that lane never runs a reduction itself)
   double* chunk_part = H->ws.partials;
-  Ev ready[2], freed[2];
+  Ev ready[2], freed[2], sent[PIN_SLOTS];
   for (int i = 0; i < 2; i++) { if (int rc = ready[i].init()) return rc; if (int rc = freed[i].init()) return rc; }
+  const bool staged = n > 0 && !dma_readable(in_host);        // pageable input: through the pinned ring
+  if (staged)
+  {
+    if (int rc = ensure_pinned_ring()) return rc;
+    for (int i = 0; i < PIN_SLOTS; i++) if (int rc = sent[i].init()) return rc;
+  }
   for (uint64_t k = 0; k < nchunks; k++)
   {
     const int b = (int)(k & 1);
     const uint64_t cnt = (k + 1 == nchunks) ? n - k * chunk : chunk;
+    const double* src = in_host + k * chunk;
+    if (staged)
+    {
+      const int s = (int)(k % PIN_SLOTS);
+      if (k >= (uint64_t)PIN_SLOTS) ONK_CUDA(cudaEventSynchronize(sent[s].e));    // slot s has crossed PCIe
+      CopyPool::instance().copy(g_pin[s], src, cnt * sizeof(double));            // overlaps the transfers of the previous slots
+      src = (const double*)g_pin[s];
+    }
     if (k >= 2) ONK_CUDA(cudaStreamWaitEvent(H->stream, freed[b].e, 0));
-    ONK_CUDA(cudaMemcpyAsync(r.stage_dev[b], in_host + k * chunk, cnt * sizeof(double), cudaMemcpyHostToDevice, H->stream));
+    ONK_CUDA(cudaMemcpyAsync(r.stage_dev[b], src, cnt * sizeof(double), cudaMemcpyHostToDevice, H->stream));
+    if (staged) ONK_CUDA(cudaEventRecord(sent[(int)(k % PIN_SLOTS)].e, H->stream));
     ONK_CUDA(cudaEventRecord(ready[b].e, H->stream));
     ONK_CUDA(cudaStreamWaitEvent(K->stream, ready[b].e, 0));
     if (int rc = onk_reduce_f64(op, (const double*)r.stage_dev[b], cnt, chunk_part + k, LANE_COMPUTE)) return rc;

@@ -15,7 +15,8 @@ PLUGIN_FLAGS = [
     "-std=c++20", "--extended-lambda", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O2",
     "--fmad=false", "-Xcompiler", "-fopenmp", "-Xcompiler", "-Wno-deprecated-declarations", "-I" + INCLUDE,
 ]
-PROGRAMS = {"frontend_test": (["frontend_test.cu"], []), "frontend_test_generic": (["frontend_test.cu"], ["-DONIKA_B200_DISABLE_TYPED_FAST_PATHS"])}
+PROGRAMS = {"frontend_test": (["frontend_test.cu"], []), "frontend_test_generic": (["frontend_test.cu"], ["-DONIKA_B200_DISABLE_TYPED_FAST_PATHS"]),
+            "multi_gpu_test": (["multi_gpu_test.cu"], [])}
 
 
 def compile_program(sources, output, extra_flags=(), verbose=False):
@@ -87,6 +88,25 @@ def build_reference_plugins(force: bool = False, verbose: bool = False):
     return compile_program([os.path.join(CXX_TESTS, "run_operator.cu")] + srcs, REFPLUGIN_BIN, verbose=verbose)
 
 
+MIXED_TU_BIN = os.path.join(CXX_TESTS, "mixed_tu_test")
+
+
+def build_mixed_tu_test(force: bool = False, verbose: bool = False):
+    """one program from a g++-compiled and an nvcc-compiled translation unit that share the default CUDA context
+    (tests/cxx/mixed_tu_host.cpp + mixed_tu_device.cu): the layouts of the shared types must not depend on the compiler"""
+    if not force and not needs_build("mixed_tu_test"):
+        return MIXED_TU_BIN
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    obj = os.path.join(CXX_TESTS, "mixed_tu_host.o")
+    cmd = ["g++", "-std=c++20", "-O2", "-fopenmp", "-c", "-I" + INCLUDE, os.path.join(CXX_TESTS, "mixed_tu_host.cpp"), "-o", obj]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd, env=env)
+    return compile_program([os.path.join(CXX_TESTS, "mixed_tu_device.cu"), obj], MIXED_TU_BIN, verbose=verbose)
+
+
 def build_all(force: bool = False, verbose: bool = False):
     outs = []
     build_reference_plugins(force, verbose)
@@ -94,6 +114,7 @@ def build_all(force: bool = False, verbose: bool = False):
         if force or needs_build(name):
             compile_program([os.path.join(CXX_TESTS, s) for s in srcs], program_path(name), extra_flags=flags, verbose=verbose)
         outs.append(program_path(name))
+    outs.append(build_mixed_tu_test(force, verbose))
     return outs
 
 

@@ -358,6 +358,48 @@ static int scenario_autolanes(Out& out, size_t rows, size_t cols, int iters)
   return pq.empty() ? 0 : 3;
 }
 
+// ordering rule of the lane placement for one-sided declarations (any_lane + accesses): a WO producer followed by an RO
+// consumer (read-after-write) and an RO consumer followed by a WO producer (write-after-read) must both order, two readers
+// need not.  The slow kernels make a missing edge visible in the results.
+static int scenario_autolanes_raw_war(Out& out, size_t rows, size_t cols, int iters)
+{
+  extras::Array2D A, B, C, D;
+  A.resize(rows,cols); B.resize(rows,cols); C.resize(rows,cols); D.resize(rows,cols);
+  fill(A.m_data,8,1e-3,1.0); fill(B.m_data,9,1e-3,1.0); fill(C.m_data,10,1e-3,1.0); fill(D.m_data,11,1e-3,1.0);
+  const auto a_wo = local_access( A.m_data.data() , 2 , AccessStencilElement::WO , "a_wo" );
+  const auto a_ro = local_access( A.m_data.data() , 2 , AccessStencilElement::RO , "a_ro" );
+  const auto b_rw = local_access( B.m_data.data() , 2 , AccessStencilElement::RW , "b_rw" );
+  const auto c_rw = local_access( C.m_data.data() , 2 , AccessStencilElement::RW , "c_rw" );
+  const auto d_rw = local_access( D.m_data.data() , 2 , AccessStencilElement::RW , "d_rw" );
+  ParallelExecutionContext* pec[6] = { parallel_execution_context("A","produce") , parallel_execution_context("B","+=A") , parallel_execution_context("C","slow")
+                                     , parallel_execution_context("C","+=A") , parallel_execution_context("A","overwrite") , parallel_execution_context("D","+=A") };
+  auto & pq = ParallelExecutionQueue::default_queue();
+  pq << any_lane(4)
+     << a_wo << block_parallel_for( rows , RepeatedAddFunctor{ A , 1.1 , iters } , pec[0] )      // slow producer of A, declared write-only
+     << a_ro << b_rw << block_parallel_for( rows , AddArrayFunctor{ A , B } , pec[1] )             // RAW: must see the produced A
+     << c_rw << block_parallel_for( rows , RepeatedAddFunctor{ C , 1.3 , iters } , pec[2] )      // slow, independent of A
+     << a_ro << c_rw << block_parallel_for( rows , AddArrayFunctor{ A , C } , pec[3] )             // reads A behind the slow kernel on C
+     << a_wo << block_parallel_for( rows , extras::BlockParallelValueAddFunctor<true>{ A , 1.4 } , pec[4] )   // WAR: must wait for BOTH readers of A
+     << a_ro << d_rw << block_parallel_for( rows , AddArrayFunctor{ A , D } , pec[5] );            // RAW again, after the overwrite
+  pq << flush;
+  double lanes[6], waits[6];
+  for(int k=0;k<6;k++)
+  {
+    lanes[k] = pec[k]->m_lane;
+    int nw = 0; for(int l=0;l<256;l++) if( pec[k]->depends_on_lane(l) ) ++nw;
+    waits[k] = nw;
+  }
+  pq << synchronize;
+  out.doubles( A.data() , rows*cols ); out.doubles( B.data() , rows*cols ); out.doubles( C.data() , rows*cols ); out.doubles( D.data() , rows*cols );
+  out.doubles( lanes , 6 ); out.doubles( waits , 6 );
+  // the printed test of the reference keeps its (different) meaning: writer vs reader -> no "conflict", reader vs reader -> "conflict"
+  ParallelDataAccessVector vw, vr; vw.push_back( a_wo ); vr.push_back( a_ro );
+  const double ref_rule[4] = { double( concurrent_data_access( vw , vr ) ) , double( concurrent_data_access( vr , vr ) ) ,
+                               double( data_access_dependency( vw , vr ) ) , double( data_access_dependency( vr , vr ) ) };
+  out.doubles( ref_rule , 4 );
+  return pq.empty() ? 0 : 3;
+}
+
 // what the lane DAG buys: the tutorial pattern (2 arrays x 2 kernels, few blocks each) serialised on one lane, on two
 // explicit lanes, and under any_lane() with declared accesses.  Prints wall milliseconds of flush..synchronize.
 static int scenario_autolanes_perf(Out& out, size_t rows, size_t cols, int iters)
@@ -932,6 +974,7 @@ int main(int argc, char* argv[])
   else if( sc == "value_add" ) rc = scenario_value_add( out , arg(3,257) , arg(4,129) );
   else if( sc == "lanes" ) rc = scenario_lanes( out , argc>3 ? argv[3] : "hybrid-lane" , arg(4,1024) , arg(5,1024) , arg(6,1) != 0 );
   else if( sc == "autolanes" ) rc = scenario_autolanes( out , arg(3,64) , arg(4,4096) , int(arg(5,2000)) );
+  else if( sc == "autolanes_raw_war" ) rc = scenario_autolanes_raw_war( out , arg(3,64) , arg(4,4096) , int(arg(5,2000)) );
   else if( sc == "autolanes_perf" ) rc = scenario_autolanes_perf( out , arg(3,4) , arg(4,8192) , int(arg(5,20000)) );
   else if( sc == "graph" ) rc = scenario_graph( out , arg(3,128) , arg(4,512) , int(arg(5,3)) , int(arg(6,200)) );
   else if( sc == "cells_generic_perf" ) rc = scenario_cells_generic_perf( out , arg(3,1<<18) );

@@ -263,3 +263,72 @@ int main(int argc, char* argv[])
         f.write_text(bad)
         rc, out, err = parse(f)
         assert rc == 3 and where in err, (bad, err)
+
+
+def test_oarray_order_and_pfa_size_calculator_match_the_reference_headers(tmp_path):
+    """oarray_t::operator<=> (coordinate 0 most significant, include/onika/oarray.h:49-58 in the reference) and the SOATL size
+    calculator names (pfa_size_calculator_t, pfa_details::check_size_for_capacity, pfa_storage_size, pfa_pointer_offset:
+    include/onika/soatl/packed_field_arrays.h:36-178): ONE program compiled against this repo's headers and, where the
+    reference tree is present, against the reference's own headers -- the two outputs must be identical, and the sizes must
+    equal the oracle's calculator (pinned against oracle/_ref in test_oracle_vs_reference.py)."""
+    import oracle
+    src = tmp_path / "probe.cpp"
+    src.write_text(r'''
+#include <onika/oarray.h>
+#include <onika/soatl/field_id.h>
+#include <onika/soatl/packed_field_arrays.h>
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+using namespace onika;
+struct t_rx {}; struct t_at {}; struct t_e {}; struct t_mid {}; struct t_h {};
+namespace onika { namespace soatl {
+  template<> struct FieldId<t_rx>  { using value_type = double;        using Id = t_rx;  static const char* name() { return "rx"; } };
+  template<> struct FieldId<t_at>  { using value_type = unsigned char; using Id = t_at;  static const char* name() { return "at"; } };
+  template<> struct FieldId<t_e>   { using value_type = double;        using Id = t_e;   static const char* name() { return "e"; } };
+  template<> struct FieldId<t_mid> { using value_type = int;           using Id = t_mid; static const char* name() { return "mid"; } };
+  template<> struct FieldId<t_h>   { using value_type = short;         using Id = t_h;   static const char* name() { return "h"; } };
+} }
+template<size_t A, size_t C> void sizes()
+{
+  using Fids = soatl::FieldIds<t_rx,t_at,t_e,t_mid,t_h>;
+  for(size_t cap : { size_t(0) , C , 2*C , 7*C , 1000*C })
+  {
+    using IA = std::integral_constant<size_t,A>; using IC = std::integral_constant<size_t,C>;
+    std::printf("%zu %zu %zu %zu %zu %zu %zu\n", A, C, cap, soatl::pfa_size_calculator_t<A,Fids,C>::storage_size(cap),
+                soatl::pfa_details::check_size_for_capacity( IA{} , IC{} , Fids{} , cap ),
+                soatl::pfa_storage_size<A,C,Fids>( cap ), soatl::pfa_pointer_offset<A,C,t_mid,t_rx,t_at,t_e,t_mid,t_h>( cap ) );
+  }
+}
+int main()
+{
+  using C3 = oarray_t<long,3>;
+  std::vector<C3> v = { C3{{2,0,0}} , C3{{0,0,5}} , C3{{0,3,0}} , C3{{1,9,9}} , C3{{0,3,-1}} , C3{{2,0,0}} };
+  std::sort( v.begin() , v.end() );
+  for(const auto& c : v) std::printf("%ld,%ld,%ld ", c[0], c[1], c[2]);
+  std::printf("| %d %d %d\n", int( C3{{0,9,9}} < C3{{1,0,0}} ), int( C3{{1,0,0}} < C3{{0,9,9}} ), int( C3{{1,2,3}} == C3{{1,2,3}} ));
+  sizes<64,16>(); sizes<64,8>(); sizes<256,16>(); sizes<1,1>(); sizes<32,4>();
+  return 0;
+}
+''')
+    stub = os.path.join(os.path.dirname(INC), "oracle", "stub")
+
+    def build_and_run(include, name):
+        exe = tmp_path / name
+        subprocess.check_call(["g++", "-std=c++20", "-fopenmp", "-DSOATL_SIZE_TYPE_32BITS=1", f"-I{include}", f"-I{stub}", str(src), "-o", str(exe)]
+                              + ([f"-L{os.path.dirname(lib)}", "-lonika_b200", f"-Wl,-rpath,{os.path.dirname(lib)}"] if include == INC else []), env=_env())
+        return subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+
+    from onika_b200 import _build
+    lib = _build.build()
+    ours = build_and_run(INC, "ours")
+    assert ours[0] == "0,0,5 0,3,-1 0,3,0 1,9,9 2,0,0 2,0,0 | 1 0 1"          # coordinate 0 first
+    sizes = {8: "rx", 1: "at", 4: "mid", 2: "h"}
+    for line in ours[1:]:
+        a, c, cap, calc, chk, stor, off = map(int, line.split())
+        assert calc == chk == stor == oracle.orc.storage_size_calc(a, c, [8, 1, 8, 4, 2], cap), line
+        assert off == oracle.orc.storage_size_calc(a, c, [8, 1, 8], cap), line
+    ref_inc = "/root/reference/include"
+    if os.path.isdir(ref_inc):
+        theirs = build_and_run(ref_inc, "theirs")
+        assert theirs == ours

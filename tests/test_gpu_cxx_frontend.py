@@ -89,6 +89,30 @@ def test_automatic_lanes_from_declared_accesses(prog, tmp_path):
     assert list(waits) == [0, 0, 0, 1, 0, 0]                      # only B += A carries a cross-lane edge (to B's lane)
 
 
+def test_automatic_lanes_order_write_only_and_read_only_declarations(prog, tmp_path):
+    """one-sided declarations under any_lane(): a WO producer followed by an RO consumer (read-after-write), then RO
+    consumers followed by a WO producer (write-after-read, readers on two lanes) -- results must equal serial FIFO execution.
+    The reference's printed test concurrent_data_access() keeps its own answers (no 'conflict' for writer/reader)."""
+    rows, cols, iters = 64, 4096, 2000
+    d = run(prog, tmp_path, "autolanes_raw_war", rows, cols, iters).view(np.float64)
+    n = rows * cols
+    A, B, C, D = lcg_uniform(n, 8), lcg_uniform(n, 9), lcg_uniform(n, 10), lcg_uniform(n, 11)
+    for _ in range(iters):
+        A += 1.1
+    B += A
+    for _ in range(iters):
+        C += 1.3
+    C += A
+    A += 1.4
+    D += A
+    assert np.array_equal(d[:n], A) and np.array_equal(d[n:2 * n], B) and np.array_equal(d[2 * n:3 * n], C) and np.array_equal(d[3 * n:4 * n], D)
+    lanes, waits = d[4 * n:4 * n + 6].astype(int), d[4 * n + 6:4 * n + 12].astype(int)
+    assert lanes[1] == lanes[0]                                   # the consumer follows its producer's lane
+    assert lanes[2] != lanes[0]                                   # the independent slow kernel overlaps
+    assert waits[3] >= 1 and waits[4] >= 1                        # C += A waits for A's lane; the overwrite waits for the reader on C's lane
+    assert list(d[4 * n + 12:4 * n + 16]) == [0.0, 1.0, 1.0, 0.0]  # reference rule (printed) vs ordering rule
+
+
 def test_automatic_lanes_overlap_like_explicit_lanes(prog, tmp_path):
     """few-block kernels on two arrays: any_lane()+accesses must overlap them like explicit lanes 0/1 do (and both beat one
     lane); results stay exact: 9 sequential runs of (k1,k2) per array"""
@@ -296,6 +320,70 @@ def test_soatl_parallel_apply_simd_vectorised_device_kernel(prog, tmp_path, orc,
         assert np.array_equal(d[k * n:(k + 1) * n], st[k * stride:k * stride + 8 * n].view(np.float64)), k
     want = orc.soatl_dist(lcg_uniform(n, 10, 0, 1), lcg_uniform(n, 11, 0, 1), lcg_uniform(n, 12, 0, 1))
     assert np.array_equal(d[8 * n:], want, equal_nan=True)
+
+
+def _multi_gpu_expected(orc, n, world):
+    """what every rank of tests/cxx/multi_gpu_test must write: fused min/max/sum of the sharded array (twice), then the
+    all_reduce_multi results -- rank-order folds from the identity"""
+    d = lcg_uniform(n, 7, -1.0, 1.0)
+    a = 0.0
+    f = np.float64(0.0)
+    cnt = 0.0
+    for r in range(world):
+        a = a + 0.5 * (r + 1)
+        f = f + np.float64(np.float32(1.25) * np.float32(r + 1))
+        cnt = cnt + (10 + r)
+    return d, [a, float(np.float32(f)), float(int(cnt)), -3.0, -3.0 + (world - 1)]
+
+
+def run_multi_gpu_program(tmp_path, world, n):
+    from onika_b200 import cxx
+    exe = cxx.program_path("multi_gpu_test")
+    if not os.path.exists(exe):
+        cxx.build_all()
+    rdv = os.path.join(tmp_path, f"rdv{world}_{n}")
+    os.makedirs(rdv, exist_ok=True)
+    procs = [subprocess.Popen([exe, str(r), str(world), rdv, str(n), os.path.join(rdv, f"out{r}.bin")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+             for r in range(world)]
+    outs = []
+    for r, p in enumerate(procs):
+        so, se = p.communicate(timeout=300)
+        assert p.returncode == 0, (r, p.returncode, so[-1000:], se[-1000:])
+        outs.append(np.fromfile(os.path.join(rdv, f"out{r}.bin"), dtype=np.float64))
+    return outs
+
+
+def check_multi_gpu_outputs(outs, orc, n, world):
+    d, multi = _multi_gpu_expected(orc, n, world)
+    mag = np.abs(d).sum()
+    for o in outs:
+        assert o.size == 12
+        for rep in range(2):
+            mn, mx, sm = o[3 * rep:3 * rep + 3]
+            assert mn == orc.reduce_min(d) and mx == orc.reduce_max(d)
+            assert abs(sm - orc.reduce_sum_ld(d)) <= SUM_RTOL * mag
+        assert list(o[0:3]) == list(o[3:6])                         # reproducible
+        assert list(o[6:11]) == multi and o[11] == 1.0
+        assert np.array_equal(o, outs[0])                           # same bits on every rank
+
+
+def test_cxx_multi_gpu_helper_world_of_one(tmp_path, orc):
+    """onika/parallel/multi_gpu.h (all_reduce_multi in the reference's call shape, fused reduce + exchange) with one rank:
+    the whole protocol runs, the folds start from the identity"""
+    n = 1_000_003
+    check_multi_gpu_outputs(run_multi_gpu_program(tmp_path, 1, n), orc, n, 1)
+
+
+def test_host_compiler_and_nvcc_translation_units_share_one_context():
+    """a plugin = .cpp files compiled by g++ plus .cu files compiled by nvcc: the default CUDA context is created by the g++
+    half and read by the nvcc half (tests/cxx/mixed_tu_*): every shared type has one layout, the SM count that sizes fixed
+    grids is the device's"""
+    from onika_b200 import cxx
+    if not os.path.exists(cxx.MIXED_TU_BIN):
+        cxx.build_mixed_tu_test()
+    r = subprocess.run([cxx.MIXED_TU_BIN], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[-1000:], r.stderr[-1000:])
+    assert "mixed TU ok" in r.stdout
 
 
 # ---------------------------------------------------------------- the reference's own tutorial plugins, compiled unchanged

@@ -336,3 +336,14 @@ def test_bench_multi_gpu_checks_two_gpus():
         assert p.exitcode == 0
     for rank in range(world):
         assert len(got[rank]) == 5 and all(v == "ok" for v in got[rank].values()), got[rank]
+
+
+def test_cxx_multi_gpu_helper_two_processes(tmp_path, orc):
+    """the C++ front end's multi-GPU helper (include/onika/parallel/multi_gpu.h) without MPI or Python in the data path: two
+    processes of tests/cxx/multi_gpu_test, handles exchanged through the file rendezvous"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from tests.test_gpu_cxx_frontend import run_multi_gpu_program, check_multi_gpu_outputs
+    for n in (4_000_003, 5):
+        check_multi_gpu_outputs(run_multi_gpu_program(str(tmp_path), 2, n), orc, n, 2)
