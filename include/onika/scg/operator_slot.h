@@ -58,7 +58,13 @@ namespace onika { namespace scg {
     }
     inline bool set_from_string(const std::string& s) override
     {
-      if constexpr ( std::is_arithmetic_v<T> ) { std::istringstream iss(s); T v{}; if( iss >> v ) { *m_value = v; return true; } return false; }
+      if constexpr ( std::is_same_v<T,bool> )
+      {
+        if( s == "true" || s == "yes" || s == "on" || s == "1" ) { *m_value = true; return true; }
+        if( s == "false" || s == "no" || s == "off" || s == "0" ) { *m_value = false; return true; }
+        return false;
+      }
+      else if constexpr ( std::is_arithmetic_v<T> ) { std::istringstream iss(s); T v{}; if( iss >> v ) { *m_value = v; return true; } return false; }
       else if constexpr ( std::is_same_v<T,std::string> ) { *m_value = s; return true; }
       else return false;
     }

@@ -17,10 +17,36 @@
 #include <condition_variable>
 #include <thread>
 #include <sched.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 namespace onk
 {
-  // ---- host copy pool: memcpy of one large block split over a few persistent threads ----
+  // copy into a pinned staging buffer that the CPU will not read again: non-temporal stores skip the read-for-ownership
+  // of the destination lines, one pass less over host DRAM (the staging path is bound by host memory bandwidth)
+  static void copy_streaming(char* dst, const char* src, size_t bytes)
+  {
+#if defined(__x86_64__)
+    if (((uintptr_t)dst & 15) == 0)
+    {
+      const size_t nvec = bytes / 64;
+      const __m128i* s = (const __m128i*)src;
+      __m128i* d = (__m128i*)dst;
+      for (size_t i = 0; i < nvec; i++)
+      {
+        const __m128i a = _mm_loadu_si128(s + 4 * i), b = _mm_loadu_si128(s + 4 * i + 1), c = _mm_loadu_si128(s + 4 * i + 2), e = _mm_loadu_si128(s + 4 * i + 3);
+        _mm_stream_si128(d + 4 * i, a); _mm_stream_si128(d + 4 * i + 1, b); _mm_stream_si128(d + 4 * i + 2, c); _mm_stream_si128(d + 4 * i + 3, e);
+      }
+      _mm_sfence();
+      if (bytes & 63) memcpy(dst + nvec * 64, src + nvec * 64, bytes & 63);
+      return;
+    }
+#endif
+    memcpy(dst, src, bytes);
+  }
+
+  // ---- host copy pool: copy of one large block split over a few persistent threads ----
   class CopyPool
   {
   public:
@@ -28,7 +54,7 @@ namespace onk
     int threads() const { return m_nthreads; }
     void copy(void* dst, const void* src, size_t bytes)
     {
-      if (bytes < (1u << 20) || m_nthreads <= 1) { memcpy(dst, src, bytes); return; }
+      if (bytes < (1u << 20) || m_nthreads <= 1) { copy_streaming((char*)dst, (const char*)src, bytes); return; }
       {
         std::lock_guard<std::mutex> lk(m_mutex);
         m_dst = (char*)dst; m_src = (const char*)src; m_bytes = bytes; m_pending = m_nthreads - 1; ++m_generation;
@@ -46,7 +72,7 @@ namespace onk
       if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
       if (n <= 0) n = (int)std::thread::hardware_concurrency();
       if (const char* e = getenv("ONK_HOST_COPY_THREADS")) n = atoi(e);
-      m_nthreads = n < 1 ? 1 : (n > 8 ? 8 : n);
+      m_nthreads = n < 1 ? 1 : (n > 12 ? 12 : n);
       for (int t = 1; t < m_nthreads; t++) std::thread([this, t]{ worker(t); }).detach();
     }
     void slice(int t, char* dst, const char* src, size_t bytes) const
@@ -55,7 +81,7 @@ namespace onk
       const size_t b = (size_t)t * per;
       if (b >= bytes) return;
       const size_t e = (t == m_nthreads - 1 || b + per > bytes) ? bytes : b + per;
-      memcpy(dst + b, src + b, e - b);
+      copy_streaming(dst + b, src + b, e - b);
     }
     void worker(int t)
     {

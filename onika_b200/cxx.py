@@ -52,6 +52,7 @@ REFERENCE_TUTORIAL = "/root/reference/plugins/onikaParallelTutorial"
 REFPLUGIN_BIN = os.path.join(CXX_TESTS, "_refplugins", "run_reference_tutorial")
 
 
+REFERENCE_MSP_DIR = os.path.join(os.path.dirname(REFPLUGIN_BIN), "data")
 REFERENCE_TESTS = os.path.join(os.path.dirname(os.path.dirname(REFERENCE_TUTORIAL)), "tests")
 REFERENCE_GPU_TESTS = ("gpu_uvm_benchmark", "gpu_reduce_min_fp64", "parallel_queue_lane")
 REFERENCE_SOATL_TESTS = ("soatupletest", "soatlserializetest")
@@ -85,6 +86,16 @@ def build_reference_plugins(force: bool = False, verbose: bool = False):
         src = os.path.join(REFERENCE_TESTS, name + ".cpp")
         if os.path.exists(src):
             compile_program([src], reference_test_path(name), extra_flags=["-x", "cu", "-I" + REFERENCE_TESTS], verbose=verbose)
+    # the reference's own application input files (data/config/main-config.msp, data/exemples/*.msp), unchanged: like the
+    # binaries above they land in the git-ignored directory and travel to the GPU box with it
+    import shutil
+    ref_data = os.path.join(os.path.dirname(os.path.dirname(REFERENCE_TUTORIAL)), "data")
+    for sub in ("config", "exemples"):
+        dst = os.path.join(REFERENCE_MSP_DIR, sub)
+        os.makedirs(dst, exist_ok=True)
+        for f in sorted(os.listdir(os.path.join(ref_data, sub))):
+            if f.endswith(".msp"):
+                shutil.copyfile(os.path.join(ref_data, sub, f), os.path.join(dst, f))
     return compile_program([os.path.join(CXX_TESTS, "run_operator.cu")] + srcs, REFPLUGIN_BIN, verbose=verbose)
 
 

@@ -11,11 +11,20 @@
 //               - <operator>
 //       operators run in body order; a consuming slot without a value in the file aliases the latest earlier producing
 //       slot of the same name (INPUT_OUTPUT / OUTPUT), which is how `my_array` travels from one operator to the next
+//   run_operator --app [--config <main-config.msp>] <file.msp> [more.msp ...] [--<key> <value> ...] [dump:<slot>=<file> ...]
+//       the reference's application flow (apps/onika-exec.cpp:21-30, src/core/api.cpp:261-312,833) on its own files: the
+//       documents are layered (config first, user files on top, `--key value` options last; maps merge key by key), the
+//       `configuration` block is set aside, every other top-level key is an operator default / alias / batch definition, and
+//       the `simulation` sequence is built into an operator tree: names resolve through aliases (`run: nop`, `--run run_test`),
+//       names without a factory become batches (`name`, `task_group`, `body`, nested at will), `- op: {slot: value}` items
+//       set slots.  mpi_comm_world / init_cuda / finalize_cuda / global / unit_system / message / nop are stand-ins of the
+//       reference's built-in components: the control plane is out of scope, the chain they form is not.
 // Linked together with UNMODIFIED plugin sources (e.g. the reference's plugins/onikaParallelTutorial/*.cu compiled from
 // where they lie) it shows that plugin code runs on this runtime unchanged.
 #include <onika/scg/operator.h>
 #include <onika/extras/array2d.h>
 #include "msp_reader.h"
+#include "msp_yaml.h"
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -58,6 +67,166 @@ namespace
     std::fwrite( arr->data() , 8 , arr->rows()*arr->columns() , f );
     std::fclose(f);
     return true;
+  }
+
+  // ---------------------------------------------------------------- application mode (--app)
+  // stand-ins of the reference's built-in components named by data/config/main-config.msp (src/scg-builtin-components/*.cpp)
+  struct NopNode : public OperatorNode { void execute() override final {} };
+  struct MessageNode : public OperatorNode
+  {
+    ADD_SLOT( std::string , mesg , INPUT , std::string() );
+    ADD_SLOT( bool , endl , INPUT , true );
+    void execute() override final { std::printf( "%s%s" , mesg->c_str() , *endl ? "\n" : "" ); }
+  };
+  struct InitCudaNode : public OperatorNode
+  {
+    void execute() override final
+    {
+      auto* ctx = global_cuda_ctx();                      // device selection + context: src/scg-builtin-components/init_cuda.cpp:84-225
+      if( ctx == nullptr || ! ctx->has_devices() ) fatal_error() << "init_cuda: no CUDA device" << std::endl;
+      std::printf( "init_cuda: %s, %d SMs\n" , ctx->m_devices[0].m_deviceProp.name , ctx->m_devices[0].m_deviceProp.multiProcessorCount );
+    }
+  };
+  struct FinalizeCudaNode : public OperatorNode { void execute() override final { ONIKA_B200_CHECK( onk_device_sync() ); std::printf("finalize_cuda\n"); } };
+
+  class BatchNode : public OperatorNode
+  {
+  public:
+    std::vector< std::shared_ptr<OperatorNode> > m_ops;
+    void execute() override final { for(auto& op : m_ops) op->run(); }
+  };
+
+  struct AppBuilder
+  {
+    Node defaults;                                        // top-level keys: aliases, operator defaults, batch definitions
+    std::map<std::string,OperatorSlotBase*> producer;     // latest producing slot per name, in creation (= execution) order
+    std::vector<std::string> trace;                       // flattened tree, for the caller to print / check
+    std::string error;
+
+    static bool produces(const OperatorSlotBase* s) { return ! s->is_private() && ( s->direction() == OUTPUT || s->direction() == INPUT_OUTPUT ); }
+    static bool consumes(const OperatorSlotBase* s) { return ! s->is_private() && ( s->direction() == INPUT || s->direction() == INPUT_OUTPUT ); }
+    bool has_factory(const std::string& n) const { for(const auto& k : OperatorNodeFactory::instance()->available_operators()) if( k == n ) return true; return false; }
+    bool fail(const std::string& m) { if( error.empty() ) error = m; return false; }
+
+    bool item(const Node& it, BatchNode* parent, int depth)
+    {
+      if( it.is_scalar() ) return make( it.scalar , Node{} , parent , depth );
+      if( it.is_map() && it.map.size() == 1 ) return make( it.map[0].first , it.map[0].second , parent , depth );
+      return fail( "batch body items must be `name` or `name: parameters`, got " + it.str() );
+    }
+
+    bool make(std::string name, Node params, BatchNode* parent, int depth)
+    {
+      if( depth > 32 ) return fail( "operator definitions nest too deep (alias cycle ?) at " + name );
+      // aliases: `run: nop`, `--run run_test` (src/scg/operator_factory.cpp:219-240)
+      for(int guard=0; guard<32; guard++)
+      {
+        const Node* d = defaults.find(name);
+        if( d != nullptr && d->is_scalar() ) { name = d->scalar; continue; }
+        if( params.is_null() && d != nullptr ) params = *d;
+        break;
+      }
+      if( has_factory(name) )
+      {
+        std::shared_ptr<OperatorNode> op = OperatorNodeFactory::instance()->make_operator( name );
+        op->set_parent( parent );
+        Node values = params;
+        if( params.is_scalar() ) { values = Node{}; values.set( "mesg" , params ); }          // `- message: "text"` (message.cpp yaml_initialize)
+        for(const auto& [sname,slot] : op->slots())
+        {
+          const bool valued = values.is_map() && values.find(sname) != nullptr;
+          auto pit = producer.find(sname);
+          if( ! valued && consumes(slot) && pit != producer.end() && ! slot->share_value_of( * pit->second ) ) return fail( "slot " + sname + " of " + name + ": type differs from its producer" );
+          if( produces(slot) ) producer[sname] = slot;
+        }
+        if( values.is_map() ) for(const auto& [k,v] : values.map)
+        {
+          auto* sl = op->slot(k);
+          if( sl == nullptr ) { if( op->slots().empty() ) continue; return fail( "operator " + name + " has no slot " + k ); }   // slot-less stand-ins accept any parameters
+          if( ! v.is_scalar() || ! sl->set_from_string( v.scalar ) ) return fail( "cannot set slot " + k + " of " + name + " from " + v.str() );
+        }
+        trace.push_back( std::string( size_t(depth)*2 , ' ' ) + name );
+        parent->m_ops.push_back( op );
+        return true;
+      }
+      // no factory: an (implicit) batch, defined by a sequence or by { name, task_group, body }
+      if( params.is_null() ) return fail( "Could not find a operator factory for '" + name + "' (and no default declaration exists for this name)" );
+      const Node* body = params.is_seq() ? & params : params.find("body");
+      if( body == nullptr || ! body->is_seq() ) return fail( "batch '" + name + "' has no body sequence: " + params.str() );
+      auto batch = std::make_shared<BatchNode>();
+      batch->set_name( name );
+      batch->set_parent( parent );
+      if( params.is_map() ) for(const auto& [k,v] : params.map)
+      {
+        if( k == "body" ) continue;
+        if( k == "name" && v.is_scalar() ) batch->set_name( v.scalar );
+        else if( k == "task_group" && v.is_scalar() ) batch->set_task_group( v.scalar == "true" );
+        else return fail( "batch '" + name + "': attribute '" + k + "' is not supported by this runner (control flow is out of scope)" );
+      }
+      trace.push_back( std::string( size_t(depth)*2 , ' ' ) + name + " [batch " + batch->name() + ( batch->task_group() ? ", task_group]" : "]" ) );
+      for(const auto& it : body->seq) if( ! item( it , batch.get() , depth+1 ) ) return false;
+      if( parent != nullptr ) parent->m_ops.push_back( batch );
+      else root = batch;
+      return true;
+    }
+    std::shared_ptr<BatchNode> root;
+  };
+
+  int run_app(int argc, char* argv[])
+  {
+    auto* F = OperatorNodeFactory::instance();
+    for(const char* n : { "nop" , "mpi_comm_world" , "global" , "unit_system" }) F->register_factory( n , make_simple_operator<NopNode> );
+    F->register_factory( "message" , make_simple_operator<MessageNode> );
+    F->register_factory( "init_cuda" , make_simple_operator<InitCudaNode> );
+    F->register_factory( "finalize_cuda" , make_simple_operator<FinalizeCudaNode> );
+
+    Node doc; doc.kind = Node::Map;
+    SlotValues dumps;
+    std::vector<std::string> files;
+    for(int i=2;i<argc;i++)
+    {
+      std::string a = argv[i];
+      if( a == "--config" && i+1 < argc ) { files.insert( files.begin() , argv[++i] ); continue; }
+      if( a.rfind("dump:",0) == 0 && a.find('=') != std::string::npos ) { dumps.push_back( { a.substr(5,a.find('=')-5) , a.substr(a.find('=')+1) } ); continue; }
+      if( a.rfind("--",0) != 0 ) { files.push_back( a ); continue; }
+      // `--a-b value` -> { a: { b: value } } layered on top of the files (src/yaml/cmdline.cpp:54-84); applied after the loop
+    }
+    for(const auto& f : files)
+    {
+      Node d; std::string err;
+      if( ! parse_yaml_file( f , d , err ) ) { std::fprintf(stderr,"%s\n",err.c_str()); return 2; }
+      doc = merge_nodes( doc , d );
+    }
+    for(int i=2;i<argc;i++)
+    {
+      std::string a = argv[i];
+      if( a == "--config" ) { ++i; continue; }
+      if( a.rfind("--",0) != 0 ) continue;
+      std::string val = "true";
+      if( i+1 < argc && std::string(argv[i+1]).rfind("--",0) != 0 && std::string(argv[i+1]).rfind("dump:",0) != 0 ) val = argv[++i];
+      Node v; std::string err;
+      if( ! parse_yaml_text( "x: " + val , "<command line>" , v , err ) ) { std::fprintf(stderr,"%s\n",err.c_str()); return 2; }
+      Node leaf = v.map[0].second;
+      std::string key = a.substr(2);
+      for(size_t p = key.rfind('-'); p != std::string::npos; p = key.rfind('-'))
+      { Node up; up.set( key.substr(p+1) , leaf ); leaf = up; key = key.substr(0,p); }
+      Node top; top.set( key , leaf );
+      doc = merge_nodes( doc , top );
+    }
+    const Node* sim = doc.find("simulation");
+    if( sim == nullptr ) { std::fprintf(stderr,"no `simulation` in the loaded files (pass the reference's data/config/main-config.msp with --config)\n"); return 2; }
+    AppBuilder B;
+    B.defaults.kind = Node::Map;
+    for(const auto& kv : doc.map) if( kv.first != "simulation" && kv.first != "configuration" ) B.defaults.map.push_back( kv );
+    if( ! B.make( "simulation" , *sim , nullptr , 0 ) ) { std::fprintf(stderr,"%s\n",B.error.c_str()); return 2; }
+    std::printf("simulation graph:\n");
+    for(const auto& t : B.trace) std::printf("  %s\n", t.c_str());
+    B.root->run();
+    for(const auto& d : dumps)
+      if( B.producer.find(d.first) == B.producer.end() || ! dump_array( B.producer[d.first] , d.second ) ) { std::fprintf(stderr,"cannot dump slot %s\n",d.first.c_str()); return 2; }
+    B.root->m_ops.clear();
+    B.root.reset();
+    return 0;
   }
 
   int run_msp(int argc, char* argv[])
@@ -125,6 +294,7 @@ int main(int argc, char* argv[])
     return 2;
   }
   if( std::strcmp( argv[1] , "--msp" ) == 0 ) return run_msp( argc , argv );
+  if( std::strcmp( argv[1] , "--app" ) == 0 ) return run_app( argc , argv );
 
   std::shared_ptr<OperatorNode> op;
   try { op = OperatorNodeFactory::instance()->make_operator( argv[1] ); }

@@ -332,3 +332,66 @@ int main()
     if os.path.isdir(ref_inc):
         theirs = build_and_run(ref_inc, "theirs")
         assert theirs == ours
+
+
+def test_msp_yaml_reader_on_the_reference_files(tmp_path):
+    """tests/cxx/msp_yaml.h (what `run_operator --app` reads): block maps / sequences, `- key:` items continuing as maps, nested
+    flow maps, quoted scalars with escapes, comments, document layering -- on the reference's own data/config/main-config.msp
+    and data/exemples/concurrent_block_parallel.msp (read in place; skipped parts when the tree is absent) and on edge cases"""
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = tmp_path / "yaml_probe.cpp"
+    src.write_text(r'''
+#include "msp_yaml.h"
+int main(int argc, char* argv[])
+{
+  msp::Node doc; doc.kind = msp::Node::Map;
+  for(int i=1;i<argc;i++)
+  {
+    msp::Node d; std::string err;
+    if( ! msp::parse_yaml_file( argv[i] , d , err ) ) { std::fprintf(stderr,"%s\n",err.c_str()); return 3; }
+    doc = msp::merge_nodes( doc , d );
+  }
+  for(const auto& kv : doc.map)
+  {
+    std::string v = kv.second.str();
+    for(auto& c : v) if( c == '\n' ) c = '$';
+    std::printf("%s => %s\n", kv.first.c_str(), v.c_str());
+  }
+  return 0;
+}
+''')
+    exe = tmp_path / "yaml_probe"
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", f"-I{os.path.join(here, 'cxx')}", str(src), "-o", str(exe)], env=_env())
+
+    def parse(*paths):
+        r = subprocess.run([str(exe), *map(str, paths)], capture_output=True, text=True)
+        return r.returncode, dict(ln.split(" => ", 1) for ln in r.stdout.splitlines()), r.stderr
+
+    a = tmp_path / "a.msp"
+    a.write_text('top:\n  sub:\n    deep: 1   # comment\n    text: "a # not a comment: still text"\nrun: nop\nlist:\n- x\n- y: { k: [1, 2, {z: 3}] }\n'
+                 'sim:\n  - msg: "line\\nbreak"\n  - plain\n  - unit:\n      verbose: true\n      map: { a: b , c: d }\n  - op: { s: 1 }\n    extra: 2\n  -\n    nested: block\n'
+                 'multi: { a: 1 ,\n          b: 2 }\n')
+    rc, d, err = parse(a)
+    assert rc == 0, err
+    assert d["top"] == "{sub:{deep:1,text:a # not a comment: still text}}" and d["run"] == "nop"
+    assert d["list"] == "[x,{y:{k:[1,2,{z:3}]}}]"
+    assert d["sim"] == "[{msg:line$break},plain,{unit:{verbose:true,map:{a:b,c:d}}},{op:{s:1},extra:2},{nested:block}]"
+    assert d["multi"] == "{a:1,b:2}"
+    b = tmp_path / "b.msp"
+    b.write_text("run: run_test\ntop:\n  sub:\n    deep: 2\n  other: 3\nlist: [z]\n")
+    rc, d, _ = parse(a, b)                      # layering: maps merge key by key, scalars and sequences are replaced
+    assert rc == 0 and d["run"] == "run_test" and d["top"] == "{sub:{deep:2,text:a # not a comment: still text},other:3}" and d["list"] == "[z]"
+    for bad, where in (("a:\n    b: 1\n  c: 2\n", ":3:"), ("a: { b: 1\n", ":1:"), ("a:\n  - x\n  y: 1\n", ":3:"), ("a: [1, , 2]\n", ":1:"), ("  a: 1\n", ":1:")):
+        f = tmp_path / "bad.msp"
+        f.write_text(bad)
+        rc, _, err = parse(f)
+        assert rc == 3 and where in err, (bad, err)
+    ref = "/root/reference/data"
+    if os.path.isdir(ref):
+        rc, d, err = parse(os.path.join(ref, "config", "main-config.msp"), os.path.join(ref, "exemples", "concurrent_block_parallel.msp"))
+        assert rc == 0, err
+        assert d["configuration"] == "{logging:{debug:false}}" and d["run"] == "nop" and d["init"] == "nop"
+        assert d["run_test"] == "{name:concurrent_block_parallel_test,task_group:true,body:[{concurrent_block_parallel:{value:2.3,rows:4,columns:65536,iter_count:65536}}]}"
+        sim = d["simulation"]
+        assert sim.startswith("[{message:") and sim.endswith(",mpi_comm_world,init_cuda,global,{unit_system:{verbose:true,unit_system:{length:meter,mass:kilogram,time:second,"
+                                                                "charge:coulomb,temperature:kelvin,amount:mol,luminosity:candela,angle:radian,energy:joule}}},init,run,finalize_cuda]")

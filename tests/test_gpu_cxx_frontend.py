@@ -481,6 +481,57 @@ def test_reference_plugins_from_msp_example_shape(tmp_path):
     assert np.allclose(_load_array(out), x, rtol=1e-10, atol=0)     # pow/sin: libm vs libdevice, few iterations (the map is chaotic)
 
 
+def _reference_msp(*parts):
+    from onika_b200 import cxx
+    path = os.path.join(cxx.REFERENCE_MSP_DIR, *parts)
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not staged (needs /root/reference at build time)")
+    return path
+
+
+def _run_app(tmp_path, *args):
+    exe = _refplugins()
+    out = os.path.join(tmp_path, "app.bin")
+    r = subprocess.run([exe, "--app", *[a.replace("@OUT2", out + "2").replace("@OUT", out) for a in args]], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.returncode, r.stdout[-2500:], r.stderr[-1500:])
+    return out, r.stdout
+
+
+def test_reference_application_chain_with_nested_batches(tmp_path):
+    """the reference's own data/config/main-config.msp (unchanged) as the base document -- its simulation chain
+    message / mpi_comm_world / init_cuda / global / unit_system / init / run / finalize_cuda -- with a user file layered on
+    top that turns `run` into nested batches of unchanged tutorial plugins; `my_array` is connected through all of them"""
+    out, stdout = _run_app(tmp_path, "--config", _reference_msp("config", "main-config.msp"), os.path.join(MSP_DIR, "nested_app.msp"), "dump:my_array=@OUT")
+    graph = [ln.strip() for ln in stdout.split("simulation graph:")[1].splitlines() if ln.strip()]
+    names = [g.split()[0] for g in graph[:14]]
+    assert names == ["simulation", "message", "mpi_comm_world", "init_cuda", "global", "unit_system", "nop", "my_run", "first_stage",
+                     "synchronous_block_parallel", "second_stage", "async_block_parallel", "synchronous_block_parallel", "finalize_cuda"]
+    assert "[batch nested_run]" in stdout and "first_stage [batch first_stage, task_group]" in stdout
+    assert "init_cuda:" in stdout and "SMs" in stdout and stdout.rstrip().endswith("finalize_cuda")
+    want = np.zeros((1024, 1024))
+    for v in (1.1, 1.2, 1.3):
+        want += v
+    assert np.array_equal(_load_array(out), want)
+
+
+def test_reference_example_msp_unchanged(tmp_path):
+    """the reference's own example input, data/exemples/concurrent_block_parallel.msp layered on data/config/main-config.msp,
+    run the way the reference's application runs it (`onika-exec <file> --run run_test`, apps/onika-exec.cpp:21-30): the
+    task-group batch holds the unchanged concurrent_block_parallel plugin with the file's parameters (4 x 65536 elements,
+    65536 iterations of the pow/sin map on two lanes).  The map is chaotic over that many iterations, so the arrays are
+    checked for what must hold exactly: shape, both arrays identical (same operations from the same zeros), finite, and the
+    last value-add applied; bit parity of the same sequence with short iteration counts is test_parallel_queue_lane_scenarios"""
+    cfg, ex = _reference_msp("config", "main-config.msp"), _reference_msp("exemples", "concurrent_block_parallel.msp")
+    out1, stdout = _run_app(tmp_path, "--config", cfg, ex, "--run", "run_test", "dump:array1=@OUT", "dump:array2=@OUT2")
+    assert "run_test [batch concurrent_block_parallel_test, task_group]" in stdout and "All operations have terminated" in stdout
+    a1, a2 = _load_array(out1), _load_array(out1 + "2")
+    assert a1.shape == (4, 65536) and np.array_equal(a1, a2) and np.isfinite(a1).all()
+    assert np.all(a1 == a1[0, 0])                                 # every element went through the same map from 0.0
+    # without the override `run` stays the reference's `nop`: the chain runs, the example batch does not
+    _, stdout = _run_app(tmp_path, "--config", cfg, ex)
+    assert "All operations have terminated" not in stdout and stdout.rstrip().endswith("finalize_cuda")
+
+
 def _run_reference_test(name, stdin):
     from onika_b200 import cxx
     exe = cxx.reference_test_path(name)

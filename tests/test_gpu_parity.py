@@ -575,6 +575,12 @@ def test_host_buffer_entry_points(ob, orc):
         assert P.host_reduce(_capi.OP_MIN, src) == orc.reduce_min(d)
         assert P.host_reduce(_capi.OP_MAX, src) == orc.reduce_max(d)
         assert abs(P.host_reduce(_capi.OP_SUM, src) - orc.reduce_sum_ld(d)) <= SUM_RTOL * np.abs(d).sum()
+    # pageable input through the pinned staging ring: more chunks than ring slots, source only 8-byte aligned, ragged tail
+    big = lcg_uniform((40 << 20) + 778, 78, -1, 1)
+    odd = big[1:]
+    assert odd.ctypes.data % 16 == 8
+    assert P.host_reduce(_capi.OP_MIN, odd) == orc.reduce_min(odd) and P.host_reduce(_capi.OP_MAX, odd) == orc.reduce_max(odd)
+    assert abs(P.host_reduce(_capi.OP_SUM, odd) - orc.reduce_sum_ld(odd)) <= SUM_RTOL * np.abs(odd).sum()
     x, y = lcg_uniform(n, 1, -1, 1), lcg_uniform(n, 2, -1, 1)
     yo = y.copy()
     orc.axpy(yo, x, 0.5)
