@@ -348,21 +348,61 @@ def secondary_kernels(ob, torch):
     t = timed(lambda: fa.parallel_apply_rmw(1.0000001, c), reps=5)
     out["C3_soatl_rmw_8x64Mi"] = {"GB/s": round(128 * n / t / 1e9, 1), "ms": round(t * 1e3, 4), "bytes_per_elem": 128}
     fa.clear()
-    counts = poisson_counts(128 ** 3)
-    cg = cellgrid.CellGrid(counts, 64, 16, (8, 8, 8, 8), 64)
-    cg.arena.view(torch.float64).uniform_(-1, 1)
-    npart = int(counts.sum())
-    alg = 8 * npart + cg.ncells * (8 + 8 + 4 + 4)
-    t = flushed(lambda: cg.cell_sum(3))
-    out["C4_cell_sum_128^3"] = {"GB/s": round(alg / t / 1e9, 1), "ms": round(t * 1e3, 4), "algorithmic_bytes": alg,
-                                "arena_bytes": cg.arena_bytes, "particles": npart, "l2": "flushed", "variant": "field e only (8 B/particle + 24 B/cell tables+out)"}
-    del cg
-    fm = cellgrid.FieldMajorCellGrid(counts, nfields=1)
-    fm.columns[0].uniform_(-1, 1)
-    alg = 8 * npart + fm.ncells * (8 + 8)
-    t = flushed(lambda: fm.cell_sum(0))
-    out["C4_cell_sum_128^3_field_major"] = {"GB/s": round(alg / t / 1e9, 1), "ms": round(t * 1e3, 4), "algorithmic_bytes": alg, "particles": npart, "l2": "flushed",
-                                            "variant": "same cells, field-major layout: 8 B/particle + 16 B/cell (offset + out)"}
+    # config C4 at the BASELINE size (128^3 cells, working set ~ L2-sized for the e-only variant: L2 flushed) and at 256^3
+    # cells (2.4 GB of e lines / 12.3 GB arena: steady state); three variants each, as SURVEY 8(d) asks to state:
+    #   field e only, per-cell SOATL blocks  : 8 B/particle + 24 B/cell (offset 8, size 4, capacity 4, out 8)
+    #   all 4 fields, per-cell SOATL blocks  : 32 B/particle + 48 B/cell (tables 16 + 4 outputs) -- the arena is one contiguous stream
+    #   field e only, field-major layout     : 8 B/particle + 16 B/cell
+    for side in (128, 256):
+        counts = poisson_counts(side ** 3)
+        npart = int(counts.sum())
+        tag = f"C4_cell_sum_{side}^3"
+        run = flushed if side == 128 else (lambda fn: timed(fn, reps=5, warm=2))
+        cg = cellgrid.CellGrid(counts, 64, 16, (8, 8, 8, 8), 64)
+        cg.arena.view(torch.float64).uniform_(-1, 1)
+        alg = 8 * npart + cg.ncells * (8 + 8 + 4 + 4)
+        t = run(lambda: cg.cell_sum(3))
+        out[tag] = {"GB/s": round(alg / t / 1e9, 1), "ms": round(t * 1e3, 4), "algorithmic_bytes": alg, "arena_bytes": cg.arena_bytes, "particles": npart,
+                    "l2": "flushed" if side == 128 else "working set larger than L2", "variant": "field e only (8 B/particle + 24 B/cell tables+out)"}
+        alg = 32 * npart + cg.ncells * (8 + 4 + 4 + 32)
+        t = run(lambda: cg.cell_sum_all_fields())
+        out[tag + "_all_fields"] = {"GB/s": round(alg / t / 1e9, 1), "ms": round(t * 1e3, 4), "algorithmic_bytes": alg, "arena_bytes": cg.arena_bytes,
+                                    "arena_stream_GB/s": round((cg.arena_bytes + cg.ncells * 48) / t / 1e9, 1), "particles": npart,
+                                    "variant": "all 4 fields of every cell block (32 B/particle + 48 B/cell): the arena streams as one range, chunk padding included in arena_stream"}
+        del cg
+        fm = cellgrid.FieldMajorCellGrid(counts, nfields=1)
+        fm.columns[0].uniform_(-1, 1)
+        alg = 8 * npart + fm.ncells * (8 + 8)
+        t = run(lambda: fm.cell_sum(0))
+        out[tag + "_field_major"] = {"GB/s": round(alg / t / 1e9, 1), "ms": round(t * 1e3, 4), "algorithmic_bytes": alg, "particles": npart,
+                                     "variant": "same cells, field-major layout: 8 B/particle + 16 B/cell (offset + out)"}
+        del fm
+        torch.cuda.empty_cache()
+    # the GENERIC paths of the C++ front end (user functors / operators, no typed entry point), timed by the front-end test
+    # program in its own process: config C4 written the application way (one block per cell) and the two C3 operators
+    # through soatl::parallel_apply_simd
+    try:
+        import tempfile
+        import numpy as np
+        exe = os.path.join(ROOT, "tests", "cxx", "frontend_test")
+        if os.path.exists(exe):
+            with tempfile.TemporaryDirectory() as tmp:
+                o = os.path.join(tmp, "o.bin")
+                subprocess.run([exe, "cells_generic_perf", o, str(128 ** 3)], check=True, capture_output=True, timeout=300)
+                us = np.fromfile(o, dtype=np.float64, count=6)
+                out["C4_generic_functor_path_128^3_us"] = {
+                    "one_block_of_128_threads_per_cell": round(float(us[0]), 1), "one_block_of_32_threads_per_cell": round(float(us[1]), 1),
+                    "sub_block_items_32_16_8_threads": [round(float(v), 1) for v in us[3:6]], "typed_field_major_kernel": round(float(us[2]), 1),
+                    "what": "block_parallel_for(ncells, functor) with ONIKA_CU_BLOCK_SIMD_FOR + block_reduce_add, unchanged functor source; sub-block items = several cells per CTA (BlockParallelForFunctorTraits::SubBlockItems)"}
+                subprocess.run([exe, "soatl_apply", o, str(64 << 20), "1"], check=True, capture_output=True, timeout=300)
+                us = np.fromfile(o, dtype=np.float64, count=4)
+                n = 64 << 20
+                out["C3_soatl_parallel_apply_simd_generic_64Mi"] = {
+                    "rmw_8_fields_GB/s": round(128 * n / float(us[0]) / 1e3, 1), "rmw_8_fields_typed_GB/s": round(128 * n / float(us[1]) / 1e3, 1),
+                    "benchmark_cpp_operator_GB/s": round(32 * n / float(us[2]) / 1e3, 1), "benchmark_cpp_operator_typed_GB/s": round(32 * n / float(us[3]) / 1e3, 1),
+                    "what": "extended lambdas through the vectorised generic kernel of include/onika/soatl/compute.h vs the typed entry points on the same arrays"}
+    except Exception as ex:  # pragma: no cover
+        out["generic_paths_error"] = str(ex)[:200]
     return out
 
 

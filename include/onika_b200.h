@@ -253,6 +253,13 @@ int onk_cell_sum_f64(const void* arena_dev, const uint64_t* cell_off_dev, const 
                      const uint32_t* cell_cap_dev, uint64_t ncells, uint64_t align,
                      const uint32_t* field_bytes, int nfields, int field,
                      double* cell_sum_dev, double* total_dev, int lane);
+/* per-cell sums of EVERY field of the cell blocks (all fields fp64): cell_sums_dev[c*nfields + k] is the in-order sum of field k
+ * over the particles of cell c (bit-identical to the host loop), totals_dev[k] (optional) the fixed-order sum over the cells.
+ * With all fields wanted the per-cell layout is one contiguous stream (32 B per particle for rx,ry,rz,e: SURVEY 8d, C4 "all 4
+ * fields streamed"); arena_bytes = size of the arena allocation (the layout value returned by onk_cell_grid_layout). */
+int onk_cell_sum_fields_f64(const void* arena_dev, uint64_t arena_bytes, const uint64_t* cell_off_dev, const uint32_t* cell_size_dev,
+                            const uint32_t* cell_cap_dev, uint64_t ncells, uint64_t align, const uint32_t* field_bytes, int nfields,
+                            double* cell_sums_dev, double* totals_dev, int lane);
 /* the same per-cell sum over a FIELD-MAJOR grid: `values_dev` is the summed field of all cells back to back, cell c owns
  * [cell_begin[c], cell_begin[c+1]) (ncells+1 offsets).  Same per-cell bits as the loop above (particle order); the layout
  * turns the kernel into a pure stream (8 B per particle + 16 B per cell of traffic, no padding between cells). */

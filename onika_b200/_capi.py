@@ -91,6 +91,7 @@ PROTOTYPES = {
     "onk_cell_grid_layout": (u64, [P(u32), u64, u64, u64, P(u32), i32, u64, P(u32), P(u64)]),
     "onk_cell_sum_f64": (i32, [vp, vp, vp, vp, u64, u64, P(u32), i32, i32, vp, vp, i32]),
     "onk_cell_sum_packed_f64": (i32, [vp, u64, vp, u64, vp, vp, i32]),
+    "onk_cell_sum_fields_f64": (i32, [vp, u64, vp, vp, vp, u64, u64, P(u32), i32, vp, vp, i32]),
     "onk_host_reduce_f64": (i32, [i32, vp, u64, vp]),
     "onk_host_axpy_f64": (i32, [vp, vp, dbl, u64]),
     "onk_host_value_add_f64": (i32, [vp, u64, u64, dbl]),

@@ -74,6 +74,19 @@ class CellGrid:
         return sums, total
 
 
+    def cell_sum_all_fields(self, with_totals: bool = True, lane: int = LANE_DEFAULT):
+        """per-cell sums of every (fp64) field in one pass over the arena (onk_cell_sum_fields_f64); returns
+        (ncells x nfields tensor, nfields totals or None)"""
+        import torch
+        nf = len(self.field_bytes)
+        sums = torch.empty((max(self.ncells, 1), nf), dtype=torch.float64, device=self.device)[: self.ncells]
+        totals = torch.zeros(nf, dtype=torch.float64, device=self.device) if with_totals else None
+        fb = (C.c_uint32 * nf)(*self.field_bytes)
+        check(lib().onk_cell_sum_fields_f64(ptr(self.arena), self.arena_bytes, ptr(self.cell_off), ptr(self.cell_size), ptr(self.cell_cap), self.ncells,
+                                            self.align, fb, nf, ptr(sums), ptr(totals) if with_totals else None, lane))
+        return sums, totals
+
+
 class FieldMajorCellGrid:
     """Cell grid stored FIELD-MAJOR: every field is one contiguous column over all cells, cell c owning
     [cell_begin[c], cell_begin[c+1]) in each column.  The B200-first layout of config C4: per-cell work streams the

@@ -620,6 +620,214 @@ namespace onk
   }
 }
 
+namespace onk
+{
+  // ---- per-cell sums of EVERY fp64 field of the cell blocks (config C4, "all four fields streamed": 32 B per particle) ----
+  // When all the fields of a cell are wanted the per-cell layout IS a contiguous stream: cell blocks lie back to back in the
+  // arena, so a tile of consecutive cells is one byte range.  The arena is described to the TMA unit as a 2D tensor of
+  // 128-byte rows; a tile of NT/nfields cells is the box of BOXROWS rows that starts at the row holding the tile's first
+  // byte -- ONE cp.async.bulk.tensor issued by one thread, laid out with the 128-byte swizzle (16-byte chunk c of row r at
+  // chunk c ^ (r & 7)) so that the threads, each folding its own column from its own row(s), spread over the banks.  Thread t
+  // owns column (cell t / nfields, field t % nfields) and folds it in particle order (bit-identical to the host loop); the
+  // nfields sums of a cell leave as consecutive doubles (coalesced: thread t -> element t of the tile's output).  Columns
+  // that reach beyond the box (dense tiles) or beyond the last full row of the arena finish from global memory.  Tiles are
+  // drawn from a global ticket one tile ahead, as in the field-major kernel above.  Per-field totals: per-CTA partials in
+  // shared memory (thread order), then the ticketed last CTA folds the CTAs' partials in index order.
+  constexpr int CELL_ALLF_MAX = 8;
+  struct CellAllFieldsParams { uint32_t nfields; uint32_t align_mask; };
+
+  template<int CTAS, int NT, int BOXROWS>
+  __global__ void __launch_bounds__(NT, CTAS)
+  cell_sum_fields_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ arena, uint64_t nrows_full,
+                             const uint64_t* __restrict__ cell_off, const uint32_t* __restrict__ cell_size, const uint32_t* __restrict__ cell_cap,
+                             uint64_t ncells, const __grid_constant__ CellAllFieldsParams prm,
+                             double* __restrict__ cell_sums, double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ totals)
+  {
+    extern __shared__ unsigned char dyn_smem[];
+    __shared__ unsigned long long s_next_tile[2];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ double s_thread_total[NT];
+    __shared__ bool s_is_last;
+    constexpr unsigned BOX_BYTES = BOXROWS * 128u;
+    const unsigned tile_smem = (smem_u32(dyn_smem) + 1023u) & ~1023u;     // the swizzle pattern is anchored at 1024-byte boundaries
+    const unsigned bar = smem_u32(&s_bar);
+    const unsigned nf = prm.nfields;
+    const unsigned cpt = (unsigned)NT / nf;                                // cells per tile
+    const unsigned lc = threadIdx.x / nf, f = threadIdx.x - lc * nf;       // this thread's column: (local cell, field)
+    const bool active = lc < cpt;
+    const uint64_t ntiles = (ncells + cpt - 1) / cpt;
+    unsigned* tile_counter = ticket + 1;
+    double thread_total = 0.0;
+    bool drawing = true;
+    if (threadIdx.x == 0)
+    {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    auto draw = [&](int slot)                                             // thread 0 only
+    {
+      unsigned long long t = ~0ull;
+      if (drawing)
+      {
+        const unsigned old = atomicAdd(tile_counter, 1u);
+        t = (unsigned long long)gridDim.x + old;
+        if (t >= ntiles) drawing = false;
+        if ((uint64_t)old + 1u == ntiles) atomicExch(tile_counter, 0u);   // the last draw of the launch
+      }
+      s_next_tile[slot] = t;
+    };
+
+    // tables of the tile after the current one, loaded while the current one is in flight
+    uint64_t nx_base = 0, nx_col = 0; uint32_t nx_sz = 0;
+    auto load_tables = [&](uint64_t tile)
+    {
+      nx_base = nx_col = 0; nx_sz = 0;
+      if (tile < ntiles)
+      {
+        const uint64_t c0 = tile * cpt, c = c0 + lc;
+        nx_base = __ldg(cell_off + c0);
+        if (active && c < ncells)
+        {
+          const uint32_t cap = __ldg(cell_cap + c);
+          const uint64_t stride = ((uint64_t)cap * 8ull + prm.align_mask) & ~(uint64_t)prm.align_mask;    // fp64 column of FieldArrays<align,...>
+          nx_col = __ldg(cell_off + c) + (uint64_t)f * stride;
+          nx_sz = __ldg(cell_size + c);
+        }
+      }
+    };
+
+    uint64_t col = 0, row0 = 0; uint32_t sz = 0, cnt = 0;
+    auto issue = [&](uint64_t following)
+    {
+      row0 = nx_base >> 7;                                                // first 128-byte row of the box
+      col = nx_col; sz = nx_sz;
+      const uint64_t rows_avail = row0 < nrows_full ? nrows_full - row0 : 0;
+      cnt = (uint32_t)((rows_avail < (uint64_t)BOXROWS ? rows_avail : (uint64_t)BOXROWS) << 4);     // doubles of the box that exist
+      if (threadIdx.x == 0)
+      {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(BOX_BYTES) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     :: "r"(tile_smem), "l"(&tmap), "r"(0), "r"((int)row0), "r"(bar) : "memory");
+      }
+      load_tables(following);
+    };
+    auto slot_addr = [&](uint32_t q) -> unsigned                          // double q of the box, swizzled
+    {
+      const uint32_t row = q >> 4;
+      return tile_smem + (row << 7) + ((((q >> 1) ^ row) & 7u) << 4) + ((q & 1u) << 3);
+    };
+
+    uint64_t cur = blockIdx.x;
+    if (threadIdx.x == 0) draw(0);
+    load_tables(cur);
+    __syncthreads();                                                      // barrier initialised, first ticket visible
+    uint64_t nxt = s_next_tile[0];
+    if (cur < ntiles) issue(nxt);
+    unsigned phase = 0;
+
+    for (int slot = 1; cur < ntiles; slot ^= 1)                           // CTA-uniform
+    {
+      unsigned landed = 0;
+      while (!landed)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(landed) : "r"(bar), "r"(phase) : "memory");
+      phase ^= 1u;
+      if (threadIdx.x == 0) draw(slot);                                   // ticket of the tile after the next one
+      const uint64_t c = cur * cpt + lc;
+      if (active && c < ncells)
+      {
+        const uint64_t q0 = (col - (row0 << 7)) >> 3;                     // first double of the column, relative to the box
+        const uint64_t qe = q0 + sz;
+        const uint32_t staged_end = (uint32_t)(qe < (uint64_t)cnt ? qe : (q0 < (uint64_t)cnt ? (uint64_t)cnt : q0));
+        double s = 0.0;
+        uint32_t q = (uint32_t)q0;
+        if (q0 < (uint64_t)cnt)                                           // particle order
+        {
+          if ((q & 1u) && q < staged_end) { s = __dadd_rn(s, lds64_u32(slot_addr(q))); ++q; }
+          for (; q + 2u <= staged_end; q += 2u)
+          {
+            double x0, x1; lds128_u32(slot_addr(q), x0, x1);
+            s = __dadd_rn(s, x0); s = __dadd_rn(s, x1);
+          }
+          if (q < staged_end) { s = __dadd_rn(s, lds64_u32(slot_addr(q))); ++q; }
+        }
+        if (qe > (uint64_t)staged_end)                                    // beyond the box / the last full row: global memory
+        {
+          const double* g = reinterpret_cast<const double*>(arena + col);
+          const uint64_t done = (q0 < (uint64_t)cnt) ? (uint64_t)staged_end - q0 : 0ull;
+          for (uint64_t i = done; i < (uint64_t)sz; i++) s = __dadd_rn(s, ld_stream_ro1(g + i));
+        }
+        cell_sums[c * nf + f] = s;
+        thread_total = __dadd_rn(thread_total, s);
+      }
+      __syncthreads();                                                    // everybody is done reading the tile; the new ticket is visible
+      cur = nxt;
+      nxt = s_next_tile[slot];
+      if (cur < ntiles) issue(nxt);
+    }
+
+    // per-field totals
+    if (totals == nullptr) return;
+    s_thread_total[threadIdx.x] = active ? thread_total : 0.0;
+    __syncthreads();
+    if (threadIdx.x < nf)
+    {
+      double r = 0.0;
+      for (unsigned t = threadIdx.x; t < cpt * nf; t += nf) r = __dadd_rn(r, s_thread_total[t]);     // thread order: fixed
+      partials[(size_t)blockIdx.x * CELL_ALLF_MAX + threadIdx.x] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      __threadfence();
+      s_is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_is_last)
+    {
+      __threadfence();
+      if (threadIdx.x < nf)
+      {
+        double r = 0.0;
+        for (unsigned b = 0; b < gridDim.x; b++) r = __dadd_rn(r, __ldcg(partials + (size_t)b * CELL_ALLF_MAX + threadIdx.x));
+        totals[threadIdx.x] = r;
+      }
+      if (threadIdx.x == 0) *ticket = 0u;
+    }
+  }
+
+  // fallback for arenas the tensor map cannot describe (unaligned base, less than one row): one thread per column, global loads
+  __global__ void __launch_bounds__(THREADS)
+  cell_sum_fields_plain_kernel(const uint8_t* __restrict__ arena, const uint64_t* __restrict__ cell_off, const uint32_t* __restrict__ cell_size,
+                               const uint32_t* __restrict__ cell_cap, uint64_t ncells, const __grid_constant__ CellAllFieldsParams prm,
+                               double* __restrict__ cell_sums)
+  {
+    const uint64_t ncol = ncells * prm.nfields;
+    for (uint64_t t = (uint64_t)blockIdx.x * THREADS + threadIdx.x; t < ncol; t += (uint64_t)gridDim.x * THREADS)
+    {
+      const uint64_t c = t / prm.nfields; const unsigned f = (unsigned)(t - c * prm.nfields);
+      const uint64_t stride = ((uint64_t)__ldg(cell_cap + c) * 8ull + prm.align_mask) & ~(uint64_t)prm.align_mask;
+      const double* g = reinterpret_cast<const double*>(arena + __ldg(cell_off + c) + (uint64_t)f * stride);
+      const uint32_t n = __ldg(cell_size + c);
+      double s = 0.0;
+      for (uint32_t i = 0; i < n; i++) s = __dadd_rn(s, ld_stream_ro1(g + i));
+      cell_sums[t] = s;
+    }
+  }
+
+  // totals of the plain path: column f of the ncells x nfields result, one CTA, fixed order (rarely used: tiny or odd arenas)
+  __global__ void __launch_bounds__(THREADS)
+  cell_sum_fields_totals_kernel(const double* __restrict__ cell_sums, uint64_t ncells, unsigned nf, double* __restrict__ totals)
+  {
+    for (unsigned f = 0; f < nf; f++)
+    {
+      double r = 0.0;
+      for (uint64_t c = threadIdx.x; c < ncells; c += THREADS) r = __dadd_rn(r, cell_sums[c * nf + f]);
+      r = block_reduce<ONK_OP_SUM, THREADS>(r);
+      if (threadIdx.x == 0) totals[f] = r;
+    }
+  }
+}
+
 using namespace onk;
 
 extern "C" {
@@ -763,6 +971,69 @@ int onk_cell_sum_packed_f64(const double* values_dev, uint64_t nvalues, const ui
   if (shape == 1) ONK_PK_GO(5, 256); else if (shape == 2) ONK_PK_GO(3, 512); else ONK_PK_GO(10, 128);
 #undef ONK_PK_GO
   ONK_CHECK_LAUNCH(); count_launch();
+  return ONK_OK;
+}
+
+int onk_cell_sum_fields_f64(const void* arena_dev, uint64_t arena_bytes, const uint64_t* cell_off_dev, const uint32_t* cell_size_dev,
+                            const uint32_t* cell_cap_dev, uint64_t ncells, uint64_t align, const uint32_t* field_bytes, int nfields,
+                            double* cell_sums_dev, double* totals_dev, int lane)
+{
+  ONK_REQUIRE(nfields >= 1 && nfields <= CELL_ALLF_MAX && field_bytes != nullptr, "onk_cell_sum_fields_f64: 1..%d fields", CELL_ALLF_MAX);
+  for (int k = 0; k < nfields; k++) ONK_REQUIRE(field_bytes[k] == 8, "onk_cell_sum_fields_f64: field %d is not fp64", k);
+  ONK_REQUIRE(align >= 8 && (align & (align - 1)) == 0, "onk_cell_sum_fields_f64: alignment must be a power of two >= 8 (fp64 columns)");
+  Lane* L; if (int rc = lane_get(lane, &L)) return rc;
+  if (ncells == 0)
+  {
+    if (totals_dev) ONK_CUDA(cudaMemsetAsync(totals_dev, 0, sizeof(double) * nfields, L->stream));
+    return ONK_OK;
+  }
+  ONK_REQUIRE(arena_dev && cell_off_dev && cell_size_dev && cell_cap_dev && cell_sums_dev, "onk_cell_sum_fields_f64: null pointer");
+  ONK_REQUIRE(((uintptr_t)arena_dev & 7) == 0, "onk_cell_sum_fields_f64: arena is not 8-byte aligned");
+  CellAllFieldsParams prm{ (uint32_t)nfields, (uint32_t)(align - 1) };
+  const uint64_t nrows_full = arena_bytes / 128;
+  static const bool allow_tma = []{ const char* e = getenv("ONK_CELLF_KERNEL"); return !(e && e[0] == 'p'); }();
+  if (allow_tma && ((uintptr_t)arena_dev & 15) == 0 && nrows_full > 0 && nrows_full < (1ull << 31))
+  {
+    typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_t encode = nullptr;
+    if (!encode)
+    {
+      void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+      ONK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+      if (!fn) { set_error("onk_cell_sum_fields_f64: cuTensorMapEncodeTiled entry point not found"); return ONK_ERR_CUDA; }
+      encode = (encode_t)fn;
+    }
+    // 128 threads = 32 cells x 4 fields per tile: 32 x 4 x 1.43 rows = 183 rows on average for Poisson(16) cells in chunks of
+    // 16, sigma 11: the 224-row box (28 KiB) holds all but 1 tile in 10^4; 7 resident CTAs keep 196 KiB in flight per SM
+    constexpr int CT = 7, NTH = 128, BR = 224;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = { 16, (cuuint64_t)nrows_full };
+    const cuuint64_t gstride[1] = { 128 };
+    const cuuint32_t box[2] = { 16, (cuuint32_t)BR };
+    const cuuint32_t estr[2] = { 1, 1 };
+    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)arena_dev, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("onk_cell_sum_fields_f64: cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return ONK_ERR_CUDA; }
+    constexpr size_t smem = (size_t)BR * 128 + 1024;
+    static bool configured = false;
+    if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_fields_tma_kernel<CT, NTH, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+    const unsigned cpt = NTH / (unsigned)nfields;
+    unsigned grid = grid_for(ncells, cpt, CT);
+    if (grid > (unsigned)(MAX_PARTIALS / CELL_ALLF_MAX)) grid = MAX_PARTIALS / CELL_ALLF_MAX;
+    cell_sum_fields_tma_kernel<CT, NTH, BR><<<grid, NTH, smem, L->stream>>>(tmap, (const uint8_t*)arena_dev, nrows_full, cell_off_dev, cell_size_dev, cell_cap_dev,
+                                                                            ncells, prm, cell_sums_dev, L->ws.partials, L->ws.ticket, totals_dev);
+    ONK_CHECK_LAUNCH(); count_launch();
+    return ONK_OK;
+  }
+  unsigned grid = grid_for(ncells * (uint64_t)nfields, THREADS, 8);
+  cell_sum_fields_plain_kernel<<<grid, THREADS, 0, L->stream>>>((const uint8_t*)arena_dev, cell_off_dev, cell_size_dev, cell_cap_dev, ncells, prm, cell_sums_dev);
+  ONK_CHECK_LAUNCH(); count_launch();
+  if (totals_dev)
+  {
+    cell_sum_fields_totals_kernel<<<1, THREADS, 0, L->stream>>>(cell_sums_dev, ncells, (unsigned)nfields, totals_dev);
+    ONK_CHECK_LAUNCH(); count_launch();
+  }
   return ONK_OK;
 }
 

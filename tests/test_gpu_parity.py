@@ -440,6 +440,60 @@ def test_cell_sum_vs_oracle(ob, orc, side, maxn):
         assert host(t2)[0] == host(total)[0]                # reproducible total
 
 
+@pytest.mark.parametrize("side,mean,maxn,nf,align", [(1, 16.0, 64, 4, 64), (7, 16.0, 64, 4, 64), (40, 16.0, 64, 4, 64), (24, 40.0, 400, 4, 64), (16, 0.3, 4, 4, 64),
+                                                         (20, 16.0, 64, 3, 64), (20, 16.0, 64, 1, 256), (12, 16.0, 64, 8, 64), (20, 16.0, 63, 5, 8)])
+def test_cell_sum_all_fields_vs_oracle(ob, orc, gold, side, mean, maxn, nf, align):
+    """onk_cell_sum_fields_f64 (config C4, every field of the cell blocks streamed): each field's per-cell sums bit for bit
+    against the oracle's per-field loop over the same arena (dense tiles reach beyond the staged box, empty cells, field
+    counts that do not divide the CTA, alignments down to 8); totals within 1e-12 and reproducible"""
+    from tests._inputs import lcg_uniform, poisson_counts
+    from onika_b200 import cellgrid
+    counts = poisson_counts(side ** 3, mean, 42, 0, maxn)
+    if maxn > 64:
+        counts[::53] = maxn
+    if counts.size > 5:
+        counts[5] = 0
+    fb = (8,) * nf
+    cg = cellgrid.CellGrid(counts, align, 16, fb, 64)
+    npart = int(counts.sum())
+    arena = np.zeros(max(cg.arena_bytes, 1), np.uint8)
+    vals = []
+    for k in range(nf):
+        v = lcg_uniform(npart, 40 + k, -1, 1)
+        vals.append(v)
+        arena |= cg.host_arena_with_field(k, v)             # the fields occupy disjoint bytes
+    cg.upload(arena)
+    sums, totals = cg.cell_sum_all_fields()
+    ob.lane_sync()
+    got, tot = host(sums), host(totals)
+    assert got.shape == (counts.size, nf)
+    for k in range(nf):
+        so, to = orc.cell_sum(arena, cg.cell_off_host, cg.cell_size_host, cg.cell_cap_host, align, list(fb), k)
+        assert np.array_equal(got[:, k], so), k
+        assert abs(tot[k] - to) <= SUM_RTOL * max(np.abs(vals[k]).sum(), 1e-300)
+    s2, t2 = cg.cell_sum_all_fields()
+    ob.lane_sync()
+    assert np.array_equal(host(t2), tot) and np.array_equal(host(s2), got)
+    # the single-field entry point agrees bit for bit on the same arena
+    s1, _ = cg.cell_sum(nf - 1)
+    ob.lane_sync()
+    assert np.array_equal(host(s1), got[:, nf - 1])
+
+
+def test_cell_sum_all_fields_golden(ob, gold):
+    """the reference's own per-cell loop produced this golden vector for field e (3) of FieldArrays<64,16,rx,ry,rz,e> cells"""
+    from tests._inputs import unhx
+    from onika_b200 import cellgrid
+    g = gold["cell_sum"]
+    counts = np.array(g["counts"], np.uint32)
+    cg = cellgrid.CellGrid(counts, 64, 16, (8, 8, 8, 8), 64)
+    cg.upload(cg.host_arena_with_field(3, unhx(g["e"])))
+    sums, totals = cg.cell_sum_all_fields()
+    ob.lane_sync()
+    assert np.array_equal(host(sums)[:, 3], unhx(g["cell_sum"])) and not host(sums)[:, :3].any()
+    assert abs(host(totals)[3] - float.fromhex(g["total"])) <= SUM_RTOL * np.abs(unhx(g["e"])).sum()
+
+
 def test_cell_sum_config_c4_full_size_properties(ob):
     """128^3 cells x ~16 particles: every e = 1.0 makes the sums exact integers => cell_sum == counts, total == N."""
     from tests._inputs import poisson_counts
