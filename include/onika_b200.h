@@ -133,6 +133,8 @@ int onk_launch_count(uint64_t* n);          /* kernels launched by this library 
 typedef struct onk_graph onk_graph;
 int onk_graph_begin(int origin_lane, const int* other_lanes, int n_other);
 int onk_graph_end(onk_graph** graph);
+/* replays the captured sequence on `lane`.  The captured kernels keep using the reduction scratch of the lanes they were
+ * captured on: do not queue reductions directly on those lanes while a replay may be running (wait for the replay first). */
 int onk_graph_launch(onk_graph* graph, int lane);
 int onk_graph_destroy(onk_graph* graph);
 

@@ -31,6 +31,12 @@ namespace onk
   // ---- per-lane state -------------------------------------------------------------------------------------
   // Reduction workspace: one partial per CTA + a self-resetting ticket, private to the lane so reductions queued on
   // different lanes never share scratch (the reference's per-PEC GPUKernelExecutionScratch plays this role).
+  // Concurrency contract: the workspace is only ever touched by KERNELS, and kernels of one lane execute in stream order,
+  // so any number of host threads may queue reductions on the same lane (the launches serialise on the stream; each kernel
+  // leaves the ticket at 0).  What is NOT allowed is running two kernels that use the same lane's workspace concurrently:
+  // (a) rebinding a lane to another stream (onk_lane_bind_stream) while work is pending on it, and (b) replaying a captured
+  // graph (onk_graph_launch) on lane X while reductions are queued directly on one of the lanes the graph was CAPTURED on --
+  // the graph's kernels keep the workspace pointers of their capture lanes.  onk_graph_launch documents (b) in the header.
   struct LaneWorkspace
   {
     double*   partials = nullptr;   // MAX_PARTIALS doubles

@@ -42,7 +42,9 @@ def fold_partials(op: int, partials: Sequence[float]) -> float:
 
 def combine_across_ranks(op: int, partial, group=None):
     """partial: 1-element float64 tensor (device or CPU).  Returns a 1-element tensor holding the global result on
-    every rank.  Asynchronous on the current stream for device tensors."""
+    every rank.  For device tensors the collective is asynchronous on TORCH's current stream: the kernel that produced
+    `partial` must have been queued on a lane bound to that stream (lane 0 after runtime.init(), or any lane passed to
+    bind_lane_to_torch_stream) -- otherwise synchronise the producing lane first (lane_sync)."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:

@@ -7,9 +7,21 @@ from . import _capi
 from ._capi import check, lib
 
 
-def init(device: int = 0) -> None:
-    """onk_init: one process drives one device (reference: init_cuda device selection, init_cuda.cpp:84-111)."""
+def init(device: int = 0, bind_torch_stream: bool = True) -> None:
+    """onk_init: one process drives one device (reference: init_cuda device selection, init_cuda.cpp:84-111).
+
+    Ordering with torch: the library's lanes are non-blocking streams of their own, so nothing orders a lane's kernels with
+    torch operations on the same tensors unless they share a stream.  By default lane 0 (the default lane of every Python
+    call here) is therefore bound to torch's current stream when torch is in use: torch ops, lane-0 kernels and
+    torch.distributed collectives (which run on torch's current stream) then execute in program order.  Work put on OTHER
+    lanes must be ordered explicitly (lane_sync, onk_lane_wait_lane, or bind that lane too).  bind_torch_stream=False keeps
+    lane 0 on its own stream."""
     check(lib().onk_init(device))
+    if bind_torch_stream:
+        import sys
+        torch = sys.modules.get("torch")
+        if torch is not None and torch.cuda.is_available():
+            bind_lane_to_torch_stream(0)
 
 
 def finalize() -> None:
@@ -46,7 +58,10 @@ def lane_stream(lane: int) -> int:
 
 
 def bind_lane_to_torch_stream(lane: int, stream=None) -> None:
-    """Run `lane` on a torch stream (default: torch's current stream) so torch.cuda.Event timing sees the kernels."""
+    """Run `lane` on a torch stream (default: torch's current stream).  This is what ORDERS the lane's kernels with torch
+    operations and torch.distributed collectives on the same tensors (they all run on that stream, in program order); it also
+    makes torch.cuda.Event timing see the kernels.  init() does it for lane 0; a lane that is not bound runs concurrently
+    with torch's stream and needs explicit synchronisation."""
     import torch
     if stream is None:
         stream = torch.cuda.current_stream()

@@ -208,6 +208,61 @@ static int scenario_helpers(Out& out, size_t rows)
   return 0;
 }
 
+// the block vocabulary inside a CTA of sub-blocks (and, with the same source, inside ordinary CTAs): every item records what
+// its "block" looks like through the ONIKA_CU_* macros and the block_reduce_* helpers
+template<int BS>
+struct BlockVocabularyFunctor
+{
+  const double* values; double* out;      // out: 8 doubles per item
+  ONIKA_HOST_DEVICE_FUNC inline void operator () ( size_t i ) const
+  {
+    const unsigned int tid = ONIKA_CU_THREAD_IDX , bs = ONIKA_CU_BLOCK_SIZE;
+    const double v = values[ i * BS + ( tid % BS ) ];
+    const double sum_ids = onika::cuda::block_reduce_add( double(tid+1) , onika::IntConst<BS>{} );       // bs*(bs+1)/2
+    const double vmin = onika::cuda::block_reduce_min( v , onika::IntConst<BS>{} );
+    const double vmax = onika::cuda::block_reduce_max( v , onika::IntConst<BS>{} );
+    const int any = ONIKA_CU_BLOCK_SYNC_OR( tid == ( i % BS ) );               // exactly one thread of the block says yes
+    const int all = ONIKA_CU_BLOCK_SYNC_AND( tid < bs );
+    const int none = ONIKA_CU_BLOCK_SYNC_OR( tid >= bs );
+    double cnt = 0.0;
+    ONIKA_CU_BLOCK_SIMD_FOR(unsigned int, k, 0, 3u*BS+1u) { cnt += 1.0; }       // iterations shared by the block's threads
+    cnt = onika::cuda::block_reduce_add( cnt , onika::IntConst<BS>{} );         // 3*BS+1 in total
+    ONIKA_CU_BLOCK_SYNC();
+    if( tid == 0 )
+    {
+      double* o = out + i * 8;
+      o[0] = double(bs); o[1] = sum_ids; o[2] = vmin; o[3] = vmax; o[4] = double( ( any != 0 ) + 2 * ( all != 0 ) + 4 * ( none != 0 ) );
+      o[5] = cnt; o[6] = double( ONIKA_CU_BLOCK_IDX < ONIKA_CU_GRID_SIZE ); o[7] = double( ONIKA_CU_BLOCK_DIMS.x * ONIKA_CU_BLOCK_DIMS.y * ONIKA_CU_BLOCK_DIMS.z );
+    }
+  }
+};
+template<int BS> struct PackedBlockVocabularyFunctor : public BlockVocabularyFunctor<BS> {};
+namespace onika { namespace parallel {
+  template<int BS> struct BlockParallelForFunctorTraits< BlockVocabularyFunctor<BS> > { static inline constexpr bool CudaCompatible = true; };
+  template<int BS> struct BlockParallelForFunctorTraits< PackedBlockVocabularyFunctor<BS> > { static inline constexpr bool CudaCompatible = true; static inline constexpr bool SubBlockItems = true; };
+} }
+
+static int scenario_block_vocabulary(Out& out, size_t nitems)
+{
+  CudaMMVector<double> values( nitems * 128 ); fill( values , 21 , -1.0 , 1.0 );
+  auto run = [&](auto functor_of, unsigned int bs)
+  {
+    CudaMMVector<double> res( nitems * 8 , -1.0 );
+    BlockParallelForOptions o; o.max_block_size = bs;
+    block_parallel_for( nitems , functor_of( res.data() ) , parallel_execution_context("vocabulary") , o );
+    out.doubles( res.data() , res.size() );
+  };
+  // ordinary CTAs (one block per item at a time) and CTAs of sub-blocks, block sizes 8 / 16 / 32; then a 128-thread block
+  run( [&](double* r) { return BlockVocabularyFunctor<8>{ values.data() , r }; } , 8 );
+  run( [&](double* r) { return PackedBlockVocabularyFunctor<8>{ { values.data() , r } }; } , 8 );
+  run( [&](double* r) { return BlockVocabularyFunctor<16>{ values.data() , r }; } , 16 );
+  run( [&](double* r) { return PackedBlockVocabularyFunctor<16>{ { values.data() , r } }; } , 16 );
+  run( [&](double* r) { return BlockVocabularyFunctor<32>{ values.data() , r }; } , 32 );
+  run( [&](double* r) { return PackedBlockVocabularyFunctor<32>{ { values.data() , r } }; } , 32 );
+  run( [&](double* r) { return PackedBlockVocabularyFunctor<128>{ { values.data() , r } }; } , 128 );   // too large to pack: ordinary CTAs
+  return 0;
+}
+
 // ---------------------------------------------------------------- scenarios
 static int scenario_axpy(Out& out, size_t n)
 {
@@ -985,6 +1040,7 @@ int main(int argc, char* argv[])
   else if( sc == "soatl" ) rc = scenario_soatl( out , arg(3,53) );
   else if( sc == "soatl_apply" ) rc = scenario_soatl_apply( out , arg(3,100003) , arg(4,0) != 0 );
   else if( sc == "perf" ) rc = scenario_perf( out , arg(3,1<<27) );
+  else if( sc == "block_vocabulary" ) rc = scenario_block_vocabulary( out , arg(3,1000) );
   else if( sc == "helpers" ) rc = scenario_helpers( out , arg(3,333) );
   else if( sc == "reduce_helpers" ) rc = scenario_reduce_helpers( out , arg(3,513) , arg(4,1027) );
   ParallelExecutionQueue::default_queue() << flush << synchronize;

@@ -190,6 +190,7 @@ namespace
       if( a.rfind("dump:",0) == 0 && a.find('=') != std::string::npos ) { dumps.push_back( { a.substr(5,a.find('=')-5) , a.substr(a.find('=')+1) } ); continue; }
       if( a.rfind("--",0) != 0 ) { files.push_back( a ); continue; }
       // `--a-b value` -> { a: { b: value } } layered on top of the files (src/yaml/cmdline.cpp:54-84); applied after the loop
+      if( i+1 < argc && std::string(argv[i+1]).rfind("--",0) != 0 && std::string(argv[i+1]).rfind("dump:",0) != 0 ) ++i;
     }
     for(const auto& f : files)
     {

@@ -322,6 +322,24 @@ def test_soatl_parallel_apply_simd_vectorised_device_kernel(prog, tmp_path, orc,
     assert np.array_equal(d[8 * n:], want, equal_nan=True)
 
 
+def test_block_vocabulary_in_ordinary_ctas_and_in_ctas_of_sub_blocks(prog, tmp_path):
+    """ONIKA_CU_THREAD_IDX / BLOCK_SIZE / BLOCK_DIMS / BLOCK_IDX / GRID_SIZE / BLOCK_SIMD_FOR / BLOCK_SYNC[_OR|_AND] and
+    block_reduce_add/min/max mean the functor's BLOCK whether a CTA holds one block (reference launch shape) or several
+    sub-blocks (SubBlockItems): same functor source, same per-item answers"""
+    nitems = 1000
+    d = run(prog, tmp_path, "block_vocabulary", nitems).view(np.float64).reshape(7, nitems, 8)
+    values = lcg_uniform(nitems * 128, 21, -1.0, 1.0)
+    for k, bs in enumerate((8, 8, 16, 16, 32, 32, 128)):
+        r = d[k]
+        v = values[: nitems * bs].reshape(nitems, bs)                                           # item i reads values[i*bs + tid]
+        assert np.all(r[:, 0] == bs) and np.all(r[:, 7] == bs), (k, bs)                         # block size and dims of the (sub-)block
+        assert np.all(r[:, 1] == bs * (bs + 1) / 2)                                             # every thread index 0..bs-1 exactly once
+        assert np.array_equal(r[:, 2], v.min(axis=1)) and np.array_equal(r[:, 3], v.max(axis=1))
+        assert np.all(r[:, 4] == 3.0)                                                            # OR: yes, AND: yes, OR of nothing: no
+        assert np.all(r[:, 5] == 3 * bs + 1) and np.all(r[:, 6] == 1.0)
+    assert np.array_equal(d[0], d[1]) and np.array_equal(d[2], d[3]) and np.array_equal(d[4], d[5])   # packed == unpacked, bit for bit
+
+
 def _multi_gpu_expected(orc, n, world):
     """what every rank of tests/cxx/multi_gpu_test must write: fused min/max/sum of the sharded array (twice), then the
     all_reduce_multi results -- rank-order folds from the identity"""

@@ -86,6 +86,7 @@ def main():
     alg = 8 * int(counts.sum()) + cg.ncells * 24
     timed("cells", lambda: cg.cell_sum(3), alg, True)
     timed("cells_f0", lambda: cg.cell_sum(0), alg, True)
+    timed("cells_all", lambda: cg.cell_sum_all_fields(), 32 * int(counts.sum()) + cg.ncells * 48, True)
     # raw back-to-back launches through the C ABI with preallocated outputs (the arena is 1.5 GB >> L2)
     import ctypes as C
     from onika_b200 import _capi
