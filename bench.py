@@ -651,7 +651,9 @@ def e2e_measure(K, world, rank, torch, dist, ob, P, data, n):
            "per_rank_GBps": [round(v, 2) for v in per_rank],
            "h2d_peak_GBps": agg_peak, "h2d_peak_per_rank_GBps": per_rank_peak,
            "h2d_peak_how": "1 GiB cudaMemcpyAsync from pinned memory on every rank at the same time, best of 4",
-           "frac_of_pcie": round(world * n * 8 / dt / 1e9 / agg_peak, 4) if agg_peak else None}
+           "frac_of_pcie": round(world * n * 8 / dt / 1e9 / agg_peak, 4) if agg_peak else None,
+           # weak scaling: every rank moves the same bytes, so the step ends with the rank on the slowest host link
+           "frac_of_pcie_slowest_rank": round(n * 8 / dt / 1e9 / min(per_rank_peak), 4) if per_rank_peak and min(per_rank_peak) > 0 else None}
     pageable = torch.empty(n, dtype=torch.float64)
     pageable.copy_(pinned)
     del pinned
