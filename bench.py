@@ -854,7 +854,6 @@ def run_ours(args) -> int:
         tl = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(tl, op=dist.ReduceOp.SUM)
         launches = int(tl.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     ms_per_step = total_ms / K
     value = n_total * 8 / (ms_per_step * 1e-3) / 1e9
 
@@ -881,6 +880,9 @@ def run_ours(args) -> int:
         kev[k + 1].record()
     torch.cuda.synchronize()
     per_step = sorted(kev[k].elapsed_time(kev[k + 1]) for k in range(Ks))
+    # clocks: sampled from the start of the timed region to the end of the kernel-only passes above (the same kernel under
+    # the same load: more NVML samples than the few milliseconds of the K timed steps alone would give)
+    clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
     peaks = read_json(os.path.join(ROOT, "MEASURED_PEAKS.json"))
     peak, peak_src = (float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)") if peaks and "hbm_gbs" in peaks \
         else (6650.0, "fallback (B200_PROFILING.md)")
@@ -892,6 +894,35 @@ def run_ours(args) -> int:
                 "algorithmic_bytes_per_launch": n * 8, "kernel_ms": round(kernel_ms, 5),
                 "traffic": (traffic or {}).get("reduce_f64_kernel_dram_bytes_per_launch") if n == N_ELEMS else None,
                 "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this size (profiles/roofline_traffic.json), not measured in this run"}
+
+    # ---- the headline kernel against the ORACLE on this rank's shard (outside every timed region): min and max bit for bit,
+    # sum within 1e-12; at N > 1 the fused result must equal the minimum of the ranks' oracle minima ----
+    shard_check = None
+    if not args.profile_mode:
+        try:
+            import oracle
+            try:
+                ncpu = len(os.sched_getaffinity(0))
+            except AttributeError:
+                ncpu = os.cpu_count() or 1
+            oracle.orc.set_num_threads(max(1, ncpu // world))
+            host = data.cpu().numpy()
+            got = {}
+            for name, op in (("min", ob.OP_MIN), ("max", ob.OP_MAX), ("sum", ob.OP_SUM)):
+                P.ReduceFunctor(op, data, result).launch(n, 0)
+                got[name] = float(result.item())
+            omin, omax, osum = oracle.orc.reduce_min(host), oracle.orc.reduce_max(host), oracle.orc.reduce_sum_ld(host)
+            ok = got["min"] == omin and got["max"] == omax and abs(got["sum"] - osum) <= 1e-12 * float(np.abs(host).sum())
+            gmin = omin
+            if world > 1:
+                t = torch.tensor([omin], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                gmin = float(t.item())
+            ok = ok and expect == gmin
+            shard_check = "ok" if ok else f"FAILED on rank {rank}: kernel {got} vs oracle min {omin!r} max {omax!r} sum {osum!r}, fused {expect!r} vs {gmin!r}"
+            del host
+        except Exception as ex:  # pragma: no cover
+            shard_check = f"FAILED on rank {rank}: {str(ex)[:200]}"
 
     # ---- e2e: the plugin-facing host-buffer call (host -> device copies inside the timed region) ----
     e2e = None
@@ -926,6 +957,11 @@ def run_ours(args) -> int:
             from tests import _multigpu_checks
             checks = _multigpu_checks.run_checks(rank, world)        # never raises: {name: "ok" | message}
             failures += [f"{k}: {v}" for k, v in checks.items() if v != "ok"]
+    if shard_check is not None:
+        checks = dict(checks or {})
+        checks["headline_shard_min_max_sum_vs_oracle"] = shard_check
+        if shard_check != "ok":
+            failures.append(shard_check)
     failed = "; ".join(failures) if failures else None
     if world > 1:
         bad = torch.tensor([1 if failed else 0], dtype=torch.int32, device="cuda")

@@ -372,6 +372,57 @@ namespace onk
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(a) : "memory");
   }
 
+  // In-order fold of doubles [qb, qe) of a tile staged with the 128-byte swizzle (16-byte chunk c of 128-byte row r at chunk
+  // c ^ (r & 7); `tile` = shared address of the tile, 1024-byte aligned).  Row by row: the row base is 128-byte aligned, so the
+  // address of chunk c is (base ^ ((r & 7) << 4)) ^ (c << 4) -- one XOR with an immediate per LDS.128 once the row term is
+  // hoisted (the per-element form recomputes the whole slot expression: 7 integer instructions per load; the field-major
+  // kernel was issue-bound on them).  Whole rows are unrolled.
+  __device__ __forceinline__ double fold_swizzled(unsigned tile, uint32_t qb, uint32_t qe, double s)
+  {
+    uint32_t q = qb;
+    if (q >= qe) return s;
+    if (q & 1u)
+    {
+      const uint32_t r = q >> 4;
+      s = __dadd_rn(s, lds64_u32(((tile + (r << 7)) ^ ((r & 7u) << 4)) ^ (((q >> 1) & 7u) << 4) | 8u));
+      ++q;
+    }
+    while (q + 2u <= qe)
+    {
+      const uint32_t r = q >> 4;
+      const unsigned bx = (tile + (r << 7)) ^ ((r & 7u) << 4);
+      const uint32_t row_end = (r + 1u) << 4;
+      if ((q & 15u) == 0u && row_end <= qe)
+      {
+#pragma unroll
+        for (unsigned c = 0; c < 8u; c++)
+        {
+          double x0, x1; lds128_u32(bx ^ (c << 4), x0, x1);
+          s = __dadd_rn(s, x0); s = __dadd_rn(s, x1);
+        }
+        q = row_end;
+      }
+      else
+      {
+        const uint32_t stop = row_end < qe ? row_end : qe;
+        unsigned a = (q >> 1) & 7u;
+#pragma unroll 4
+        for (; q + 2u <= stop; q += 2u, a++)
+        {
+          double x0, x1; lds128_u32(bx ^ (a << 4), x0, x1);
+          s = __dadd_rn(s, x0); s = __dadd_rn(s, x1);
+        }
+        if (q < stop) break;                    // a single element is left (only possible at qe)
+      }
+    }
+    if (q < qe)
+    {
+      const uint32_t r = q >> 4;
+      s = __dadd_rn(s, lds64_u32(((tile + (r << 7)) ^ ((r & 7u) << 4)) ^ (((q >> 1) & 7u) << 4)));
+    }
+    return s;
+  }
+
   // One tile in flight per CTA, CTAS resident CTAs per SM (resident warps, not a deeper ring per CTA, hide the latency
   // here: 3 stages x 2 CTAs 77 us, 2 x 3 67 us, 1 x 6 66 us, 1 x 5 64 us on 128^3 cells).  Tiles are handed out
   // dynamically: the first one is the CTA's own index, further ones come from a global ticket drawn by thread 0 one tile
@@ -582,11 +633,6 @@ namespace onk
       }
       load_tables(following);
     };
-    auto slot_addr = [&](uint32_t q) -> unsigned                          // value q of the box, swizzled
-    {
-      const uint32_t row = q >> 4;
-      return tile_smem + (row << 7) + ((((q >> 1) ^ row) & 7u) << 4) + ((q & 1u) << 3);
-    };
 
     uint64_t cur = blockIdx.x;
     if (threadIdx.x == 0) draw(0);
@@ -604,18 +650,7 @@ namespace onk
       phase ^= 1u;
       if (threadIdx.x == 0) draw(slot);                                   // ticket of the tile after the next one
       const uint32_t staged_end = pe < cnt ? pe : cnt;
-      double s = 0.0;
-      if (pb < staged_end)                                                // particle order
-      {
-        uint32_t q = pb;
-        if (q & 1u) { s = __dadd_rn(s, lds64_u32(slot_addr(q))); ++q; }
-        for (; q + 2u <= staged_end; q += 2u)
-        {
-          double x0, x1; lds128_u32(slot_addr(q), x0, x1);
-          s = __dadd_rn(s, x0); s = __dadd_rn(s, x1);
-        }
-        if (q < staged_end) s = __dadd_rn(s, lds64_u32(slot_addr(q)));
-      }
+      double s = fold_swizzled(tile_smem, pb, staged_end, 0.0);           // particle order
       const uint64_t c = cur * NT + threadIdx.x;
       if (pe > cnt && c < ncells)                                         // beyond the box or in the last partial row: global memory
       {
@@ -731,11 +766,6 @@ namespace onk
       }
       load_tables(following);
     };
-    auto slot_addr = [&](uint32_t q) -> unsigned                          // double q of the box, swizzled
-    {
-      const uint32_t row = q >> 4;
-      return tile_smem + (row << 7) + ((((q >> 1) ^ row) & 7u) << 4) + ((q & 1u) << 3);
-    };
 
     uint64_t cur = blockIdx.x;
     if (threadIdx.x == 0) draw(0);
@@ -759,17 +789,7 @@ namespace onk
         const uint64_t qe = q0 + sz;
         const uint32_t staged_end = (uint32_t)(qe < (uint64_t)cnt ? qe : (q0 < (uint64_t)cnt ? (uint64_t)cnt : q0));
         double s = 0.0;
-        uint32_t q = (uint32_t)q0;
-        if (q0 < (uint64_t)cnt)                                           // particle order
-        {
-          if ((q & 1u) && q < staged_end) { s = __dadd_rn(s, lds64_u32(slot_addr(q))); ++q; }
-          for (; q + 2u <= staged_end; q += 2u)
-          {
-            double x0, x1; lds128_u32(slot_addr(q), x0, x1);
-            s = __dadd_rn(s, x0); s = __dadd_rn(s, x1);
-          }
-          if (q < staged_end) { s = __dadd_rn(s, lds64_u32(slot_addr(q))); ++q; }
-        }
+        if (q0 < (uint64_t)cnt) s = fold_swizzled(tile_smem, (uint32_t)q0, staged_end, 0.0);    // particle order
         if (qe > (uint64_t)staged_end)                                    // beyond the box / the last full row: global memory
         {
           const double* g = reinterpret_cast<const double*>(arena + col);
