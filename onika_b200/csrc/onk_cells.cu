@@ -375,8 +375,9 @@ namespace onk
   // In-order fold of doubles [qb, qe) of a tile staged with the 128-byte swizzle (16-byte chunk c of 128-byte row r at chunk
   // c ^ (r & 7); `tile` = shared address of the tile, 1024-byte aligned).  Row by row: the row base is 128-byte aligned, so the
   // address of chunk c is (base ^ ((r & 7) << 4)) ^ (c << 4) -- one XOR with an immediate per LDS.128 once the row term is
-  // hoisted (the per-element form recomputes the whole slot expression: 7 integer instructions per load; the field-major
-  // kernel was issue-bound on them).  Whole rows are unrolled.
+  // hoisted (the per-element form recomputes the whole slot expression: 7 integer instructions per load).  Whole rows are
+  // unrolled.  Worth 6 % on the all-fields kernel, whose columns are whole rows (6.45 -> 6.83 TB/s at 256^3 cells); the
+  // field-major kernel, whose cells start anywhere, keeps the per-element form (no gain, more registers).
   __device__ __forceinline__ double fold_swizzled(unsigned tile, uint32_t qb, uint32_t qe, double s)
   {
     uint32_t q = qb;
@@ -557,10 +558,9 @@ namespace onk
   // than the box, are read from global memory by the owning thread.
   // The tensor map's box is SUBROWS (16) rows = 2 KiB; a tile is brought in by as many such copies as its values span (up to
   // the BOXROWS rows of the staging buffer), all completing on the same mbarrier: nothing beyond the tile's last row is
-  // requested.  (One fixed box per tile had to be sized for the densest tile and re-read 25 % of the column on average: at
-  // 256^3 cells that kernel ran at 5.0 TB/s, the copies themselves at 6.1 TB/s.)
+  // requested (one fixed box per tile had to be sized for the densest tile and re-read 25 % of the column through L2).
   constexpr int TMA_SUBROWS = 16;
-  template<int CTAS, int NT, int BOXROWS>
+  template<int CTAS, int NT, int BOXROWS, bool ROWFOLD = true>
   __global__ void __launch_bounds__(NT, CTAS)
   cell_sum_packed_tma_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ values, uint64_t nrows_full,
                              const uint64_t* __restrict__ cell_begin, uint64_t ncells,
@@ -650,7 +650,20 @@ namespace onk
       phase ^= 1u;
       if (threadIdx.x == 0) draw(slot);                                   // ticket of the tile after the next one
       const uint32_t staged_end = pe < cnt ? pe : cnt;
-      double s = fold_swizzled(tile_smem, pb, staged_end, 0.0);           // particle order
+      double s = 0.0;
+      if constexpr (ROWFOLD) s = fold_swizzled(tile_smem, pb, staged_end, 0.0);           // particle order
+      else if (pb < staged_end)
+      {
+        auto slot_addr = [&](uint32_t q) -> unsigned { const uint32_t row = q >> 4; return tile_smem + (row << 7) + ((((q >> 1) ^ row) & 7u) << 4) + ((q & 1u) << 3); };
+        uint32_t q = pb;
+        if (q & 1u) { s = __dadd_rn(s, lds64_u32(slot_addr(q))); ++q; }
+        for (; q + 2u <= staged_end; q += 2u)
+        {
+          double x0, x1; lds128_u32(slot_addr(q), x0, x1);
+          s = __dadd_rn(s, x0); s = __dadd_rn(s, x1);
+        }
+        if (q < staged_end) s = __dadd_rn(s, lds64_u32(slot_addr(q)));
+      }
       const uint64_t c = cur * NT + threadIdx.x;
       if (pe > cnt && c < ncells)                                         // beyond the box or in the last partial row: global memory
       {
@@ -972,11 +985,8 @@ int onk_cell_sum_packed_f64(const double* values_dev, uint64_t nvalues, const ui
       if (!fn) { set_error("onk_cell_sum_packed_f64: cuTensorMapEncodeTiled entry point not found"); return ONK_ERR_CUDA; }
       encode = (encode_t)fn;
     }
-    // shape: 10 resident CTAs of 128 threads, 160-row (20 KiB) boxes for tiles of 128 rows on average.  Measured on 128^3
-    // cells (C ABI call, cold L2): 10x128x160 53.3 us, 6x192x256 53.3, 12x128x144 54.3, 8x128x192 55.3, 20x64x96 65.5,
-    // 16x64x112 66.6; L2 promotion none / 64 B / 128 B 53.2-53.3 us, 256 B 55.3 us
     constexpr int l2p = (int)CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-#define ONK_PK_TMA_GO(C, NTH, BR) do { \
+#define ONK_PK_TMA_GO(C, NTH, BR, RF) do { \
     CUtensorMap tmap; \
     const cuuint64_t gdim[2] = { 16, (cuuint64_t)nrows_full }; \
     const cuuint64_t gstride[1] = { 128 }; \
@@ -987,12 +997,20 @@ int onk_cell_sum_packed_f64(const double* values_dev, uint64_t nvalues, const ui
     if (r != CUDA_SUCCESS) { set_error("onk_cell_sum_packed_f64: cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return ONK_ERR_CUDA; } \
     constexpr size_t smem = (size_t)BR * 128 + 1024; \
     static bool configured = false; \
-    if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_packed_tma_kernel<C, NTH, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; } \
+    if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_packed_tma_kernel<C, NTH, BR, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; } \
     unsigned grid = grid_for(ncells, NTH, C); \
     if (grid > (unsigned)MAX_PARTIALS) grid = MAX_PARTIALS; \
-    cell_sum_packed_tma_kernel<C, NTH, BR><<<grid, NTH, smem, L->stream>>>(tmap, values_dev, nrows_full, cell_begin_dev, ncells, cell_sum_dev, \
+    cell_sum_packed_tma_kernel<C, NTH, BR, RF><<<grid, NTH, smem, L->stream>>>(tmap, values_dev, nrows_full, cell_begin_dev, ncells, cell_sum_dev, \
                                                                            L->ws.partials, L->ws.ticket, total_dev); } while (0)
-    ONK_PK_TMA_GO(10, 128, 160);
+    // shape: 8 resident CTAs of 128 threads, 160-row (20 KiB) staging buffers for tiles of 128 rows on average.  Measured with
+    // the C ABI call, cold L2, 128^3 / 256^3 cells (tools/exp_field_major_fold.py): 8x128x160 56.4 us / 357 us (6.76 TB/s),
+    // 9x128x160 with the row-wise fold 58.4 / 355, 10x128x160 (round 1: capped at 48 registers) 56.3 / 466, 7x128x160 58.4 / 374,
+    // 6x128x160 62.5 / 400, 12x128x144 68.6 / 441, 6x192x256 60.4 / 365, 4x256x320 64.5 / 400: at scale FEWER resident CTAs
+    // with uncapped registers win; L2 promotion none / 64 B / 128 B within 0.1 us, 256 B +2 us
+    static const int shape = []{ const char* e = getenv("ONK_PK_FOLD"); return e ? atoi(e) : 0; }();      // tuning / comparison only
+    if (shape == 1) ONK_PK_TMA_GO(10, 128, 160, false);
+    else if (shape == 4) ONK_PK_TMA_GO(9, 128, 160, true);
+    else ONK_PK_TMA_GO(8, 128, 160, false);
 #undef ONK_PK_TMA_GO
     ONK_CHECK_LAUNCH(); count_launch();
     return ONK_OK;
@@ -1045,8 +1063,7 @@ int onk_cell_sum_fields_f64(const void* arena_dev, uint64_t arena_bytes, const u
       encode = (encode_t)fn;
     }
     // 128 threads = 32 cells x 4 fields per tile: 32 x 4 x 1.43 rows = 183 rows on average for Poisson(16) cells in chunks of
-    // 16, sigma 11: the 224-row box (28 KiB) holds all but 1 tile in 10^4; 7 resident CTAs keep 196 KiB in flight per SM
-    constexpr int CT = 7, NTH = 128, BR = 224;
+    // 16, sigma 11: the 224-row staging buffer (28 KiB) holds all but 1 tile in 10^4 (the rest finishes from global memory)
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = { 16, (cuuint64_t)nrows_full };
     const cuuint64_t gstride[1] = { 128 };
@@ -1055,14 +1072,22 @@ int onk_cell_sum_fields_f64(const void* arena_dev, uint64_t arena_bytes, const u
     const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)arena_dev, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("onk_cell_sum_fields_f64: cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return ONK_ERR_CUDA; }
-    constexpr size_t smem = (size_t)BR * 128 + 1024;
-    static bool configured = false;
-    if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_fields_tma_kernel<CT, NTH, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
-    const unsigned cpt = NTH / (unsigned)nfields;
-    unsigned grid = grid_for(ncells, cpt, CT);
-    if (grid > (unsigned)(MAX_PARTIALS / CELL_ALLF_MAX)) grid = MAX_PARTIALS / CELL_ALLF_MAX;
-    cell_sum_fields_tma_kernel<CT, NTH, BR><<<grid, NTH, smem, L->stream>>>(tmap, (const uint8_t*)arena_dev, arena_bytes, nrows_full, cell_off_dev, cell_size_dev, cell_cap_dev,
-                                                                            ncells, prm, cell_sums_dev, L->ws.partials, L->ws.ticket, totals_dev);
+#define ONK_CELLF_GO(CT, NTH, BR) do { \
+    constexpr size_t smem = (size_t)BR * 128 + 1024; \
+    static bool configured = false; \
+    if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_fields_tma_kernel<CT, NTH, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; } \
+    const unsigned cpt = NTH / (unsigned)nfields; \
+    unsigned grid = grid_for(ncells, cpt, CT); \
+    if (grid > (unsigned)(MAX_PARTIALS / CELL_ALLF_MAX)) grid = MAX_PARTIALS / CELL_ALLF_MAX; \
+    cell_sum_fields_tma_kernel<CT, NTH, BR><<<grid, NTH, smem, L->stream>>>(tmap, (const uint8_t*)arena_dev, arena_bytes, nrows_full, cell_off_dev, cell_size_dev, cell_cap_dev, \
+                                                                            ncells, prm, cell_sums_dev, L->ws.partials, L->ws.ticket, totals_dev); } while (0)
+    // 7 x 128 x 224 6134 / 6821 GB/s of arena stream at 128^3 / 256^3 cells (tools/exp_cell_fields_shape.py); 6 x 128 x 224
+    // 6084 / 6865, 6 x 128 x 256 6044 / 6880, 3 x 256 x 448 6182 / 6850, 5 x 128 x 224 5823 / 6493, 4 x 128 x 224 5216 / 5686
+    static const int shape = []{ const char* e = getenv("ONK_CELLF_SHAPE"); return e ? atoi(e) : 0; }();      // tuning / comparison only
+    if (shape == 1) ONK_CELLF_GO(6, 128, 224);
+    else if (shape == 4) ONK_CELLF_GO(3, 256, 448);
+    else ONK_CELLF_GO(7, 128, 224);
+#undef ONK_CELLF_GO
     ONK_CHECK_LAUNCH(); count_launch();
     return ONK_OK;
   }
