@@ -108,9 +108,9 @@ namespace onk
     int m_pending = 0, m_nthreads = 1;
   };
 
-  // pinned ring for pageable input
-  constexpr int    PIN_SLOTS = 3;
-  static void*     g_pin[PIN_SLOTS] = {nullptr, nullptr, nullptr};
+  // pinned rings for pageable buffers: slots [0,3) first input, [3,6) second input (axpy's x), [6,8) results on their way back
+  constexpr int    PIN_SLOTS = 3, PIN_X0 = 3, PIN_OUT0 = 6, PIN_OUT_SLOTS = 2, PIN_TOTAL = 8;
+  static void*     g_pin[PIN_TOTAL] = {};
 
   // can the copy engine read this host pointer directly ?  (pinned, registered or managed memory)
   static bool dma_readable(const void* p)
@@ -137,9 +137,9 @@ namespace onk
     r.stage_bytes = STAGE_BYTES;
     return ONK_OK;
   }
-  static int ensure_pinned_ring()
+  static int ensure_pinned_ring(int first = 0, int count = PIN_SLOTS)
   {
-    for (int i = 0; i < PIN_SLOTS; i++)
+    for (int i = first; i < first + count; i++)
       if (!g_pin[i]) ONK_CUDA(cudaHostAlloc(&g_pin[i], STAGE_BYTES, cudaHostAllocDefault));
     return ONK_OK;
   }
@@ -217,26 +217,73 @@ static int host_update(double* y_host, const double* x_host, uint64_t n, double 
   Runtime& r = rt();
   const uint64_t chunk = STAGE_BYTES / sizeof(double);
   const uint64_t nchunks = (n + chunk - 1) / chunk;
-  Ev ready[2], done[2], drained[2];
+  Ev ready[2], done[2], drained[2], sent_y[PIN_SLOTS], sent_x[PIN_SLOTS], landed[PIN_OUT_SLOTS];
   for (int i = 0; i < 2; i++) { if (int rc = ready[i].init()) return rc; if (int rc = done[i].init()) return rc; if (int rc = drained[i].init()) return rc; }
+  // pageable buffers travel through pinned rings filled / drained by the host copy pool (see onk_host_reduce_f64)
+  const bool stage_y = !dma_readable(y_host), stage_x = is_axpy && !dma_readable(x_host);
+  if (stage_y)
+  {
+    if (int rc = ensure_pinned_ring(0, PIN_SLOTS)) return rc;
+    if (int rc = ensure_pinned_ring(PIN_OUT0, PIN_OUT_SLOTS)) return rc;
+    for (int i = 0; i < PIN_SLOTS; i++) if (int rc = sent_y[i].init()) return rc;
+    for (int i = 0; i < PIN_OUT_SLOTS; i++) if (int rc = landed[i].init()) return rc;
+  }
+  if (stage_x)
+  {
+    if (int rc = ensure_pinned_ring(PIN_X0, PIN_SLOTS)) return rc;
+    for (int i = 0; i < PIN_SLOTS; i++) if (int rc = sent_x[i].init()) return rc;
+  }
+  auto unstage = [&](uint64_t j) -> int                     // results of chunk j: pinned ring -> the caller's pageable memory
+  {
+    const int so = (int)(j % PIN_OUT_SLOTS);
+    const uint64_t cj = (j + 1 == nchunks) ? n - j * chunk : chunk;
+    ONK_CUDA(cudaEventSynchronize(landed[so].e));
+    CopyPool::instance().copy(y_host + j * chunk, g_pin[PIN_OUT0 + so], cj * sizeof(double));
+    return ONK_OK;
+  };
   for (uint64_t k = 0; k < nchunks; k++)
   {
     const int b = (int)(k & 1);
     const uint64_t cnt = (k + 1 == nchunks) ? n - k * chunk : chunk;
     double* yd = (double*)r.stage_dev[b];
     double* xd = is_axpy ? (double*)r.stage_dev[2 + b] : nullptr;
+    const double* ysrc = y_host + k * chunk;
+    const double* xsrc = is_axpy ? x_host + k * chunk : nullptr;
+    const int si = (int)(k % PIN_SLOTS);
+    if (stage_y)
+    {
+      if (k >= (uint64_t)PIN_SLOTS) ONK_CUDA(cudaEventSynchronize(sent_y[si].e));
+      CopyPool::instance().copy(g_pin[si], ysrc, cnt * sizeof(double));
+      ysrc = (const double*)g_pin[si];
+    }
+    if (stage_x)
+    {
+      if (k >= (uint64_t)PIN_SLOTS) ONK_CUDA(cudaEventSynchronize(sent_x[si].e));
+      CopyPool::instance().copy(g_pin[PIN_X0 + si], xsrc, cnt * sizeof(double));
+      xsrc = (const double*)g_pin[PIN_X0 + si];
+    }
     if (k >= 2) ONK_CUDA(cudaStreamWaitEvent(H->stream, drained[b].e, 0));      // buffer b has been copied back
-    ONK_CUDA(cudaMemcpyAsync(yd, y_host + k * chunk, cnt * sizeof(double), cudaMemcpyHostToDevice, H->stream));
-    if (is_axpy) ONK_CUDA(cudaMemcpyAsync(xd, x_host + k * chunk, cnt * sizeof(double), cudaMemcpyHostToDevice, H->stream));
+    ONK_CUDA(cudaMemcpyAsync(yd, ysrc, cnt * sizeof(double), cudaMemcpyHostToDevice, H->stream));
+    if (stage_y) ONK_CUDA(cudaEventRecord(sent_y[si].e, H->stream));
+    if (is_axpy) ONK_CUDA(cudaMemcpyAsync(xd, xsrc, cnt * sizeof(double), cudaMemcpyHostToDevice, H->stream));
+    if (stage_x) ONK_CUDA(cudaEventRecord(sent_x[si].e, H->stream));
     ONK_CUDA(cudaEventRecord(ready[b].e, H->stream));
     ONK_CUDA(cudaStreamWaitEvent(K->stream, ready[b].e, 0));
     if (is_axpy) { if (int rc = onk_axpy_f64(yd, xd, a, cnt, LANE_COMPUTE)) return rc; }
     else         { if (int rc = onk_value_add_f64(yd, 1, cnt, a, LANE_COMPUTE)) return rc; }
     ONK_CUDA(cudaEventRecord(done[b].e, K->stream));
     ONK_CUDA(cudaStreamWaitEvent(D->stream, done[b].e, 0));
-    ONK_CUDA(cudaMemcpyAsync(y_host + k * chunk, yd, cnt * sizeof(double), cudaMemcpyDeviceToHost, D->stream));
+    if (stage_y)
+    {
+      const int so = (int)(k % PIN_OUT_SLOTS);            // free: chunk k-2 was unstaged in the previous iteration
+      ONK_CUDA(cudaMemcpyAsync(g_pin[PIN_OUT0 + so], yd, cnt * sizeof(double), cudaMemcpyDeviceToHost, D->stream));
+      ONK_CUDA(cudaEventRecord(landed[so].e, D->stream));
+    }
+    else ONK_CUDA(cudaMemcpyAsync(y_host + k * chunk, yd, cnt * sizeof(double), cudaMemcpyDeviceToHost, D->stream));
     ONK_CUDA(cudaEventRecord(drained[b].e, D->stream));
+    if (stage_y && k >= 1) { if (int rc = unstage(k - 1)) return rc; }          // overlaps the transfers of chunk k
   }
+  if (stage_y && nchunks >= 1) { if (int rc = unstage(nchunks - 1)) return rc; }
   ONK_CUDA(cudaStreamSynchronize(D->stream));
   ONK_CUDA(cudaStreamSynchronize(K->stream));
   return ONK_OK;

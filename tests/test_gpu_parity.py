@@ -635,6 +635,17 @@ def test_host_buffer_entry_points(ob, orc):
     assert odd.ctypes.data % 16 == 8
     assert P.host_reduce(_capi.OP_MIN, odd) == orc.reduce_min(odd) and P.host_reduce(_capi.OP_MAX, odd) == orc.reduce_max(odd)
     assert abs(P.host_reduce(_capi.OP_SUM, odd) - orc.reduce_sum_ld(odd)) <= SUM_RTOL * np.abs(odd).sum()
+    # in-place update of pageable arrays: both inputs and the results go through the pinned rings (6 chunks > ring slots)
+    x2, y2 = lcg_uniform(odd.size, 79, -1, 1), odd.copy()
+    yo2 = y2.copy()
+    orc.axpy(yo2, x2, 0.25)
+    P.host_axpy(y2, x2, 0.25)
+    assert np.array_equal(y2, yo2)
+    pinned_x = torch.from_numpy(x2).pin_memory()                # mixed: pinned x, pageable y
+    P.host_axpy(y2, pinned_x, 0.25)
+    orc.axpy(yo2, x2, 0.25)
+    assert np.array_equal(y2, yo2)
+    del x2, y2, yo2, pinned_x, big
     x, y = lcg_uniform(n, 1, -1, 1), lcg_uniform(n, 2, -1, 1)
     yo = y.copy()
     orc.axpy(yo, x, 0.5)
