@@ -207,6 +207,14 @@ namespace onk
   {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
   }
+  __device__ __forceinline__ double lds64_u32(unsigned a)
+  {
+    double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v;
+  }
+  __device__ __forceinline__ void lds128_u32(unsigned a, double& x0, double& x1)
+  {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(a) : "memory");
+  }
 
   // PACKED: field-major grid -- `arena` is the summed column of all cells back to back and cell_off holds ncells+1 element
   // offsets (cell c = [cell_off[c], cell_off[c+1])); rows are staged from the even element at or below the cell's first
@@ -362,14 +370,6 @@ namespace onk
   __device__ __forceinline__ void cp_async16(unsigned dst, const void* src)
   {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
-  }
-  __device__ __forceinline__ double lds64_u32(unsigned a)
-  {
-    double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v;
-  }
-  __device__ __forceinline__ void lds128_u32(unsigned a, double& x0, double& x1)
-  {
-    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(a) : "memory");
   }
 
   // In-order fold of doubles [qb, qe) of a tile staged with the 128-byte swizzle (16-byte chunk c of 128-byte row r at chunk
@@ -925,18 +925,29 @@ int onk_cell_sum_f64(const void* arena_dev, const uint64_t* cell_off_dev, const 
   const unsigned cells_per_cta = (THREADS / 32) * 32;
   unsigned grid = grid_for(ncells, cells_per_cta, CELL_CTAS_PER_SM);
   if (grid > (unsigned)MAX_PARTIALS) grid = MAX_PARTIALS;
-  // "ldg" = register-staged kernel; default = cp.async ring of 8 warps x 3 stages x 32 particles.  Other shapes were
-  // measured on 128^3 cells and dropped: 12 warps x 2 stages x 32 -> same 81 us, 16 x 2 x 24 -> 85 us, 16 x 3 x 16 -> 122 us
-  // (cells longer than the staged part fall back to per-lane global loads): this layout is bound by its DRAM access
-  // pattern (0.42 GB of 64-byte bursts for 0.30 GB of payload), not by resident warps.
+  // "ldg" = register-staged kernel; default = cp.async ring (shapes below): this layout is bound by its DRAM access
+  // pattern (0.42 GB of full 128-byte lines for 0.30 GB of payload), not by the SM.
   static const int variant = []{ const char* e = getenv("ONK_CELL_KERNEL"); return (e && e[0] == 'l') ? 0 : 1; }();
   if (variant == 1)
   {
-    static bool configured = false;
-    if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_f64_async_kernel<false,8,3,32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asy_smem<8,3,32>())); configured = true; }
-    grid = grid_for(ncells, cells_per_cta, ASY_CTAS_PER_SM);
-    cell_sum_f64_async_kernel<false,8,3,32><<<grid, THREADS, asy_smem<8,3,32>(), L->stream>>>((const uint8_t*)arena_dev, cell_off_dev, cell_size_dev, cell_cap_dev, ncells, fp,
-                                                                                             cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev);
+#define ONK_ASY_GO(NW, ST, RC) do { \
+    static bool configured = false; \
+    if (!configured) { ONK_CUDA(cudaFuncSetAttribute(cell_sum_f64_async_kernel<false,NW,ST,RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asy_smem<NW,ST,RC>())); configured = true; } \
+    grid = grid_for(ncells, NW * 32, ASY_CTAS_PER_SM); \
+    cell_sum_f64_async_kernel<false,NW,ST,RC><<<grid, NW * 32, asy_smem<NW,ST,RC>(), L->stream>>>((const uint8_t*)arena_dev, cell_off_dev, cell_size_dev, cell_cap_dev, ncells, fp, \
+                                                                                             cell_sum_dev, L->ws.partials, L->ws.ticket, total_dev); } while (0)
+    // ring shape, measured on 128^3 / 256^3 cells (tools/exp_cell_ring.py, cold L2): 16 warps x 1 stage x 32 particles
+    // 78.8 us / 540 us (default); 8 x 3 x 32 (round 1) 80.7 / 552; 12 x 2 x 32 80.9 / 542; 20 x 1 x 32 80.9 / 572;
+    // 24 x 1 x 32 80.9 / 579; 16 x 1 x 24 82.9 / 558.  A compact ring (32 first lines + second lines only for the cells
+    // that have one, 4 KB + 2.5 KB per stage instead of 8.7 KB, hence 12-16 warps with 2-3 stages) was built and measured at
+    // 87-93 us: the extra bookkeeping of the compaction costs more than the resident warps bring.  The line pattern itself
+    // can be fetched in 62-64 us by >= 12 resident warps (tools/exp_gather4.cu, list-driven ring, TMA gather4 or cp.async
+    // alike); tables and results add 13 % of traffic: this kernel is within ~10 % of what the layout allows
+    // (profiles/r2_c4_floor.md).
+    static const int shape = []{ const char* e = getenv("ONK_CELL_SHAPE"); return e ? atoi(e) : 0; }();      // tuning / comparison only
+    if (shape == 1) ONK_ASY_GO(8, 3, 32);
+    else ONK_ASY_GO(16, 1, 32);
+#undef ONK_ASY_GO
   }
   else
     cell_sum_f64_kernel<<<grid, THREADS, 0, L->stream>>>((const uint8_t*)arena_dev, cell_off_dev, cell_size_dev, cell_cap_dev, ncells, fp,
