@@ -288,9 +288,14 @@ namespace onk
     uint64_t head = ((32 - ((uintptr_t)in & 31)) & 31) / 8;
     if (head > n) head = n;
     // large inputs take the TMA-staged body (ONK_RED_KERNEL=ldg forces the register-staged kernel: tuning / comparison)
-    static const bool allow_tma = []{ const char* e = getenv("ONK_RED_KERNEL"); return !(e && e[0] == 'l'); }();
+    // ONK_RED_KERNEL (tuning / tests): "ldg" never takes the TMA-staged body, "tma" takes it from 2 tiles per SM on
+    static const int red_mode = []{ const char* e = getenv("ONK_RED_KERNEL"); return (e && e[0] == 'l') ? 1 : (e && e[0] == 't') ? 2 : 0; }();
+    const bool allow_tma = red_mode != 1;
+    // the TMA-staged body pays off on long streams (1 GiB: 151.6 vs 162.7 us); up to 512 MiB the register-staged kernel with
+    // its 4 CTAs per SM ramps up and drains a little faster (256 MiB back to back: 41.7 vs 43.1 us, 128 MiB: 20.7 vs 25.0 us;
+    // tools/exp_reduce_small.py) -- the per-GPU shards of a strong-scaling run are in that range
     const uint64_t tma_tiles = (n - head) / TMA_TILE;
-    if (allow_tma && tma_tiles >= 2ull * (uint64_t)rt().sm_count)
+    if (allow_tma && tma_tiles >= (red_mode == 2 ? 2ull * (uint64_t)rt().sm_count : 12288ull))
     {
       static bool configured = false;
       if (!configured)

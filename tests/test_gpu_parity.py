@@ -124,8 +124,8 @@ def test_reduce_min_full_size_2pow28_properties(ob):
 @pytest.mark.parametrize("offset", [0, 1, 2, 3])
 @pytest.mark.parametrize("n", [296 * 8192 - 1, 296 * 8192 + 3, 5_000_001])
 def test_reduce_large_inputs_unaligned_starts_and_ragged_tails(ob, orc, offset, n):
-    """around and above the size where the reduction switches to the TMA-staged body (2 tiles of 8192 doubles per SM):
-    starts that are 8-byte but not 32-byte aligned (scalar head), tails that do not fill a tile"""
+    """medium inputs through the register-staged kernel: starts that are 8-byte but not 32-byte aligned (scalar head), tails that
+    do not fill a tile (the same sizes through the TMA-staged kernel: test_tma_staged_reduction_around_its_smallest_size)"""
     import torch
     from onika_b200 import parallel as P
     from tests._inputs import lcg_uniform
@@ -137,6 +137,33 @@ def test_reduce_large_inputs_unaligned_starts_and_ragged_tails(ob, orc, offset, 
     s1, s2 = host(P.reduce_sum(t))[0], host(P.reduce_sum(t))[0]
     assert s1 == s2
     assert abs(s1 - orc.reduce_sum_ld(h)) <= SUM_RTOL * np.abs(h).sum()
+
+
+def test_tma_staged_reduction_around_its_smallest_size(orc):
+    """the TMA-staged reduction kernel serves inputs >= 768 MiB by default; ONK_RED_KERNEL=tma lets it start at 2 tiles per SM so
+    that its edges can be tested at sizes the oracle finishes quickly: unaligned starts, ragged tails, all three operators"""
+    import subprocess
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import onika_b200 as ob
+from onika_b200 import parallel as P
+from tests._inputs import lcg_uniform
+import oracle
+ob.init(0)
+for n in (296 * 8192 - 1, 296 * 8192 + 3, 5_000_001):
+    for offset in (0, 1, 2, 3):
+        d = lcg_uniform(n + offset, 77, -1.0, 1.0)
+        t = torch.from_numpy(d).cuda()[offset:]
+        h = d[offset:]
+        assert float(P.reduce_min(t).item()) == oracle.orc.reduce_min(h), ("min", n, offset)
+        assert float(P.reduce_max(t).item()) == oracle.orc.reduce_max(h), ("max", n, offset)
+        s1, s2 = float(P.reduce_sum(t).item()), float(P.reduce_sum(t).item())
+        assert s1 == s2 and abs(s1 - oracle.orc.reduce_sum_ld(h)) <= 1e-12 * np.abs(h).sum(), ("sum", n, offset)
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env={**os.environ, "ONK_RED_KERNEL": "tma"})
+    assert r.returncode == 0 and "ok" in r.stdout, (r.stdout[-1000:], r.stderr[-2000:])
 
 
 def test_more_than_2pow32_elements(ob):
@@ -818,7 +845,7 @@ from tests._inputs import lcg_uniform, poisson_counts
 import oracle
 L = _capi.lib()
 ob.init(0)
-n = 4_000_003                                       # > 2 TMA tiles per SM: reduce_f64_tma_kernel
+n = 4_000_003                                       # > 2 TMA tiles per SM and ONK_RED_KERNEL=tma: reduce_f64_tma_kernel
 p = C.c_void_p(); _capi.check(L.onk_alloc(n * 8, 256, _capi.MEM_MANAGED, C.byref(p)))
 a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n,))
 d = lcg_uniform(n, 32, -1, 1)
@@ -850,7 +877,7 @@ _capi.check(L.onk_reduce_f64(_capi.OP_MIN, ph, n, out, 3)); _capi.check(L.onk_la
 assert res[0] == -9.0, "min over pinned host memory"
 print("managed ok")
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env={**os.environ, "ONK_RED_KERNEL": "tma"})
     assert r.returncode == 0 and "managed ok" in r.stdout, (r.returncode, r.stdout[-800:], r.stderr[-1500:])
 
 
