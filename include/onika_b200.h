@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ONK_ABI_VERSION 1
+#define ONK_ABI_VERSION 2   /* 2: onk_launch_ex, onk_xchg_status, onk_cell_sum_fields_f64; exchange buffers of 8 KiB (flagged packets) */
 
 /* ---- status ---- */
 #define ONK_OK               0

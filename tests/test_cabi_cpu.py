@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     L = _capi.lib()
     for name in hs:
         assert hasattr(L, name), name
-    assert L.onk_abi_version() == 1
+    assert L.onk_abi_version() == 2
 
 
 def test_only_cuda_runtime_is_linked_no_torch():

@@ -49,7 +49,7 @@ int main(void)
     subprocess.check_call(["gcc", "-std=c11", f"-I{INC}", str(src), "-o", str(exe), f"-L{os.path.dirname(lib)}", "-lonika_b200",
                            f"-Wl,-rpath,{os.path.dirname(lib)}"], env=_env())
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
-    assert out.splitlines()[0] == "1 32 1216 768 1088"          # SURVEY 8a row a23 layout probe
+    assert out.splitlines()[0] == "2 32 1216 768 1088"          # SURVEY 8a row a23 layout probe
 
 
 def test_cxx_front_end_compiles_in_a_host_only_translation_unit(tmp_path):
