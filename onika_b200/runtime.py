@@ -20,7 +20,8 @@ def init(device: int = 0, bind_torch_stream: bool = True) -> None:
     if bind_torch_stream:
         import sys
         torch = sys.modules.get("torch")
-        if torch is not None and torch.cuda.is_available():
+        # only when torch drives the same device (one process per GPU: torch.cuda.set_device(local) before init(local))
+        if torch is not None and torch.cuda.is_available() and torch.cuda.current_device() == device:
             bind_lane_to_torch_stream(0)
 
 
