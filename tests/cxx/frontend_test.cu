@@ -941,6 +941,63 @@ static int scenario_soatl_apply(Out& out, size_t n, bool timed)
   return 0;
 }
 
+// mixed column types through the vectorised apply kernel (E = 4 elements per thread: 32-byte, 16-byte, 4-byte accesses side by
+// side), read-only columns by value and by const reference, sub-ranges that start off the vector alignment (scalar kernel),
+// sizes below one tile; every device result next to the same operator run by the host loop
+static int scenario_soatl_apply_mixed(Out& out, size_t n)
+{
+  using namespace onika::soatl;
+  auto make = [&](auto& fa)
+  {
+    fa.resize(n);
+    for(size_t i=0;i<fa.capacity();i++)
+    { fa[particle_rx][i] = lcg(i,50,-1.0,1.0); fa[particle_atype][i] = (unsigned char)( lcg(i,51,0.0,200.0) ); fa[particle_mid][i] = int32_t( lcg(i,52,-1000.0,1000.0) ); fa[particle_dist][i] = float( lcg(i,53,0.0,4.0) ); }
+  };
+  auto dev = make_hybrid_field_arrays( cst::align<64>() , cst::chunk<16>() , particle_rx , particle_atype , particle_mid , particle_dist );
+  auto host = make_hybrid_field_arrays( cst::align<64>() , cst::chunk<16>() , particle_rx , particle_atype , particle_mid , particle_dist );
+  make(dev); make(host);
+  const double k = 0.25;
+  auto op = [k] ONIKA_HOST_DEVICE_FUNC (double& x, unsigned char t, int32_t& m, const float& d)
+    { x = x * k + double(t); m = m * 2 + int32_t(t) - int32_t(d); };                    // writes x and m, reads t (by value) and d (const reference)
+  parallel_apply( op , dev , particle_rx , particle_atype , particle_mid , particle_dist );           // device: vector kernel + scalar tail
+  apply( op , host , particle_rx , particle_atype , particle_mid , particle_dist );                   // host loop: the reference's sequential semantics
+  // a sub-range that starts at an odd element: columns are no longer vector-aligned -> one element per thread
+  const size_t first = ( n > 7 ) ? 3 : 0 , len = ( n > 7 ) ? n - 5 : n;
+  auto op2 = [] ONIKA_HOST_DEVICE_FUNC (float& d, double x) { d = d + float(x); };
+  parallel_apply( op2 , first , len , dev , particle_dist , particle_rx );
+  apply( op2 , first , len , host , particle_dist , particle_rx );
+  out.doubles( dev[particle_rx] , n ); out.doubles( host[particle_rx] , n );
+  out.bytes( dev[particle_atype] , n ); out.bytes( host[particle_atype] , n );
+  out.bytes( dev[particle_mid] , n*4 ); out.bytes( host[particle_mid] , n*4 );
+  out.bytes( dev[particle_dist] , n*4 ); out.bytes( host[particle_dist] , n*4 );
+  dev.clear(); host.clear();
+  return 0;
+}
+
+// sub-block items over an element LIST (indexed 1-D space) and with fewer items than one CTA holds sub-blocks
+static int scenario_sub_block_listed(Out& out, size_t ncells)
+{
+  std::vector<uint64_t> begin(ncells+1,0);
+  for(size_t c=0;c<ncells;c++) begin[c+1] = begin[c] + uint64_t( lcg(c,42,0.0,25.0) );          // 0..24 particles per cell, empty cells included
+  const size_t np = begin[ncells];
+  CudaMMVector<double> v( np > 0 ? np : 1 ); for(size_t i=0;i<np;i++) v[i] = lcg(i,40,-1.0,1.0);
+  CudaMMVector<uint64_t> b( ncells+1 ); for(size_t c=0;c<=ncells;c++) b[c] = begin[c];
+  CudaMMVector<double> sums( ncells , -7.0 );
+  CudaMMVector<ssize_t> idx; for(size_t c=0;c<ncells;c+=2) idx.push_back( ssize_t(c) );         // every other cell
+  PackedCellSumFunctor<16> f = { { v.data() , b.data() , sums.data() } };
+  BlockParallelForOptions o; o.max_block_size = 16;
+  ParallelExecutionSpace<1,1> space = { {0} , { ssize_t(idx.size()) } , std::span<const ssize_t>( idx.data() , idx.size() ) };
+  block_parallel_for( space , f , parallel_execution_context("cells","listed") , o );
+  out.doubles( sums.data() , ncells );
+  // 5 items only: less than the 16 sub-blocks of one CTA
+  CudaMMVector<double> few( ncells , -7.0 );
+  PackedCellSumFunctor<16> g = { { v.data() , b.data() , few.data() } };
+  block_parallel_for( std::min<size_t>( 5 , ncells ) , g , parallel_execution_context("cells","few") , o );
+  out.doubles( few.data() , ncells );
+  block_parallel_for( 0 , g , parallel_execution_context("cells","none") , o );                   // empty space: nothing runs
+  return 0;
+}
+
 // reduction helpers queued on lanes together with the kernels that produce their input
 static int scenario_reduce_helpers(Out& out, size_t rows, size_t cols)
 {
@@ -1038,6 +1095,8 @@ int main(int argc, char* argv[])
   else if( sc == "cells" ) rc = scenario_cells( out , arg(3,4096) );
   else if( sc == "listed" ) rc = scenario_listed( out );
   else if( sc == "soatl" ) rc = scenario_soatl( out , arg(3,53) );
+  else if( sc == "soatl_apply_mixed" ) rc = scenario_soatl_apply_mixed( out , arg(3,5000) );
+  else if( sc == "sub_block_listed" ) rc = scenario_sub_block_listed( out , arg(3,1001) );
   else if( sc == "soatl_apply" ) rc = scenario_soatl_apply( out , arg(3,100003) , arg(4,0) != 0 );
   else if( sc == "perf" ) rc = scenario_perf( out , arg(3,1<<27) );
   else if( sc == "block_vocabulary" ) rc = scenario_block_vocabulary( out , arg(3,1000) );

@@ -392,6 +392,40 @@ def test_cxx_multi_gpu_helper_world_of_one(tmp_path, orc):
     check_multi_gpu_outputs(run_multi_gpu_program(tmp_path, 1, n), orc, n, 1)
 
 
+@pytest.mark.parametrize("n", [1, 7, 1000, 1024, 4099, 200_003])
+def test_soatl_apply_mixed_types_device_equals_host_loop(prog, tmp_path, n):
+    """vectorised apply kernel with fp64 / u8 / i32 / fp32 columns side by side (32-, 4-, 16-, 16-byte accesses per thread),
+    read-only columns by value and by const reference, a sub-range off the vector alignment, sizes below one tile: the device
+    sweep leaves exactly the bytes the host loop (the reference's sequential semantics) leaves"""
+    raw = run(prog, tmp_path, "soatl_apply_mixed", n)
+    pos = 0
+    for width in (8, 1, 4, 4):
+        dev, host = raw[pos:pos + n * width], raw[pos + n * width:pos + 2 * n * width]
+        assert np.array_equal(dev, host), width
+        pos += 2 * n * width
+    assert pos == raw.size
+    x = raw[:n * 8].view(np.float64)
+    t = np.floor(lcg_uniform(n, 51, 0.0, 200.0)).astype(np.uint8)
+    assert np.array_equal(x, lcg_uniform(n, 50, -1.0, 1.0) * 0.25 + t.astype(np.float64))      # and what the operator says
+
+
+def test_sub_block_items_over_element_lists_and_tiny_spaces(prog, tmp_path, orc):
+    """SubBlockItems with an indexed 1-D space (every other cell), with fewer items than a CTA holds sub-blocks, with empty
+    cells and with an empty space: listed cells get their sums, the others stay untouched"""
+    ncells = 1001
+    d = run(prog, tmp_path, "sub_block_listed", ncells).view(np.float64)
+    sizes = np.floor(lcg_uniform(ncells, 42, 0.0, 25.0)).astype(np.uint64)
+    begin = np.zeros(ncells + 1, np.uint64)
+    begin[1:] = np.cumsum(sizes, dtype=np.uint64)
+    values = lcg_uniform(int(begin[-1]), 40, -1.0, 1.0)
+    want, _ = orc.cell_sum_packed(values, begin)
+    mag = np.add.reduceat(np.abs(np.append(values, 0.0)), np.minimum(begin[:-1].astype(np.int64), values.size)) * (sizes > 0) + 1e-300
+    listed, few = d[:ncells], d[ncells:]
+    assert np.all(listed[1::2] == -7.0) and np.all(np.abs(listed[0::2] - want[0::2]) <= SUM_RTOL * mag[0::2])
+    assert np.all(few[5:] == -7.0) and np.all(np.abs(few[:5] - want[:5]) <= SUM_RTOL * mag[:5])
+    assert np.all(listed[0::2][sizes[0::2] == 0] == 0.0)           # empty cells: exactly zero
+
+
 def test_host_compiler_and_nvcc_translation_units_share_one_context():
     """a plugin = .cpp files compiled by g++ plus .cu files compiled by nvcc: the default CUDA context is created by the g++
     half and read by the nvcc half (tests/cxx/mixed_tu_*): every shared type has one layout, the SM count that sizes fixed
