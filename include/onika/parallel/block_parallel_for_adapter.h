@@ -10,6 +10,7 @@
 //                           and an SM keeps 2048/bs items in flight instead of 16-32.  The ONIKA_CU_* block vocabulary means
 //                           the sub-block inside such a CTA (include/onika/cuda/cuda.h), so functor sources do not change;
 //                           opt-in because function-scope ONIKA_CU_BLOCK_SHARED variables would be shared by the sub-blocks.
+//                           bpf_sub_worksteal_kernel is the same with a fixed grid: every sub-block draws its own tickets.
 //   * bpf_box_kernel        same for 2D/3D boxes: items are box coordinates, first coordinate fastest
 //   * bpf_worksteal_kernel  fixed grid + atomic ticket (opts.fixed_gpu_grid_size), 1D only, as in the reference
 // Kernels live in the plugin's translation unit (device code for user functors never enters the runtime library);
@@ -64,6 +65,31 @@ namespace onika { namespace parallel {
         else func( idx[ start + ssize_t(i) ] );
         ONIKA_CU_BLOCK_SYNC();
       }
+    }
+
+    // the same CTAs of sub-blocks with a fixed grid and work stealing (opts.fixed_gpu_grid_size): every sub-block draws its own
+    // tickets -- its first lane one item ahead, the value reaches the others through a shuffle over the sub-block's lanes
+    template<bool Indexed, class ElementListT, class FuncT>
+    __global__ void __launch_bounds__(256)
+    bpf_sub_worksteal_kernel( const unsigned long long n , GPUKernelExecutionScratch* scratch , const ElementListT idx , __grid_constant__ const FuncT func , const ssize_t start )
+    {
+#     if defined(__CUDA_ARCH__)
+      const unsigned int lanes = ::onika::cuda::lane_group_mask( blockDim.x );
+      const int leader = __ffs( int(lanes) ) - 1;
+      unsigned long long * counter = & scratch->counters[GPUKernelExecutionScratch::WORKSTEALING_COUNTER];
+      unsigned long long next = 0;
+      if( threadIdx.x == 0 ) next = atomicAdd( counter , 1ull );
+      next = __shfl_sync( lanes , next , leader );
+      for(;;)
+      {
+        const unsigned long long i = next;
+        if( i >= n ) break;
+        if( threadIdx.x == 0 ) next = atomicAdd( counter , 1ull );     // the ticket of the following item travels while this one runs
+        if constexpr ( ! Indexed ) func( start + ssize_t(i) );
+        else func( idx[ start + ssize_t(i) ] );
+        next = __shfl_sync( lanes , next , leader );
+      }
+#     endif
     }
 
     // 2D/3D blocks follow ParallelExecutionContext::gpu_block_dims() (8x8x4 = 256 threads by default): no 128-thread bound here
@@ -207,10 +233,23 @@ namespace onika { namespace parallel {
           unsigned long long n = nitems;
           if( pec->m_grid_size.x > 0 )
           {
-            auto kernel = b200::bpf_worksteal_kernel<(ElemND>=1),ElementListT,FuncT>;
             GPUKernelExecutionScratch* scratch = pec->m_cuda_scratch.get();
             void* args[] = { &n , &scratch , &elements , (void*) &m_func , &start };
-            b200::launch( kernel , pec->m_grid_size.x , pec->m_block_size , pec->m_lane , args );
+            bool packed = false;
+            if constexpr ( functor_sub_block_items_v<FuncT> )
+            {
+              if( threads <= 32 && ( threads & ( threads - 1 ) ) == 0 )
+              {
+                auto kernel = b200::bpf_sub_worksteal_kernel<(ElemND>=1),ElementListT,FuncT>;
+                b200::launch( kernel , pec->m_grid_size.x , onikaDim3_t{ threads , 256u / threads , 1 } , pec->m_lane , args , ONK_LAUNCH_SUB_BLOCKS );
+                packed = true;
+              }
+            }
+            if( ! packed )
+            {
+              auto kernel = b200::bpf_worksteal_kernel<(ElemND>=1),ElementListT,FuncT>;
+              b200::launch( kernel , pec->m_grid_size.x , pec->m_block_size , pec->m_lane , args );
+            }
           }
           else
           {

@@ -995,6 +995,12 @@ static int scenario_sub_block_listed(Out& out, size_t ncells)
   block_parallel_for( std::min<size_t>( 5 , ncells ) , g , parallel_execution_context("cells","few") , o );
   out.doubles( few.data() , ncells );
   block_parallel_for( 0 , g , parallel_execution_context("cells","none") , o );                   // empty space: nothing runs
+  // fixed grid + work stealing with sub-blocks: every sub-block draws its own tickets
+  CudaMMVector<double> ws( ncells , -7.0 );
+  PackedCellSumFunctor<16> h = { { v.data() , b.data() , ws.data() } };
+  BlockParallelForOptions ow; ow.max_block_size = 16; ow.fixed_gpu_grid_size = true;
+  block_parallel_for( ncells , h , parallel_execution_context("cells","worksteal") , ow );
+  out.doubles( ws.data() , ncells );
   return 0;
 }
 

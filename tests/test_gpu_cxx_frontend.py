@@ -420,7 +420,8 @@ def test_sub_block_items_over_element_lists_and_tiny_spaces(prog, tmp_path, orc)
     values = lcg_uniform(int(begin[-1]), 40, -1.0, 1.0)
     want, _ = orc.cell_sum_packed(values, begin)
     mag = np.add.reduceat(np.abs(np.append(values, 0.0)), np.minimum(begin[:-1].astype(np.int64), values.size)) * (sizes > 0) + 1e-300
-    listed, few = d[:ncells], d[ncells:]
+    listed, few, ws = d[:ncells], d[ncells:2 * ncells], d[2 * ncells:]
+    assert ws.size == ncells and np.all(np.abs(ws - want) <= SUM_RTOL * mag)       # fixed grid + work stealing, sub-blocks
     assert np.all(listed[1::2] == -7.0) and np.all(np.abs(listed[0::2] - want[0::2]) <= SUM_RTOL * mag[0::2])
     assert np.all(few[5:] == -7.0) and np.all(np.abs(few[:5] - want[:5]) <= SUM_RTOL * mag[:5])
     assert np.all(listed[0::2][sizes[0::2] == 0] == 0.0)           # empty cells: exactly zero
