@@ -782,20 +782,25 @@ def run_ours(args) -> int:
     # peer memory (onk_reduce_xchg_f64).  --exchange nccl: separate NCCL all-reduce(MIN) after the kernel.
     xchg = None
     xchg_lanes = None
-    if world > 1 and args.exchange == "fused":
-        try:
-            xchg = D.PeerExchange()
-            xchg_lanes = (D.PeerExchange(), D.PeerExchange())     # one exchange per lane for the C5 sequence
-            ok = 1
-        except Exception as ex:   # no peer access / CUDA IPC on this box: every rank must take the same path
-            print(f"[bench] rank {rank}: fused exchange unavailable ({str(ex)[:120]}); using NCCL", file=sys.stderr)
-            ok = 0
-        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            if xchg is not None:
-                xchg.close()
-            xchg = xchg_lanes = None
+    xchg_transport = None
+    if world > 1 and args.exchange in ("fused", "fused-host"):
+        # device memory over NVLink first; where CUDA IPC / peer access is refused, the same exchange through pinned host
+        # memory in POSIX shared memory; NCCL only if neither can be set up.  Every rank must take the same path.
+        for transport in (("device", "host") if args.exchange == "fused" else ("host",)):
+            made = []
+            try:
+                made = [D.PeerExchange(transport=transport) for _ in range(3)]      # headline + one exchange per lane of the C5 sequence
+                ok = 1
+            except Exception as ex:
+                print(f"[bench] rank {rank}: fused exchange over {transport} memory unavailable ({str(ex)[:120]})", file=sys.stderr)
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                xchg, xchg_lanes, xchg_transport = made[0], (made[1], made[2]), transport
+                break
+            for m in made:
+                m.close()
 
     flush = _L2Flush(torch, ob, P) if n * 8 < (512 << 20) else None   # strong scaling at large N: the shard may fit L2
 
@@ -997,7 +1002,7 @@ def run_ours(args) -> int:
                 cpu_baseline = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
 
     if rank == 0:
-        method = {"sharding": (f"element range x{world}; one fp64 partial per rank and step, combined " + ("inside the reduction kernel over NVLink peer memory (rank order)" if xchg is not None else "by an NCCL all-reduce(min)")) if world > 1 else "single GPU",
+        method = {"sharding": (f"element range x{world}; one fp64 partial per rank and step, combined " + (("inside the reduction kernel over NVLink peer memory (rank order)" if xchg_transport == "device" else "inside the reduction kernel through pinned host memory (rank order; no peer access on this box)") if xchg is not None else "by an NCCL all-reduce(min)")) if world > 1 else "single GPU",
                   "timing": "CUDA events on the launching stream, max over ranks",
                   "before_the_timed_region": f"{SPINUP} untimed launches of the same step (clock spin-up after host-side preparation), then the {W} warm-up steps, no host work in between"}
         line = {
@@ -1072,7 +1077,7 @@ def main() -> int:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: 2^28 doubles per GPU (default, the driver's efficiency arithmetic); strong: 2^28 doubles in total")
     ap.add_argument("--cpu-seconds", type=float, default=6.0, help="wall budget per CPU-baseline variant")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="N>1: cross-GPU combine inside the kernel (NVLink peer stores) or a separate NCCL all-reduce")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "fused-host", "nccl"], help="N>1: cross-GPU combine inside the kernel (NVLink peer stores; fused-host: through pinned host memory) or a separate NCCL all-reduce")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary per-config kernel timings")
     ap.add_argument("--profile-mode", action="store_true", help="timed region + roofline only (for ncu runs): no e2e, no CPU baseline, no extras")
     args = ap.parse_args()

@@ -171,7 +171,15 @@ int onk_combine_f64(int op, const double* partials_dev, uint32_t count, double* 
 #define ONK_XCHG_MAX_VALUES    8
 #define ONK_IPC_HANDLE_BYTES  64
 typedef struct onk_xchg onk_xchg;
+/* where the exchange buffers live.  DEVICE (default): device memory shared through CUDA IPC, peer stores over NVLink / NVSwitch.
+ * HOST: pinned host memory shared through POSIX shared memory and mapped into every rank's device address space -- the same
+ * packets travel over PCIe, a few microseconds slower per exchange, and no peer access between the GPUs is needed: the
+ * fallback for boxes (or containers) where cudaIpcOpenMemHandle is refused.  All ranks of an exchange use the same transport;
+ * onk_xchg_create takes it from the environment (ONK_XCHG_TRANSPORT=host), onk_xchg_create_ex from its argument. */
+#define ONK_XCHG_TRANSPORT_DEVICE 0
+#define ONK_XCHG_TRANSPORT_HOST   1
 int onk_xchg_create(int rank, int world, onk_xchg** x);
+int onk_xchg_create_ex(int rank, int world, int transport, onk_xchg** x);
 int onk_xchg_export(onk_xchg* x, unsigned char handle[ONK_IPC_HANDLE_BYTES]);
 int onk_xchg_connect(onk_xchg* x, const unsigned char* handles /* world x ONK_IPC_HANDLE_BYTES, rank order */);
 int onk_xchg_destroy(onk_xchg* x);

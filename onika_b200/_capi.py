@@ -18,6 +18,7 @@ LANE_DEFAULT, LANE_ALL, MAX_LANES = -1, -2, 256
 MEM_DEVICE, MEM_MANAGED, MEM_PINNED = 0, 1, 2
 OP_MIN, OP_MAX, OP_SUM = 0, 1, 2
 ONK_IPC_HANDLE_BYTES, ONK_XCHG_MAX_WORLD = 64, 16
+XCHG_TRANSPORT_DEVICE, XCHG_TRANSPORT_HOST = 0, 1
 
 vp, u64, u32, i32, dbl, sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_double, C.c_size_t
 P = C.POINTER
@@ -59,6 +60,7 @@ PROTOTYPES = {
     "onk_reduce_f64": (i32, [i32, vp, u64, vp, i32]),
     "onk_combine_f64": (i32, [i32, vp, u32, vp, i32]),
     "onk_xchg_create": (i32, [i32, i32, P(vp)]),
+    "onk_xchg_create_ex": (i32, [i32, i32, i32, P(vp)]),
     "onk_xchg_export": (i32, [vp, C.c_char_p]),
     "onk_xchg_connect": (i32, [vp, C.c_char_p]),
     "onk_xchg_destroy": (i32, [vp]),

@@ -14,6 +14,10 @@
 //     summation tree depends only on (n, grid) => run-to-run reproducible sums.
 #include "onk_internal.cuh"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
 namespace onk
 {
   constexpr int RED_UNROLL = 4;                                  // 4 x 32 B per thread per tile (tools/tune.cu sweep: every shape lands within 2 % of 7.3 TB/s)
@@ -377,12 +381,39 @@ namespace onk
 
 struct onk_xchg
 {
-  XchgBuffer* local = nullptr;
+  XchgBuffer* local = nullptr;                   // device transport: cudaMalloc'ed; host transport: device view of the local shared-memory segment
   XchgParams  params{};
   bool        connected = false;
-  void*       opened[ONK_XCHG_MAX_WORLD] = {};
+  int         transport = ONK_XCHG_TRANSPORT_DEVICE;
+  void*       opened[ONK_XCHG_MAX_WORLD] = {};   // device transport: IPC mappings of the peers' buffers
   unsigned long long* error_host = nullptr;      // pinned + mapped: written by the kernels on a timeout, read by the host
+  // host transport: POSIX shared-memory segments (own + peers'), registered with the CUDA runtime
+  void*       shm_map[ONK_XCHG_MAX_WORLD] = {};
+  char        shm_name[48] = "";
 };
+
+namespace onk
+{
+  static const char XCHG_HOST_MAGIC[4] = { 'O', 'N', 'K', 'H' };
+
+  // maps (and, for the owner, creates) a shared-memory segment and registers it with the CUDA runtime; returns the device view
+  static int xchg_map_segment(const char* name, bool create, void** host_map, XchgBuffer** dev_view)
+  {
+    const int fd = shm_open(name, create ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
+    if (fd < 0) { set_error("exchange (host transport): shm_open(%s) failed", name); return ONK_ERR_STATE; }
+    if (create && ftruncate(fd, ONK_XCHG_BYTES) != 0) { close(fd); shm_unlink(name); set_error("exchange (host transport): ftruncate failed"); return ONK_ERR_NOMEM; }
+    void* p = mmap(nullptr, ONK_XCHG_BYTES, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { if (create) shm_unlink(name); set_error("exchange (host transport): mmap failed"); return ONK_ERR_NOMEM; }
+    if (create) memset(p, 0, ONK_XCHG_BYTES);
+    cudaError_t e = cudaHostRegister(p, ONK_XCHG_BYTES, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    void* d = nullptr;
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&d, p, 0);
+    if (e != cudaSuccess) { munmap(p, ONK_XCHG_BYTES); if (create) shm_unlink(name); ONK_CUDA(e); }
+    *host_map = p; *dev_view = (XchgBuffer*)d;
+    return ONK_OK;
+  }
+}
 
 namespace onk
 {
@@ -398,17 +429,29 @@ namespace onk
 
 extern "C" {
 
-int onk_xchg_create(int rank, int world, onk_xchg** x)
+int onk_xchg_create_ex(int rank, int world, int transport, onk_xchg** x)
 {
   ONK_REQUIRE(x != nullptr, "onk_xchg_create: null argument");
   ONK_REQUIRE(world >= 1 && world <= ONK_XCHG_MAX_WORLD && rank >= 0 && rank < world, "onk_xchg_create: bad rank/world %d/%d", rank, world);
+  ONK_REQUIRE(transport == ONK_XCHG_TRANSPORT_DEVICE || transport == ONK_XCHG_TRANSPORT_HOST, "onk_xchg_create: unknown transport %d", transport);
   if (int rc = require_init()) return rc;
   onk_xchg* h = new onk_xchg();
-  cudaError_t e = cudaMalloc((void**)&h->local, ONK_XCHG_BYTES);      // plain cudaMalloc: exportable through CUDA IPC
-  if (e == cudaSuccess) e = cudaMemset(h->local, 0, ONK_XCHG_BYTES);
-  if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->error_host, 64, cudaHostAllocMapped | cudaHostAllocPortable);
-  if (e != cudaSuccess) { if (h->local) cudaFree(h->local); delete h; ONK_CUDA(e); }
+  h->transport = transport;
+  cudaError_t e = cudaHostAlloc((void**)&h->error_host, 64, cudaHostAllocMapped | cudaHostAllocPortable);
+  if (e != cudaSuccess) { delete h; ONK_CUDA(e); }
   *h->error_host = 0ull;
+  if (transport == ONK_XCHG_TRANSPORT_DEVICE)
+  {
+    e = cudaMalloc((void**)&h->local, ONK_XCHG_BYTES);      // plain cudaMalloc: exportable through CUDA IPC
+    if (e == cudaSuccess) e = cudaMemset(h->local, 0, ONK_XCHG_BYTES);
+    if (e != cudaSuccess) { if (h->local) cudaFree(h->local); cudaFreeHost(h->error_host); delete h; ONK_CUDA(e); }
+  }
+  else
+  {
+    static std::atomic<unsigned> seq{0};
+    snprintf(h->shm_name, sizeof(h->shm_name), "/onkx_%d_%u_%d", (int)getpid(), seq.fetch_add(1), rank);
+    if (int rc = xchg_map_segment(h->shm_name, true, &h->shm_map[rank], &h->local)) { cudaFreeHost(h->error_host); delete h; return rc; }
+  }
   h->params.rank = rank; h->params.world = world;
   h->params.peer[rank] = h->local;
   h->params.error_host = h->error_host;          // unified addressing: the mapped host pointer is valid on the device
@@ -417,10 +460,24 @@ int onk_xchg_create(int rank, int world, onk_xchg** x)
   return ONK_OK;
 }
 
+int onk_xchg_create(int rank, int world, onk_xchg** x)
+{
+  // ONK_XCHG_TRANSPORT=host selects the shared-memory transport for every exchange of the process (boxes without peer access)
+  static const int transport = []{ const char* e = getenv("ONK_XCHG_TRANSPORT"); return (e && e[0] == 'h') ? ONK_XCHG_TRANSPORT_HOST : ONK_XCHG_TRANSPORT_DEVICE; }();
+  return onk_xchg_create_ex(rank, world, transport, x);
+}
+
 int onk_xchg_export(onk_xchg* x, unsigned char handle[ONK_IPC_HANDLE_BYTES])
 {
   ONK_REQUIRE(x != nullptr && handle != nullptr, "onk_xchg_export: null argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == ONK_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+  if (x->transport == ONK_XCHG_TRANSPORT_HOST)
+  {
+    memset(handle, 0, ONK_IPC_HANDLE_BYTES);
+    memcpy(handle, XCHG_HOST_MAGIC, 4);
+    strncpy((char*)handle + 4, x->shm_name, ONK_IPC_HANDLE_BYTES - 5);
+    return ONK_OK;
+  }
   cudaIpcMemHandle_t h;
   ONK_CUDA(cudaIpcGetMemHandle(&h, x->local));
   memcpy(handle, &h, sizeof(h));
@@ -433,8 +490,18 @@ int onk_xchg_connect(onk_xchg* x, const unsigned char* handles)
   for (int r = 0; r < x->params.world; r++)
   {
     if (r == x->params.rank) continue;
+    const unsigned char* hr = handles + (size_t)r * ONK_IPC_HANDLE_BYTES;
+    if (x->transport == ONK_XCHG_TRANSPORT_HOST)
+    {
+      ONK_REQUIRE(memcmp(hr, XCHG_HOST_MAGIC, 4) == 0, "onk_xchg_connect: rank %d did not export a host-transport handle (all ranks must use the same transport)", r);
+      char name[ONK_IPC_HANDLE_BYTES]; memcpy(name, hr + 4, ONK_IPC_HANDLE_BYTES - 4); name[ONK_IPC_HANDLE_BYTES - 5] = 0;
+      XchgBuffer* d = nullptr;
+      if (int rc = xchg_map_segment(name, false, &x->shm_map[r], &d)) return rc;
+      x->params.peer[r] = d;
+      continue;
+    }
     cudaIpcMemHandle_t h;
-    memcpy(&h, handles + (size_t)r * ONK_IPC_HANDLE_BYTES, sizeof(h));
+    memcpy(&h, hr, sizeof(h));
     void* p = nullptr;
     ONK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     x->opened[r] = p;
@@ -449,7 +516,9 @@ int onk_xchg_destroy(onk_xchg* x)
   if (!x) return ONK_OK;
   cudaDeviceSynchronize();
   for (int r = 0; r < ONK_XCHG_MAX_WORLD; r++) if (x->opened[r]) cudaIpcCloseMemHandle(x->opened[r]);
-  if (x->local) cudaFree(x->local);
+  for (int r = 0; r < ONK_XCHG_MAX_WORLD; r++) if (x->shm_map[r]) { cudaHostUnregister(x->shm_map[r]); munmap(x->shm_map[r], ONK_XCHG_BYTES); }
+  if (x->transport == ONK_XCHG_TRANSPORT_HOST) { if (x->shm_name[0]) shm_unlink(x->shm_name); }
+  else if (x->local) cudaFree(x->local);
   if (x->error_host) cudaFreeHost(x->error_host);
   delete x;
   return ONK_OK;

@@ -72,15 +72,21 @@ class PeerExchange:
     peers' flags and folds the partials in rank order.  No NCCL call on the data path.  All ranks must issue the same
     sequence of reduce() calls."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, transport=None):
+        """transport: None = the library's default (device memory over NVLink, or ONK_XCHG_TRANSPORT), "device", or "host"
+        (pinned host memory in POSIX shared memory: no peer access needed, a few microseconds slower per exchange)"""
         import ctypes as C
         import torch.distributed as dist
-        from ._capi import check, lib
+        from ._capi import check, lib, XCHG_TRANSPORT_DEVICE, XCHG_TRANSPORT_HOST
         self._C, self._check, self._lib = C, check, lib()
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.handle = C.c_void_p()
-        check(self._lib.onk_xchg_create(self.rank, self.world, C.byref(self.handle)))
+        if transport is None:
+            check(self._lib.onk_xchg_create(self.rank, self.world, C.byref(self.handle)))
+        else:
+            t = {"device": XCHG_TRANSPORT_DEVICE, "host": XCHG_TRANSPORT_HOST}[transport]
+            check(self._lib.onk_xchg_create_ex(self.rank, self.world, t, C.byref(self.handle)))
         _share_handles(lambda buf: self._lib.onk_xchg_export(self.handle, buf),
                        lambda allh: self._lib.onk_xchg_connect(self.handle, allh), group, "the exchange buffer")
 

@@ -194,8 +194,9 @@ def check_xs_move(rank, world, x, orc, n=1 << 20):
     return err.done()
 
 
-def run_checks(rank: int, world: int, which=None) -> dict:
-    """all checks (or those named in `which`) on the calling process group; lane 0 must be usable.  Collective."""
+def run_checks(rank: int, world: int, which=None, transport=None) -> dict:
+    """all checks (or those named in `which`) on the calling process group; lane 0 must be usable.  Collective.
+    transport: exchange buffers in "device" memory (CUDA IPC, default) or in "host" shared memory (no peer access needed)"""
     import os
     import torch
     import oracle
@@ -206,7 +207,7 @@ def run_checks(rank: int, world: int, which=None) -> dict:
     except AttributeError:
         ncpu = os.cpu_count() or 1
     orc.set_num_threads(max(1, ncpu // max(1, world)))
-    x, x2 = D.PeerExchange(), D.PeerExchange()
+    x, x2 = D.PeerExchange(transport=transport), D.PeerExchange(transport=transport)
     out = {}
     table = {
         "fused_reduce_min_max_sum": lambda: check_fused_reduce(rank, world, x, orc),

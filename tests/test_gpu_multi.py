@@ -301,7 +301,7 @@ def test_cell_grid_z_slabs_two_gpus(orc):
 
 
 # ---------------------------------------------------------------- the checks bench.py reports under `checks` at N > 1
-def _worker_checks(rank, world, port, q):
+def _worker_checks(rank, world, port, q, transport=None, which=None):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -312,7 +312,7 @@ def _worker_checks(rank, world, port, q):
     from tests import _multigpu_checks
     ob.init(rank)
     ob.bind_lane_to_torch_stream(0)
-    q.put((rank, _multigpu_checks.run_checks(rank, world)))
+    q.put((rank, _multigpu_checks.run_checks(rank, world, which=which, transport=transport)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -336,6 +336,30 @@ def test_bench_multi_gpu_checks_two_gpus():
         assert p.exitcode == 0
     for rank in range(world):
         assert len(got[rank]) == 5 and all(v == "ok" for v in got[rank].values()), got[rank]
+
+
+def test_exchange_through_host_shared_memory_two_gpus():
+    """ONK_XCHG_TRANSPORT_HOST: the exchange buffers live in pinned host memory shared through POSIX shared memory (the fallback
+    where CUDA IPC / peer access is refused): fused reductions, the k-value all-reduce, the C4 totals and the C5 sequence give the
+    same bits as over NVLink"""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    which = ("fused_reduce_min_max_sum", "allreduce_multi_8_values_3_ops", "c4_cell_sums_z_slabs", "c5_lane_sequence_sharded_rows")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_checks, args=(r, world, port, q, "host", which)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in range(world):
+        assert len(got[rank]) == 4 and all(v == "ok" for v in got[rank].values()), got[rank]
 
 
 def test_cxx_multi_gpu_helper_two_processes(tmp_path, orc):

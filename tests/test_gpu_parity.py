@@ -685,6 +685,40 @@ def test_host_buffer_entry_points(ob, orc):
     assert np.array_equal(a, ao)
 
 
+@pytest.mark.parametrize("transport", [0, 1])
+def test_exchange_world_of_one_both_transports(ob, orc, transport):
+    """an exchange with a single rank runs the whole packet protocol against its own buffer -- in device memory (transport 0)
+    and in pinned host memory shared through POSIX shared memory (transport 1, the fallback without peer access): fused
+    reductions equal the plain ones bit for bit, the k-value all-reduce folds from the identity, the status stays healthy"""
+    import torch
+    from onika_b200 import _capi, parallel as P
+    from tests._inputs import lcg_uniform
+    L = _capi.lib()
+    x = C.c_void_p()
+    _capi.check(L.onk_xchg_create_ex(0, 1, transport, C.byref(x)))
+    handle = C.create_string_buffer(_capi.ONK_IPC_HANDLE_BYTES)
+    _capi.check(L.onk_xchg_export(x, handle))
+    assert (handle.raw[:4] == b"ONKH") == (transport == 1)
+    d = lcg_uniform(3_000_001, 91, -1.0, 1.0)
+    t = torch.from_numpy(d).cuda()
+    out = torch.empty(1, dtype=torch.float64, device="cuda")
+    for rep in range(3):
+        for op, plain in ((_capi.OP_MIN, P.reduce_min), (_capi.OP_MAX, P.reduce_max), (_capi.OP_SUM, P.reduce_sum)):
+            _capi.check(L.onk_reduce_xchg_f64(op, t.data_ptr(), t.numel(), out.data_ptr(), x, 0))
+            ob.lane_sync(0)
+            assert host(out)[0] == host(plain(t))[0]
+    vals = torch.tensor([1.5, -2.0, 3.25], dtype=torch.float64, device="cuda")
+    _capi.check(L.onk_xchg_allreduce_f64(x, _capi.OP_SUM, vals.data_ptr(), 3, 0))
+    _capi.check(L.onk_xchg_barrier(x, 0))
+    ob.lane_sync(0)
+    assert host(vals).tolist() == [1.5, -2.0, 3.25]
+    failed = C.c_uint64(7)
+    _capi.check(L.onk_xchg_status(x, C.byref(failed)))
+    assert failed.value == 0
+    _capi.check(L.onk_xchg_destroy(x))
+    assert L.onk_xchg_create_ex(0, 1, 5, C.byref(x)) == _capi.ERR_ARG
+
+
 def test_errors_and_memory_api(ob):
     from onika_b200 import _capi
     L = _capi.lib()
