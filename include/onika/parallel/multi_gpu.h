@@ -54,10 +54,13 @@ namespace onika { namespace parallel {
   {
   public:
     // allgather( const void* mine , void* all , size_t bytes_per_rank ) -> bool : collective over the `world` processes
+    // transport: ONK_XCHG_TRANSPORT_DEVICE (device memory over NVLink, needs peer access) or ONK_XCHG_TRANSPORT_HOST (pinned host
+    // memory in POSIX shared memory, works everywhere); -1 = the library's default (ONK_XCHG_TRANSPORT in the environment)
     template<class AllGatherF>
-    inline MultiGpuExchange( int rank , int world , AllGatherF && allgather ) : m_rank(rank) , m_world(world)
+    inline MultiGpuExchange( int rank , int world , AllGatherF && allgather , int transport = -1 ) : m_rank(rank) , m_world(world)
     {
-      ONIKA_B200_CHECK( onk_xchg_create( rank , world , & m_x ) );
+      if( transport < 0 ) ONIKA_B200_CHECK( onk_xchg_create( rank , world , & m_x ) );
+      else ONIKA_B200_CHECK( onk_xchg_create_ex( rank , world , transport , & m_x ) );
       ONIKA_B200_CHECK( onk_alloc( ONK_XCHG_MAX_VALUES * sizeof(double) , 64 , ONK_MEM_PINNED , (void**) & m_values ) );
       if( world > 1 )
       {
@@ -69,8 +72,8 @@ namespace onika { namespace parallel {
       }
     }
     // file rendezvous in `dir` (unique `tag` per exchange)
-    inline MultiGpuExchange( int rank , int world , const std::string& dir , const std::string& tag )
-      : MultiGpuExchange( rank , world , [&](const void* mine, void* all, size_t n) { return file_allgather( dir , tag , rank , world , mine , all , n ); } ) {}
+    inline MultiGpuExchange( int rank , int world , const std::string& dir , const std::string& tag , int transport = -1 )
+      : MultiGpuExchange( rank , world , [&](const void* mine, void* all, size_t n) { return file_allgather( dir , tag , rank , world , mine , all , n ); } , transport ) {}
     inline ~MultiGpuExchange() { if( m_values ) onk_free( m_values , 0 ); if( m_x ) onk_xchg_destroy( m_x ); }
     MultiGpuExchange( const MultiGpuExchange& ) = delete;
     MultiGpuExchange& operator = ( const MultiGpuExchange& ) = delete;

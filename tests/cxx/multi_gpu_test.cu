@@ -1,5 +1,5 @@
 // One process per GPU, no MPI and no Python: the C++ multi-GPU helper (onika/parallel/multi_gpu.h).
-//   multi_gpu_test <rank> <world> <rendezvous-dir> <n> <out-file>
+//   multi_gpu_test <rank> <world> <rendezvous-dir> <n> <out-file> [transport: 0 device memory (default), 1 host shared memory]
 // Each rank reduces its contiguous shard of a deterministic array with the fused reduce+exchange kernel (min, max, sum) and
 // all-reduces three host scalars in the reference's all_reduce_multi call shape; results go to <out-file> as doubles.
 #include <onika/cuda/cuda_context.h>
@@ -26,7 +26,7 @@ int main(int argc, char* argv[])
   setenv( "ONIKA_B200_DEVICE" , argv[1] , 1 );
   if( onika::cuda::CudaContext::default_cuda_ctx() == nullptr ) return 9;
   using namespace onika::parallel;
-  MultiGpuExchange x( rank , world , dir , "mgx" );
+  MultiGpuExchange x( rank , world , dir , "mgx" , argc > 6 ? std::atoi(argv[6]) : -1 );
 
   const uint64_t b = ( uint64_t(rank) * n ) / world , e = ( uint64_t(rank+1) * n ) / world;
   std::vector<double> h( e - b );

@@ -354,14 +354,15 @@ def _multi_gpu_expected(orc, n, world):
     return d, [a, float(np.float32(f)), float(int(cnt)), -3.0, -3.0 + (world - 1)]
 
 
-def run_multi_gpu_program(tmp_path, world, n):
+def run_multi_gpu_program(tmp_path, world, n, transport=None):
     from onika_b200 import cxx
     exe = cxx.program_path("multi_gpu_test")
     if not os.path.exists(exe):
         cxx.build_all()
-    rdv = os.path.join(tmp_path, f"rdv{world}_{n}")
+    rdv = os.path.join(tmp_path, f"rdv{world}_{n}_{transport}")
     os.makedirs(rdv, exist_ok=True)
-    procs = [subprocess.Popen([exe, str(r), str(world), rdv, str(n), os.path.join(rdv, f"out{r}.bin")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    procs = [subprocess.Popen([exe, str(r), str(world), rdv, str(n), os.path.join(rdv, f"out{r}.bin")] + ([str(transport)] if transport is not None else []),
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE)
              for r in range(world)]
     outs = []
     for r, p in enumerate(procs):
@@ -390,6 +391,7 @@ def test_cxx_multi_gpu_helper_world_of_one(tmp_path, orc):
     the whole protocol runs, the folds start from the identity"""
     n = 1_000_003
     check_multi_gpu_outputs(run_multi_gpu_program(tmp_path, 1, n), orc, n, 1)
+    check_multi_gpu_outputs(run_multi_gpu_program(tmp_path, 1, n, transport=1), orc, n, 1)     # buffers in host shared memory
 
 
 @pytest.mark.parametrize("n", [1, 7, 1000, 1024, 4099, 200_003])

@@ -371,3 +371,4 @@ def test_cxx_multi_gpu_helper_two_processes(tmp_path, orc):
     from tests.test_gpu_cxx_frontend import run_multi_gpu_program, check_multi_gpu_outputs
     for n in (4_000_003, 5):
         check_multi_gpu_outputs(run_multi_gpu_program(str(tmp_path), 2, n), orc, n, 2)
+    check_multi_gpu_outputs(run_multi_gpu_program(str(tmp_path), 2, 100_001, transport=1), orc, 100_001, 2)      # host shared memory
