@@ -719,6 +719,62 @@ def test_exchange_world_of_one_both_transports(ob, orc, transport):
     assert L.onk_xchg_create_ex(0, 1, 5, C.byref(x)) == _capi.ERR_ARG
 
 
+def test_exchange_two_ranks_in_one_process_and_a_missing_peer(ob, orc):
+    """the whole two-rank exchange protocol on ONE GPU: with the host-memory transport both ranks' exchanges can live in one
+    process (their kernels run on two lanes); fused min / max / sum and the k-value all-reduce must give both ranks the same
+    bits = the rank-order fold of the ranks' plain results.  Then rank 1 stops showing up: rank 0's next call times out
+    (~10 s), returns NaN for every operator, reports the failed call through onk_xchg_status and refuses further calls."""
+    import math
+    import torch
+    from onika_b200 import _capi, parallel as P
+    from tests._inputs import lcg_uniform
+    L = _capi.lib()
+    xs = [C.c_void_p(), C.c_void_p()]
+    handles = b""
+    for r in range(2):
+        _capi.check(L.onk_xchg_create_ex(r, 2, _capi.XCHG_TRANSPORT_HOST, C.byref(xs[r])))
+        h = C.create_string_buffer(_capi.ONK_IPC_HANDLE_BYTES)
+        _capi.check(L.onk_xchg_export(xs[r], h))
+        handles += h.raw
+    for r in range(2):
+        _capi.check(L.onk_xchg_connect(xs[r], handles))
+    d = lcg_uniform(2_500_003, 93, -1.0, 1.0)
+    cut = 1_000_001
+    shards = [torch.from_numpy(d[:cut]).cuda(), torch.from_numpy(d[cut:]).cuda()]
+    outs = [torch.empty(1, dtype=torch.float64, device="cuda") for _ in range(2)]
+    lanes = (1, 2)
+    calls = 0
+    for rep in range(2):
+        for op, plain, fold in ((_capi.OP_MIN, P.reduce_min, min), (_capi.OP_MAX, P.reduce_max, max), (_capi.OP_SUM, P.reduce_sum, None)):
+            for r in range(2):
+                _capi.check(L.onk_reduce_xchg_f64(op, shards[r].data_ptr(), shards[r].numel(), outs[r].data_ptr(), xs[r], lanes[r]))
+            calls += 1
+            ob.lane_sync(1); ob.lane_sync(2)
+            parts = [host(plain(shards[r]))[0] for r in range(2)]
+            want = fold(parts) if fold else (0.0 + parts[0]) + parts[1]          # rank-order fold from the identity
+            assert host(outs[0])[0] == host(outs[1])[0] == want, (op, rep)
+    assert host(outs[0])[0] != 0.0 and abs(host(outs[0])[0] - orc.reduce_sum_ld(d)) <= SUM_RTOL * np.abs(d).sum()
+    vals = [torch.tensor([1.5, -2.0, 3.25, 1e-3], dtype=torch.float64, device="cuda") * (r + 1) for r in range(2)]
+    for r in range(2):
+        _capi.check(L.onk_xchg_allreduce_f64(xs[r], _capi.OP_MAX, vals[r].data_ptr(), 4, lanes[r]))
+    calls += 1
+    ob.lane_sync(1); ob.lane_sync(2)
+    assert host(vals[0]).tolist() == host(vals[1]).tolist() == [3.0, -2.0, 6.5, 2e-3]
+    failed = C.c_uint64(9)
+    _capi.check(L.onk_xchg_status(xs[0], C.byref(failed)))
+    assert failed.value == 0
+    # rank 1 goes missing
+    _capi.check(L.onk_reduce_xchg_f64(_capi.OP_MIN, shards[0].data_ptr(), shards[0].numel(), outs[0].data_ptr(), xs[0], 1))
+    ob.lane_sync(1)                                             # returns after the ~10 s device-side timeout
+    assert math.isnan(host(outs[0])[0])
+    _capi.check(L.onk_xchg_status(xs[0], C.byref(failed)))
+    assert failed.value == calls + 1
+    assert L.onk_xchg_barrier(xs[0], 1) == _capi.ERR_STATE and b"did not show up" in L.onk_last_error()
+    assert L.onk_reduce_xchg_f64(_capi.OP_SUM, shards[0].data_ptr(), 8, outs[0].data_ptr(), xs[0], 1) == _capi.ERR_STATE
+    for r in range(2):
+        _capi.check(L.onk_xchg_destroy(xs[r]))
+
+
 def test_errors_and_memory_api(ob):
     from onika_b200 import _capi
     L = _capi.lib()
