@@ -79,7 +79,9 @@ int onk_lane_sync(int lane);                           /* ONK_LANE_ALL: every la
 int onk_lane_query(int lane, int* idle);               /* *idle = 1 when nothing is pending on the lane */
 int onk_lane_wait_lane(int lane, int other_lane);      /* lane waits (on device) for what is queued on other_lane */
 int onk_lane_host_func(int lane, void (*fn)(void*), void* user);  /* ONIKA_CU_STREAM_HOST_FUNC: hybrid CPU ops ordered in a lane
-                                                                     (block_parallel_for_adapter.h:473-490) */
+                                                                     (block_parallel_for_adapter.h:473-490).  fn runs on a worker
+                                                                     thread of the library (not on a CUDA driver thread) while the
+                                                                     lane waits; it must not call the CUDA API on this lane. */
 
 /* ------------------------------------------------------------------------------------------------------------
  * memory                 replaces GenericHostAllocator::allocate/deallocate/is_gpu_addressable

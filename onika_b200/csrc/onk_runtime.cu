@@ -5,6 +5,8 @@
 
 #include <cuda.h>
 #include <cstdarg>
+#include <condition_variable>
+#include <thread>
 
 namespace onk
 {
@@ -228,11 +230,74 @@ int onk_lane_wait_lane(int lane, int other_lane)
   return ONK_OK;
 }
 
+} // extern "C"
+
+namespace onk
+{
+  // Host operations of a lane (user-declared host-only functors: OpenMP regions, arbitrary user code) do not run on the CUDA
+  // runtime's callback thread: the stream's host node hands them to ONE long-lived worker thread of the library and blocks
+  // until it is done -- the lane's ordering is unchanged, but the user's code (and its OpenMP team, created once) lives on
+  // an ordinary thread instead of a driver thread whose identity may change from stream to stream.
+  class HostWorker
+  {
+  public:
+    static HostWorker& instance() { static HostWorker* w = new HostWorker(); return *w; }     // never destroyed: sleeps on a condition variable
+    void run(void (*fn)(void*), void* user)
+    {
+      std::unique_lock<std::mutex> lk(m_mutex);
+      m_slot_free.wait(lk, [&]{ return m_fn == nullptr; });          // several lanes may reach their host nodes at the same time
+      m_fn = fn; m_user = user; const uint64_t ticket = ++m_posted;
+      m_wake.notify_one();
+      m_done.wait(lk, [&]{ return m_finished >= ticket; });
+    }
+  private:
+    HostWorker() { std::thread([this]{ loop(); }).detach(); }
+    void loop()
+    {
+      std::unique_lock<std::mutex> lk(m_mutex);
+      for (;;)
+      {
+        m_wake.wait(lk, [&]{ return m_fn != nullptr; });
+        void (*fn)(void*) = m_fn; void* user = m_user;
+        lk.unlock();
+        fn(user);
+        lk.lock();
+        m_fn = nullptr; m_finished = m_posted;
+        m_done.notify_all(); m_slot_free.notify_one();
+      }
+    }
+    std::mutex m_mutex;
+    std::condition_variable m_wake, m_done, m_slot_free;
+    void (*m_fn)(void*) = nullptr; void* m_user = nullptr;
+    uint64_t m_posted = 0, m_finished = 0;
+  };
+
+  struct HostTask { void (*fn)(void*); void* user; };
+  static void CUDART_CB host_task_trampoline(void* p)
+  {
+    HostTask* t = (HostTask*)p;
+    HostWorker::instance().run(t->fn, t->user);
+    delete t;
+  }
+}
+
+extern "C" {
+
 int onk_lane_host_func(int lane, void (*fn)(void*), void* user)
 {
   ONK_REQUIRE(fn != nullptr, "onk_lane_host_func: null function");
   Lane* L; if (int rc = lane_get(lane, &L)) return rc;
-  ONK_CUDA(cudaLaunchHostFunc(L->stream, fn, user));
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  ONK_CUDA(cudaStreamIsCapturing(L->stream, &cap));
+  if (cap != cudaStreamCaptureStatusNone)
+  {
+    // a captured host node is replayed any number of times: it keeps the caller's (fn, user) pair, which must outlive the graph
+    ONK_CUDA(cudaLaunchHostFunc(L->stream, fn, user));
+    return ONK_OK;
+  }
+  HostTask* t = new HostTask{ fn, user };
+  cudaError_t e = cudaLaunchHostFunc(L->stream, host_task_trampoline, t);
+  if (e != cudaSuccess) { delete t; ONK_CUDA(e); }
   return ONK_OK;
 }
 
