@@ -4,7 +4,7 @@
  * (paths relative to the reference tree root).  Pinned against the real reference (oracle/_ref, built from the
  * reference's own sources) and against tests/golden/ by tests/test_oracle_*.py.
  *
- * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
+ * Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference legs; `checks`, as the checker only) may load this
  * library -- as the checker, never as the thing measured or shipped.  The product path (onika_b200/) has
  * no CPU fallback and never links or loads anything under oracle/.
  */
