@@ -152,6 +152,8 @@ namespace onk
                     const __grid_constant__ XchgParams xp)
   {
     using R = Red<OP>;
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // no-op unless launched as a programmatic dependent (launch_pdl)
+    asm volatile("griddepcontrol.launch_dependents;");
     double acc[RED_UNROLL * 4];
 #pragma unroll
     for (int i = 0; i < RED_UNROLL * 4; i++) acc[i] = R::identity();
@@ -211,6 +213,8 @@ namespace onk
                         const __grid_constant__ XchgParams xp)
   {
     using R = Red<OP>;
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // no-op unless launched as a programmatic dependent (launch_pdl)
+    asm volatile("griddepcontrol.launch_dependents;");
     extern __shared__ __align__(128) unsigned char tsm[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(tsm + (size_t)TMA_STAGES * TMA_TILE_BYTES);
     const unsigned tid = threadIdx.x;
@@ -285,6 +289,28 @@ namespace onk
     }
   }
 
+  // Programmatic dependent launch, OFF by default (ONK_PDL=1 turns it on): the kernel may be SCHEDULED while its predecessor on
+  // the lane drains -- it waits for the predecessor's completion and memory flush in griddepcontrol.wait, its first instruction,
+  // before it touches anything -- so the launch latency between back-to-back reductions of a lane is hidden: 1 GiB 151.4 ->
+  // 149.3 us, 256 MiB 41.6 -> 41.3 us, 64 MiB (L2-resident) 12.2 -> 8.9 us (tools/exp_reduce_small.py), headline 7313 -> 7321
+  // GB/s.  Off because the early-resident, waiting CTAs of the dependent kernel take SM slots from the kernels of OTHER lanes:
+  // the two-lane C5 sequence on 2 GPUs went from 2.005 to 2.114 ms per step with it.
+  template<class... KArgs, class... Args>
+  static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args)
+  {
+    static const bool pdl = []{ const char* e = getenv("ONK_PDL"); return e && e[0] == '1'; }();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (pdl)
+    {
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  }
+
   template<int OP>
   static int launch_reduce(const double* in, uint64_t n, double* out, Lane* L, const XchgParams* xp = nullptr)
   {
@@ -310,9 +336,9 @@ namespace onk
       }
       const unsigned g = (unsigned)rt().sm_count;
       if (xp != nullptr && xp->world > 1)
-        reduce_f64_tma_kernel<OP, true><<<g, THREADS, TMA_SMEM, L->stream>>>(in, n, head, tma_tiles, L->ws.partials, L->ws.ticket, out, *xp);
+        ONK_CUDA(launch_pdl(reduce_f64_tma_kernel<OP, true>, g, THREADS, TMA_SMEM, L->stream, in, n, head, tma_tiles, L->ws.partials, L->ws.ticket, out, *xp));
       else
-        reduce_f64_tma_kernel<OP, false><<<g, THREADS, TMA_SMEM, L->stream>>>(in, n, head, tma_tiles, L->ws.partials, L->ws.ticket, out, XchgParams{});
+        ONK_CUDA(launch_pdl(reduce_f64_tma_kernel<OP, false>, g, THREADS, TMA_SMEM, L->stream, in, n, head, tma_tiles, L->ws.partials, L->ws.ticket, out, XchgParams{}));
       ONK_CHECK_LAUNCH();
       count_launch();
       return ONK_OK;
@@ -324,9 +350,9 @@ namespace onk
     if (ntiles == 0) grid = (unsigned)((edge + THREADS - 1) / THREADS ? (edge + THREADS - 1) / THREADS : 1);
     if (grid > (unsigned)MAX_PARTIALS) grid = MAX_PARTIALS;
     if (xp != nullptr && xp->world > 1)
-      reduce_f64_kernel<OP, true><<<grid, THREADS, 0, L->stream>>>(in, n, head, ntiles, L->ws.partials, L->ws.ticket, out, *xp);
+      ONK_CUDA(launch_pdl(reduce_f64_kernel<OP, true>, grid, THREADS, 0, L->stream, in, n, head, ntiles, L->ws.partials, L->ws.ticket, out, *xp));
     else
-      reduce_f64_kernel<OP, false><<<grid, THREADS, 0, L->stream>>>(in, n, head, ntiles, L->ws.partials, L->ws.ticket, out, XchgParams{});
+      ONK_CUDA(launch_pdl(reduce_f64_kernel<OP, false>, grid, THREADS, 0, L->stream, in, n, head, ntiles, L->ws.partials, L->ws.ticket, out, XchgParams{}));
     ONK_CHECK_LAUNCH();
     count_launch();
     return ONK_OK;
