@@ -153,7 +153,7 @@ namespace onk
   {
     using R = Red<OP>;
     asm volatile("griddepcontrol.wait;" ::: "memory");          // no-op unless launched as a programmatic dependent (launch_pdl)
-    asm volatile("griddepcontrol.launch_dependents;");
+
     double acc[RED_UNROLL * 4];
 #pragma unroll
     for (int i = 0; i < RED_UNROLL * 4; i++) acc[i] = R::identity();
@@ -214,7 +214,7 @@ namespace onk
   {
     using R = Red<OP>;
     asm volatile("griddepcontrol.wait;" ::: "memory");          // no-op unless launched as a programmatic dependent (launch_pdl)
-    asm volatile("griddepcontrol.launch_dependents;");
+
     extern __shared__ __align__(128) unsigned char tsm[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(tsm + (size_t)TMA_STAGES * TMA_TILE_BYTES);
     const unsigned tid = threadIdx.x;
@@ -289,16 +289,17 @@ namespace onk
     }
   }
 
-  // Programmatic dependent launch, OFF by default (ONK_PDL=1 turns it on): the kernel may be SCHEDULED while its predecessor on
-  // the lane drains -- it waits for the predecessor's completion and memory flush in griddepcontrol.wait, its first instruction,
-  // before it touches anything -- so the launch latency between back-to-back reductions of a lane is hidden: 1 GiB 151.4 ->
-  // 149.3 us, 256 MiB 41.6 -> 41.3 us, 64 MiB (L2-resident) 12.2 -> 8.9 us (tools/exp_reduce_small.py), headline 7313 -> 7321
-  // GB/s.  Off because the early-resident, waiting CTAs of the dependent kernel take SM slots from the kernels of OTHER lanes:
-  // the two-lane C5 sequence on 2 GPUs went from 2.005 to 2.114 ms per step with it.
+  // Programmatic dependent launch (ONK_PDL=0 turns it off): a reduction may be SCHEDULED while its predecessor on the lane
+  // drains -- it waits for the predecessor's completion and memory flush in griddepcontrol.wait, its first instruction, before it
+  // touches anything -- so part of the launch latency between back-to-back kernels of a lane is hidden.  A/B on one 2-GPU box
+  // (bench.py --gpus 2, two runs each): weak step 0.2997 -> 0.2987 ms, 2^28 in total 0.1562 -> 0.1536 ms, two-lane C5 sequence
+  // unchanged within noise.  The kernels do NOT trigger their dependents early (griddepcontrol.launch_dependents at the top):
+  // that hides more (1 GiB 151.4 -> 149.3 us, 64 MiB 12.2 -> 8.9 us) but parks the dependent's CTAs on the SMs while the
+  // predecessor runs, which takes slots from the kernels of OTHER lanes (C5 on 2 GPUs +1-2 %).
   template<class... KArgs, class... Args>
   static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args)
   {
-    static const bool pdl = []{ const char* e = getenv("ONK_PDL"); return e && e[0] == '1'; }();
+    static const bool pdl = []{ const char* e = getenv("ONK_PDL"); return !(e && e[0] == '0'); }();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
