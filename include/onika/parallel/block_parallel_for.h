@@ -57,6 +57,8 @@ namespace onika { namespace parallel {
       {
         if( indexed ) fatal_error() << "n_div_blocksize option is only valid non indexed elements " << std::endl;
         const unsigned int per_item[3] = { pec->m_block_size.x * std::max( 1u , opts.n_div_elems_per_thread ) , pec->m_block_size.y , pec->m_block_size.z };
+        // items are tiles of the configured 2D/3D block shape: the block must keep that shape (no sub-block packing)
+        if( ND > 1 ) pec->m_block_threads = uint16_t( pec->m_block_size.x * pec->m_block_size.y * pec->m_block_size.z );
         for(unsigned int d=0; d<ND; d++)
         {
           if( range_start[d] != 0 )

@@ -11,7 +11,8 @@
 //                           the sub-block inside such a CTA (include/onika/cuda/cuda.h), so functor sources do not change;
 //                           opt-in because function-scope ONIKA_CU_BLOCK_SHARED variables would be shared by the sub-blocks.
 //                           bpf_sub_worksteal_kernel is the same with a fixed grid: every sub-block draws its own tickets.
-//   * bpf_box_kernel        same for 2D/3D boxes: items are box coordinates, first coordinate fastest
+//   * bpf_box_kernel        same for 2D/3D boxes: items are box coordinates, first coordinate fastest; bpf_sub_box_kernel packs
+//                           small items of such boxes into CTAs of sub-blocks (SubBlockItems + opts.max_block_size <= 32)
 //   * bpf_worksteal_kernel  fixed grid + atomic ticket (opts.fixed_gpu_grid_size), 1D only, as in the reference
 // Kernels live in the plugin's translation unit (device code for user functors never enters the runtime library);
 // they are launched through the C ABI: cudaGetFuncBySymbol once per instantiation, then onk_launch(cufunc, ..., lane).
@@ -103,6 +104,21 @@ namespace onika { namespace parallel {
         const onikaInt3_t c = { start.x + ssize_t( i - jk * ex ) , start.y + ssize_t( jk % ey ) , start.z + ssize_t( jk / ey ) };
         func( c );
         if( i + gridDim.x < n ) __syncthreads();
+      }
+    }
+
+    // 2D/3D boxes of small items: CTAs of sub-blocks as in bpf_sub_items_kernel, every sub-block a 1-D group of blockDim.x threads
+    template<class FuncT>
+    __global__ void __launch_bounds__(256)
+    bpf_sub_box_kernel( __grid_constant__ const FuncT func , const onikaInt3_t start , const unsigned int ex , const unsigned int ey , const unsigned long long n )
+    {
+      const unsigned long long W = (unsigned long long) gridDim.x * blockDim.y;
+      for(unsigned long long i = (unsigned long long) blockIdx.x * blockDim.y + threadIdx.y; i < n; i += W)
+      {
+        const unsigned long long jk = i / ex;
+        const onikaInt3_t c = { start.x + ssize_t( i - jk * ex ) , start.y + ssize_t( jk % ey ) , start.z + ssize_t( jk / ey ) };
+        func( c );
+        ONIKA_CU_BLOCK_SYNC();
       }
     }
 
@@ -283,9 +299,27 @@ namespace onika { namespace parallel {
           if constexpr ( ND >= 2 ) { start.y = m_parallel_space.m_start[1]; ey = (unsigned int)( m_parallel_space.m_end[1] - m_parallel_space.m_start[1] ); }
           if constexpr ( ND >= 3 ) { start.z = m_parallel_space.m_start[2]; }
           unsigned long long n = nitems;
-          auto kernel = b200::bpf_box_kernel<FuncT>;
           void* args[] = { (void*) &m_func , &start , &ex , &ey , &n };
-          b200::launch( kernel , b200::persistent_grid( kernel , threads , n , sms ) , pec->m_block_size , pec->m_lane , args );
+          bool packed = false;
+          if constexpr ( functor_sub_block_items_v<FuncT> )
+          {
+            // a caller that asks for blocks of <= 32 threads (opts.max_block_size) gets 1-D sub-blocks of that size instead of the
+            // configured 2D/3D tile; pec->m_block_threads is only that small when the caller said so
+            const unsigned int bs = pec->m_block_threads;
+            if( bs >= 1 && bs <= 32 && ( bs & ( bs - 1 ) ) == 0 )
+            {
+              auto kernel = b200::bpf_sub_box_kernel<FuncT>;
+              const onikaDim3_t cta = { bs , 256u / bs , 1 };
+              const unsigned long long nctas = ( n + cta.y - 1 ) / cta.y;
+              b200::launch( kernel , b200::persistent_grid( kernel , 256 , nctas , sms ) , cta , pec->m_lane , args , ONK_LAUNCH_SUB_BLOCKS );
+              packed = true;
+            }
+          }
+          if( ! packed )
+          {
+            auto kernel = b200::bpf_box_kernel<FuncT>;
+            b200::launch( kernel , b200::persistent_grid( kernel , threads , n , sms ) , pec->m_block_size , pec->m_lane , args );
+          }
         }
       }
       else

@@ -1004,6 +1004,73 @@ static int scenario_sub_block_listed(Out& out, size_t ncells)
   return 0;
 }
 
+// sub-block items over 3-D and 2-D boxes of cells (sub-box with a non-zero start): the same functor source once as ordinary
+// 2D/3D blocks of the configured shape (8x8x4 / 8x8), once packed into CTAs of 16-thread sub-blocks
+template<int BS>
+struct GridCellSumFunctor
+{
+  const double * __restrict__ values; const uint64_t * __restrict__ cell_begin; double * __restrict__ cell_sum; ssize_t nx , ny;
+  ONIKA_HOST_DEVICE_FUNC inline void operator () ( onikaInt3_t c ) const
+  {
+    const size_t cell = size_t( ( c.z * ny + c.y ) * nx + c.x );
+    const uint64_t b = cell_begin[cell], e = cell_begin[cell+1];
+    double s = 0.0;
+    ONIKA_CU_BLOCK_SIMD_FOR(uint64_t, p, b, e) { s += values[p]; }
+    s = onika::cuda::block_reduce_add( s , onika::IntConst<BS>{} );
+    if( ONIKA_CU_THREAD_IDX == 0 ) cell_sum[cell] = s + double( ONIKA_CU_BLOCK_SIZE );       // the block size the functor saw is part of the result
+  }
+};
+template<int BS> struct PackedGridCellSumFunctor : public GridCellSumFunctor<BS> {};
+namespace onika { namespace parallel {
+  template<int BS> struct BlockParallelForFunctorTraits< GridCellSumFunctor<BS> > { static inline constexpr bool CudaCompatible = true; };
+  template<int BS> struct BlockParallelForFunctorTraits< PackedGridCellSumFunctor<BS> > { static inline constexpr bool CudaCompatible = true; static inline constexpr bool SubBlockItems = true; };
+} }
+
+static int scenario_sub_block_box(Out& out, ssize_t nx, ssize_t ny, ssize_t nz)
+{
+  const size_t ncells = size_t( nx * ny * nz );
+  std::vector<uint64_t> begin(ncells+1,0);
+  for(size_t c=0;c<ncells;c++) begin[c+1] = begin[c] + uint64_t( lcg(c,42,0.0,25.0) );
+  const size_t np = begin[ncells];
+  CudaMMVector<double> v( np > 0 ? np : 1 ); for(size_t i=0;i<np;i++) v[i] = lcg(i,40,-1.0,1.0);
+  CudaMMVector<uint64_t> b( ncells+1 ); for(size_t c=0;c<=ncells;c++) b[c] = begin[c];
+  BlockParallelForOptions small; small.max_block_size = 16;
+  const ParallelExecutionSpace<3> box3 = { {1,0,2} , {nx,ny-1,nz} };
+  const ParallelExecutionSpace<2> box2 = { {0,1} , {nx-1,ny} };
+  {
+    CudaMMVector<double> sums( ncells , -7.0 );
+    GridCellSumFunctor<256> f = { v.data() , b.data() , sums.data() , nx , ny };
+    block_parallel_for( box3 , f , parallel_execution_context("box3","blocks") );
+    out.doubles( sums.data() , ncells );
+  }
+  {
+    CudaMMVector<double> sums( ncells , -7.0 );
+    PackedGridCellSumFunctor<16> f = { { v.data() , b.data() , sums.data() , nx , ny } };
+    block_parallel_for( box3 , f , parallel_execution_context("box3","sub-blocks") , small );
+    out.doubles( sums.data() , ncells );
+  }
+  {
+    CudaMMVector<double> sums( ncells , -7.0 );
+    GridCellSumFunctor<64> f = { v.data() , b.data() , sums.data() , nx , ny };
+    block_parallel_for( box2 , f , parallel_execution_context("box2","blocks") );
+    out.doubles( sums.data() , ncells );
+  }
+  {
+    CudaMMVector<double> sums( ncells , -7.0 );
+    PackedGridCellSumFunctor<16> f = { { v.data() , b.data() , sums.data() , nx , ny } };
+    block_parallel_for( box2 , f , parallel_execution_context("box2","sub-blocks") , small );
+    out.doubles( sums.data() , ncells );
+  }
+  {
+    // the trait alone does not pack: without a small max_block_size the configured 3-D tile (256 threads) stays
+    CudaMMVector<double> sums( ncells , -7.0 );
+    PackedGridCellSumFunctor<256> f = { { v.data() , b.data() , sums.data() , nx , ny } };
+    block_parallel_for( box3 , f , parallel_execution_context("box3","trait-only") );
+    out.doubles( sums.data() , ncells );
+  }
+  return 0;
+}
+
 // reduction helpers queued on lanes together with the kernels that produce their input
 static int scenario_reduce_helpers(Out& out, size_t rows, size_t cols)
 {
@@ -1103,6 +1170,7 @@ int main(int argc, char* argv[])
   else if( sc == "soatl" ) rc = scenario_soatl( out , arg(3,53) );
   else if( sc == "soatl_apply_mixed" ) rc = scenario_soatl_apply_mixed( out , arg(3,5000) );
   else if( sc == "sub_block_listed" ) rc = scenario_sub_block_listed( out , arg(3,1001) );
+  else if( sc == "sub_block_box" ) rc = scenario_sub_block_box( out , ssize_t(arg(3,13)) , ssize_t(arg(4,11)) , ssize_t(arg(5,7)) );
   else if( sc == "soatl_apply" ) rc = scenario_soatl_apply( out , arg(3,100003) , arg(4,0) != 0 );
   else if( sc == "perf" ) rc = scenario_perf( out , arg(3,1<<27) );
   else if( sc == "block_vocabulary" ) rc = scenario_block_vocabulary( out , arg(3,1000) );

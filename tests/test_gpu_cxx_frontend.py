@@ -429,6 +429,38 @@ def test_sub_block_items_over_element_lists_and_tiny_spaces(prog, tmp_path, orc)
     assert np.all(listed[0::2][sizes[0::2] == 0] == 0.0)           # empty cells: exactly zero
 
 
+@pytest.mark.parametrize("dims", [(13, 11, 7), (40, 33, 20), (2, 2, 3)])
+def test_sub_block_items_over_2d_and_3d_boxes(prog, tmp_path, orc, dims):
+    """SubBlockItems on 2D/3D execution spaces (reference trampoline: block_parallel_for_adapter.h:95-104, one configured
+    8x8x4 tile per coordinate): with opts.max_block_size <= 32 a CTA holds 256/bs coordinates, each run by a 1-D sub-block.
+    Sub-boxes with non-zero starts; cells outside the box stay untouched; in-cell sums (<= 25 values through a butterfly or a
+    block tree) against the oracle's particle-order sums within SUM_RTOL; the block size the functor saw is added to every
+    result (16 packed, 256 / 64 unpacked); the trait without a small max_block_size keeps the configured tile"""
+    nx, ny, nz = dims
+    ncells = nx * ny * nz
+    d = run(prog, tmp_path, "sub_block_box", nx, ny, nz).view(np.float64)
+    assert d.size == 5 * ncells
+    sizes = np.floor(lcg_uniform(ncells, 42, 0.0, 25.0)).astype(np.uint64)
+    begin = np.zeros(ncells + 1, np.uint64)
+    begin[1:] = np.cumsum(sizes, dtype=np.uint64)
+    values = lcg_uniform(int(begin[-1]), 40, -1.0, 1.0)
+    want, _ = orc.cell_sum_packed(values, begin)
+    mag = np.add.reduceat(np.abs(np.append(values, 0.0)), np.minimum(begin[:-1].astype(np.int64), values.size)) * (sizes > 0) + 1e-300
+    want = want.reshape(nz, ny, nx)
+    mag = mag.reshape(nz, ny, nx)
+    in3 = np.zeros((nz, ny, nx), bool)
+    in3[2:nz, 0:ny - 1, 1:nx] = True
+    in2 = np.zeros((nz, ny, nx), bool)
+    in2[0, 1:ny, 0:nx - 1] = True
+    for k, (inside, bs) in enumerate([(in3, 256.0), (in3, 16.0), (in2, 64.0), (in2, 16.0), (in3, 256.0)]):
+        got = d[k * ncells:(k + 1) * ncells].reshape(nz, ny, nx)
+        assert np.all(got[~inside] == -7.0), k
+        assert np.all(np.abs(got[inside] - bs - want[inside]) <= SUM_RTOL * (mag[inside] + bs)), k
+    # packed and unpacked runs agree to the same tolerance; empty cells give exactly the block size
+    packed3 = d[ncells:2 * ncells].reshape(nz, ny, nx)
+    assert np.all(packed3[in3 & (sizes.reshape(nz, ny, nx) == 0)] == 16.0)
+
+
 def test_host_compiler_and_nvcc_translation_units_share_one_context():
     """a plugin = .cpp files compiled by g++ plus .cu files compiled by nvcc: the default CUDA context is created by the g++
     half and read by the nvcc half (tests/cxx/mixed_tu_*): every shared type has one layout, the SM count that sizes fixed
