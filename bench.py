@@ -390,7 +390,9 @@ def secondary_kernels(ob, torch):
                 o = os.path.join(tmp, "o.bin")
                 subprocess.run([exe, "cells_generic_perf", o, str(128 ** 3)], check=True, capture_output=True, timeout=300)
                 us = np.fromfile(o, dtype=np.float64, count=6)
+                small = np.fromfile(o, dtype=np.float64, count=2, offset=8 * (6 + 6 * 128 ** 3))
                 out["C4_generic_functor_path_128^3_us"] = {
+                    "sub_block_items_4_2_threads": [round(float(v), 1) for v in small],
                     "one_block_of_128_threads_per_cell": round(float(us[0]), 1), "one_block_of_32_threads_per_cell": round(float(us[1]), 1),
                     "sub_block_items_32_16_8_threads": [round(float(v), 1) for v in us[3:6]], "typed_field_major_kernel": round(float(us[2]), 1),
                     "what": "block_parallel_for(ncells, functor) with ONIKA_CU_BLOCK_SIMD_FOR + block_reduce_add, unchanged functor source; sub-block items = several cells per CTA (BlockParallelForFunctorTraits::SubBlockItems)"}

@@ -602,7 +602,7 @@ static int scenario_cells_generic_perf(Out& out, size_t ncells)
   auto & pq = ParallelExecutionQueue::default_queue();
   void* stream = nullptr; ONIKA_B200_CHECK( onk_lane_stream( 0 , &stream ) );
   cudaEvent_t e0, e1; ONIKA_CU_CHECK_ERRORS( cudaEventCreate(&e0) ); ONIKA_CU_CHECK_ERRORS( cudaEventCreate(&e1) );
-  double us[6] = {0,0,0,0,0,0};
+  double us[8] = {0,0,0,0,0,0,0,0};
   auto timeit = [&](int slot, auto make_op)
   {
     for(int i=0;i<2;i++) pq << set_lane(0) << make_op();
@@ -633,7 +633,7 @@ static int scenario_cells_generic_perf(Out& out, size_t ncells)
   }
   std::vector<double> rt(ncells); ONIKA_B200_CHECK( onk_memcpy( rt.data() , ps , ncells*8 , 0 ) ); ONIKA_B200_CHECK( onk_lane_sync(0) );
   // sub-block items: the same operator() in CTAs of 256/bs sub-blocks of bs threads
-  std::vector<double> rsub[3] = { std::vector<double>(ncells) , std::vector<double>(ncells) , std::vector<double>(ncells) };
+  std::vector<double> rsub[5]; for(auto& r : rsub) r.resize( ncells );
   auto sub = [&](int slot, auto functor, unsigned int bs)
   {
     ONIKA_B200_CHECK( onk_memset_bytes( ps , 0xff , ncells*8 , 0 ) );
@@ -644,13 +644,18 @@ static int scenario_cells_generic_perf(Out& out, size_t ncells)
   sub( 0 , PackedCellSumFunctor<32>{ { (const double*)pv , (const uint64_t*)pb , (double*)ps } } , 32 );
   sub( 1 , PackedCellSumFunctor<16>{ { (const double*)pv , (const uint64_t*)pb , (double*)ps } } , 16 );
   sub( 2 , PackedCellSumFunctor<8>{ { (const double*)pv , (const uint64_t*)pb , (double*)ps } } , 8 );
+  // even smaller sub-blocks: more cells in flight per SM (each item is a chain of dependent loads: the path is latency-bound)
+  sub( 3 , PackedCellSumFunctor<4>{ { (const double*)pv , (const uint64_t*)pb , (double*)ps } } , 4 );
+  sub( 4 , PackedCellSumFunctor<2>{ { (const double*)pv , (const uint64_t*)pb , (double*)ps } } , 2 );
   ParallelExecutionContext::s_gpu_timing = true;
-  std::printf("cells_generic_perf ncells=%zu particles=%zu : generic block 128 %.1f us , generic block 32 %.1f us , typed field-major %.1f us , sub-block items 32/16/8 threads %.1f / %.1f / %.1f us\n",
-              ncells, np, us[0], us[1], us[2], us[3], us[4], us[5]);
+  std::printf("cells_generic_perf ncells=%zu particles=%zu : generic block 128 %.1f us , generic block 32 %.1f us , typed field-major %.1f us , sub-block items 32/16/8/4/2 threads %.1f / %.1f / %.1f / %.1f / %.1f us\n",
+              ncells, np, us[0], us[1], us[2], us[3], us[4], us[5], us[6], us[7]);
   out.doubles( us , 6 );
   out.doubles( rt.data() , ncells );            // in-order sums (typed kernel): the reference result
   out.doubles( r128.data() , ncells ); out.doubles( r32.data() , ncells );   // tree sums of the generic functor: equal within rounding
   for(int k=0;k<3;k++) out.doubles( rsub[k].data() , ncells );
+  out.doubles( us+6 , 2 );                      // appended in round 2: sub-blocks of 4 and 2 threads
+  for(int k=3;k<5;k++) out.doubles( rsub[k].data() , ncells );
   onk_free( pv , np*8 ); onk_free( pb , (ncells+1)*8 ); onk_free( ps , ncells*8 );
   return pq.empty() ? 0 : 3;
 }

@@ -177,6 +177,11 @@ def test_cell_sums_through_the_generic_functor_path(prog, tmp_path, orc):
         sub = d[6 + k * ncells:6 + (k + 1) * ncells]
         assert sub.size == ncells and not np.isnan(sub).any()
         assert np.all(np.abs(sub - want) <= SUM_RTOL * mag)
+    tail = d[6 + 6 * ncells:]                      # sub-blocks of 4 and 2 threads: two timings, then their sums
+    assert tail.size == 2 + 2 * ncells
+    for k in range(2):
+        sub = tail[2 + k * ncells:2 + (k + 1) * ncells]
+        assert not np.isnan(sub).any() and np.all(np.abs(sub - want) <= SUM_RTOL * mag)
 
 
 def test_3d_spaces(prog, tmp_path, orc, gold):
