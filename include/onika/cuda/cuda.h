@@ -18,6 +18,7 @@
 #include <type_traits>
 
 #include <onika/macro_utils.h>
+#include <onika/atomic.h>
 
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
@@ -82,23 +83,11 @@ namespace onika
     using onika_cu_memory_order_t = std::memory_order;
 
     // host implementations of the read-modify-write atomics (what ONIKA_CU_ATOMIC_* mean in host code)
-    template<class T> inline T host_atomic_add(T& x, T a)
-    {
-      if constexpr (std::is_integral_v<T>) { return __atomic_fetch_add(&x, a, __ATOMIC_SEQ_CST); }
-      else { T old = x, want; do { want = old + a; } while (!__atomic_compare_exchange(&x, &old, &want, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)); return old; }
-    }
-    template<class T> inline T host_atomic_min(T& x, T a)
-    {
-      T old = x;
-      while (a < old) { T want = a; if (__atomic_compare_exchange(&x, &old, &want, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) break; }
-      return old;
-    }
-    template<class T> inline T host_atomic_max(T& x, T a)
-    {
-      T old = x;
-      while (a > old) { T want = a; if (__atomic_compare_exchange(&x, &old, &want, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) break; }
-      return old;
-    }
+    // (the reference's names live in onika/atomic.h: capture_atomic_add / _sub / _min / _max, inplace_atomic_add / _sub)
+    template<class T> inline T host_atomic_add(T& x, T a) { return ::onika::capture_atomic_add( x , a ); }
+    template<class T> inline T host_atomic_sub(T& x, T a) { return ::onika::capture_atomic_sub( x , a ); }
+    template<class T> inline T host_atomic_min(T& x, T a) { return ::onika::capture_atomic_min( x , a ); }
+    template<class T> inline T host_atomic_max(T& x, T a) { return ::onika::capture_atomic_max( x , a ); }
   }
 }
 
@@ -222,8 +211,8 @@ namespace onika { namespace cuda { using onika_cu_clock_t = long long int; } }
 #  define ONIKA_CU_ATOMIC_ADD(x,a,...)         ::onika::cuda::host_atomic_add( x , static_cast<std::remove_reference_t<decltype(x)> >(a) )
 #  define ONIKA_CU_INPLACE_ATOMIC_ADD(x,a,...) ::onika::cuda::host_atomic_add( x , static_cast<std::remove_reference_t<decltype(x)> >(a) )
 #  define ONIKA_CU_BLOCK_ATOMIC_ADD(x,a,...)   (x)+=(a)
-#  define ONIKA_CU_ATOMIC_SUB(x,a,...)         ::onika::cuda::host_atomic_add( x , static_cast<std::remove_reference_t<decltype(x)> >(-(a)) )
-#  define ONIKA_CU_INPLACE_ATOMIC_SUB(x,a,...) ::onika::cuda::host_atomic_add( x , static_cast<std::remove_reference_t<decltype(x)> >(-(a)) )
+#  define ONIKA_CU_ATOMIC_SUB(x,a,...)         ::onika::cuda::host_atomic_sub( x , static_cast<std::remove_reference_t<decltype(x)> >(a) )
+#  define ONIKA_CU_INPLACE_ATOMIC_SUB(x,a,...) ::onika::cuda::host_atomic_sub( x , static_cast<std::remove_reference_t<decltype(x)> >(a) )
 #  define ONIKA_CU_BLOCK_ATOMIC_SUB(x,a,...)   (x)-=(a)
 #  define ONIKA_CU_ATOMIC_MIN(x,a,...)         ::onika::cuda::host_atomic_min( x , static_cast<std::remove_reference_t<decltype(x)> >(a) )
 #  define ONIKA_CU_ATOMIC_MAX(x,a,...)         ::onika::cuda::host_atomic_max( x , static_cast<std::remove_reference_t<decltype(x)> >(a) )

@@ -64,6 +64,13 @@ static inline constexpr auto onikaSuccess            = cudaSuccess;
 static inline constexpr auto onikaErrorNotReady      = cudaErrorNotReady;
 static inline constexpr auto onikaMemcpyDeviceToHost = cudaMemcpyDeviceToHost;
 static inline constexpr auto onikaMemcpyHostToDevice = cudaMemcpyHostToDevice;
+static inline constexpr auto onikaSharedMemBankSizeFourByte  = cudaSharedMemBankSizeFourByte;
+static inline constexpr auto onikaSharedMemBankSizeEightByte = cudaSharedMemBankSizeEightByte;
+static inline constexpr auto onikaSharedMemBankSizeDefault   = cudaSharedMemBankSizeDefault;
+static inline constexpr auto onikaLimitStackSize             = cudaLimitStackSize;
+static inline constexpr auto onikaLimitPrintfFifoSize        = cudaLimitPrintfFifoSize;
+static inline constexpr auto onikaLimitMallocHeapSize        = cudaLimitMallocHeapSize;
+static inline constexpr auto onikaDevAttrClockRate           = cudaDevAttrClockRate;
 #define ONIKA_CU_NAME_STR                              "cuda-sm100a"
 // NVTX ranges (header-only NVTX3: a no-op unless a profiler injects its library), as the reference does around operators
 #if __has_include(<nvtx3/nvToolsExt.h>) && ! defined(ONIKA_B200_NO_NVTX)

@@ -8,11 +8,9 @@
 #include <type_traits>
 #include <onika/cuda/cuda.h>
 #include <onika/cuda/uninitialized_place_holder.h>
+#include <onika/type_utils.h>
 
 namespace onika {
-
-  template<class T> struct is_span_t : std::false_type {};
-  template<class T> static inline constexpr bool is_span_v = is_span_t<T>::value;
 
   namespace cuda {
 

@@ -48,4 +48,19 @@ namespace onika { namespace soatl {
     using type = std::conditional_t< N==0 , FieldIds<> , prepend_field_id_t<id1 , typename NFirstFields< ( N>0 ? N-1 : 0 ) ,FieldIds<ids...> >::type > >;
   };
 
+  // shortest leading run of FidsRef that contains every tag of a sub-set (a tag absent from FidsRef asks for more than the
+  // whole list, i.e. the whole list): FieldIdsIncludingSequence<FidsRef,FieldIds<sub...>>::type / ::n_fields()
+  template<class FidsRef , class FidsSubSet> struct FieldIdsIncludingSequence;
+  template<class FidsRef , class... SubSetIds>
+  struct FieldIdsIncludingSequence< FidsRef , FieldIds<SubSetIds...> >
+  {
+    static inline constexpr size_t n_fields()
+    {
+      size_t n = 0;
+      for( size_t last : { size_t(0) , ( size_t(1) + find_index_of_id_in_field_ids_v<SubSetIds,FidsRef> ) ... } ) if( last > n ) n = last;
+      return n;
+    }
+    using type = typename NFirstFields< n_fields() , FidsRef >::type;
+  };
+
 } }

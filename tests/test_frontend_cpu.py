@@ -334,6 +334,113 @@ int main()
         assert theirs == ours
 
 
+def test_host_atomics_and_stl_adaptors_match_the_reference_headers(tmp_path):
+    """onika/atomic.h (capture_atomic_add / _sub / _min / _max, inplace_atomic_add / _sub: include/onika/atomic.h:14-62 in the
+    reference), the host meaning of the ONIKA_CU_ATOMIC_* macros (cuda.h:200-207 there) and onika/cuda/stl_adaptors.h (vector_data
+    / vector_size, lower_bound as a first-not-less scan, span, pair ordering, forward memmove, the printf-backed cout): ONE
+    program compiled against this repo's headers and against the reference's own headers prints the same lines."""
+    src = tmp_path / "probe2.cpp"
+    src.write_text(r'''
+#include <onika/atomic.h>
+#include <onika/cuda/cuda.h>
+#include <onika/cuda/stl_adaptors.h>
+#include <onika/type_utils.h>
+#include <cstdio>
+#include <span>
+#include <vector>
+int main()
+{
+  long n = 0, n2 = 0; double s = 0.0, mn = 1e300, mx = -1e300; unsigned int u = 100000u; int lo = 1 << 30, hi = -(1 << 30);
+# pragma omp parallel for num_threads(8)
+  for(int i=0;i<20000;i++)
+  {
+    const double v = double( ( i * 7919 ) % 20011 ) - 3000.0;
+    onika::capture_atomic_add( n , 1L ); onika::inplace_atomic_add( s , 0.5 ); onika::capture_atomic_sub( u , 2u ); onika::inplace_atomic_sub( n2 , 3L );
+    onika::capture_atomic_min( mn , v ); onika::capture_atomic_max( mx , v );
+    ONIKA_CU_ATOMIC_ADD( n2 , 5 ); ONIKA_CU_ATOMIC_MIN( lo , int(v) ); ONIKA_CU_ATOMIC_MAX( hi , int(v) ); ONIKA_CU_ATOMIC_SUB( s , 0.25 );
+  }
+  std::printf("%ld %ld %.3f %.1f %.1f %u %d %d\n", n, n2, s, mn, mx, u, lo, hi);
+  double x = 3.0; long k = 7; float f = 2.0f;
+  const double a0 = onika::capture_atomic_add( x , 1.5 ), a1 = onika::capture_atomic_sub( x , 0.25 ), a2 = onika::capture_atomic_min( x , 9.0 ), a3 = onika::capture_atomic_min( x , 1.0 ), a4 = onika::capture_atomic_max( x , 0.5 ), a5 = onika::capture_atomic_max( x , 8.0 );
+  const long k0 = onika::capture_atomic_add( k , 3L ); const float f0 = onika::capture_atomic_max( f , 5.0f );
+  std::printf("%g %g %g %g %g %g -> %g | %ld %ld | %g %g\n", a0, a1, a2, a3, a4, a5, x, k0, k, double(f0), double(f));
+  long r = ONIKA_CU_ATOMIC_ADD( k , 10 ); std::printf("%ld %ld\n", r, k);
+
+  std::vector<double> v = { 1.0 , 2.0 , 2.0 , 5.0 , 8.0 };
+  const std::vector<double>& cv = v;
+  std::printf("%d %d %zu\n", int( onika::cuda::vector_data(v) == v.data() ), int( onika::cuda::vector_data(cv) == v.data() ), onika::cuda::vector_size(cv));
+  std::vector<double> empty; std::printf("%zu\n", onika::cuda::vector_size(empty));
+  const double unsorted[6] = { 1.0 , 4.0 , 2.0 , 9.0 , 3.0 , 0.5 };
+  for(double q : { 0.0 , 2.0 , 2.5 , 8.0 , 9.0 , 100.0 })
+    std::printf("%td %td ", onika::cuda::lower_bound( v.data() , v.data()+5 , q ) - v.data() , onika::cuda::lower_bound( unsorted , unsorted+6 , q ) - unsorted );
+  std::printf("\n");
+  auto sp = onika::cuda::make_span( v ); auto csp = onika::cuda::make_const_span( cv );
+  sp[1] = 2.5; double sum = 0; for(double e : csp) sum += e;
+  onika::cuda::span<double> agg = { v.data()+1 , 3 };
+  std::printf("%zu %zu %d %g %g %g %d %d %d\n", sp.size(), csp.size(), int(sp.empty()), sum, agg[0], *(agg.end()-1), int( onika::is_span_v< onika::cuda::span<double> > ), int( onika::is_span_v< std::span<const long> > ), int( onika::is_span_v< std::vector<double> > ));
+  using P = onika::cuda::pair<int,double>;
+  const P p1 = {1,2.0} , p2 = {1,3.0} , p3 = {2,0.0} , p4 = {1,2.0};
+  std::printf("%d %d %d %d %d %d %d %d\n", int(p1<p2), int(p2<p1), int(p1<p3), int(p3>=p2), int(p1>=p4), int(p1!=p4), int(p1!=p2), int(p1==p4));
+  unsigned char buf[40]; for(int i=0;i<40;i++) buf[i] = (unsigned char) i;
+  onika::cuda::memmove( buf , buf+8 , 24 ); onika::cuda::memmove( buf+1 , buf+4 , 7 ); onika::cuda::memmove( buf+30 , buf+30 , 5 );
+  for(int i=0;i<40;i++) std::printf("%d ", int(buf[i]));
+  std::printf("\n");
+  onika::cuda::cout << "cout " << uint64_t(7) << " " << int32_t(-3) << " " << 2.5 << " " << 1.5f << " " << int16_t(-2) << "\n";
+  return 0;
+}
+''')
+    stub = os.path.join(os.path.dirname(INC), "oracle", "stub")
+
+    def build_and_run(include, name):
+        exe = tmp_path / name
+        subprocess.check_call(["g++", "-std=c++20", "-fopenmp", "-O1", f"-I{include}", f"-I{stub}", str(src), "-o", str(exe)]
+                              + ([f"-L{os.path.dirname(lib)}", "-lonika_b200", f"-Wl,-rpath,{os.path.dirname(lib)}"] if include == INC else []), env=_env())
+        return subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+
+    from onika_b200 import _build
+    lib = _build.build()
+    ours = build_and_run(INC, "ours")
+    assert ours[0] == "20000 40000 5000.000 -3000.0 17010.0 60000 -3000 17010"
+    assert ours[1] == "3 4.5 4.25 4.25 1 1 -> 8 | 7 10 | 2 5"
+    assert ours[2] == "10 20"
+    assert ours[5] == "0 0 1 1 3 1 4 3 5 3 5 6 "          # sorted: std::lower_bound; unsorted: the first element that is not less
+    assert ours[8].split()[:12] == ["8", "12", "13", "14", "15", "16", "17", "18", "16", "17", "18", "19"]
+    assert ours[9] == "cout 7 -3  2.500000000e+00  1.500000000e+00 -2"
+    ref_inc = "/root/reference/include"
+    if os.path.isdir(ref_inc):
+        theirs = build_and_run(ref_inc, "theirs")
+        assert theirs == ours
+
+
+def _probe_on_both_header_trees(tmp_path, name, extra=()):
+    """compiles tests/cxx/probes/<name>.cpp with g++ against this repo's headers and, where the reference tree is present,
+    against the reference's own headers; returns (our lines, their lines or None)"""
+    from onika_b200 import _build
+    lib = _build.build()
+    src = os.path.join(ROOT, "tests", "cxx", "probes", name + ".cpp")
+    stub = os.path.join(ROOT, "oracle", "stub")
+
+    def build_and_run(include, tag):
+        exe = tmp_path / (name + "_" + tag)
+        subprocess.check_call(["g++", "-std=c++20", "-fopenmp", "-O1", *extra, f"-I{include}", f"-I{stub}", src, "-o", str(exe)]
+                              + ([f"-L{os.path.dirname(lib)}", "-lonika_b200", f"-Wl,-rpath,{os.path.dirname(lib)}"] if include == INC else []), env=_env())
+        return subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+
+    ours = build_and_run(INC, "ours")
+    ref_inc = "/root/reference/include"
+    theirs = build_and_run(ref_inc, "theirs") if os.path.isdir(ref_inc) else None
+    return ours, theirs
+
+
+def test_list_macros_field_combiner_declarations_and_including_sequences_match_the_reference_headers(tmp_path):
+    """EXPAND_WITH_PREFIX / EXPAND_WITH_FUNC (+ _PREPEND_COMMA, _NOSEP), GET_FIRST_ARG, ONIKA_STR, ONIKA_CONCAT
+    (include/onika/macro_utils.h:23-119 in the reference), ONIKA_DECLARE_FIELD_COMBINER / ONIKA_DECLARE_DYNAMIC_FIELD_COMBINER
+    (soatl/field_combiner.h:43-68) with 0, 2 and mixed-type field lists, FieldIdsIncludingSequence (soatl/field_id.h:110-121)"""
+    ours, theirs = _probe_on_both_header_trees(tmp_path, "macros_combiners")
+    assert ours == ["11 12 13 -1 104 105 | 650 18 0 1", "3 alpha 12", "norm2 norm2 25 1 | qm charge_by_mass 1.5 1 | fortytwo 42 1", "2 4 0 3 1 1"]
+    assert theirs is None or theirs == ours
+
+
 def test_msp_yaml_reader_on_the_reference_files(tmp_path):
     """tests/cxx/msp_yaml.h (what `run_operator --app` reads): block maps / sequences, `- key:` items continuing as maps, nested
     flow maps, quoted scalars with escapes, comments, document layering -- on the reference's own data/config/main-config.msp
