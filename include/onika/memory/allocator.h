@@ -5,7 +5,11 @@
 // CUDA_HOST memory is CUDA managed memory from the runtime library (onk_alloc(ONK_MEM_MANAGED)), so pointers stay
 // dereferenceable on the host as plugins expect (e.g. tutorials read results on the host after synchronize).
 // Instead of the reference's 12-byte {size,flags} trailer after every payload, the library keeps a side table keyed
-// by pointer; deallocate(ptr,bytes) still checks the byte count.
+// by pointer; deallocate(ptr,bytes) still checks the byte count (memory_info() reads that table).
+// Deliberate difference: a default-constructed GenericHostAllocator allocates GPU-ADDRESSABLE (managed) memory -- the
+// reference defaults to MALLOC and applications switch containers over with set_gpu_addressable_allocation(true) once a GPU
+// is enabled; this library has no run without a GPU, so containers are device-ready from the start.  The policy switch itself
+// (set_gpu_addressable_allocation(false) -> posix_memalign) works as in the reference.
 #pragma once
 #include <algorithm>
 #include <cstdlib>
@@ -38,9 +42,23 @@ namespace onika { namespace memory {
   static inline constexpr size_t MINIMUM_CUDA_ALIGNMENT = ONIKA_MINIMUM_CUDA_ALIGNMENT;
 # endif
 
+  // what the allocator knows about a block it handed out (the reference decodes this from the trailer it writes after the payload)
+  struct MemoryChunkInfo
+  {
+    void * alloc_base = nullptr;
+    size_t alloc_size = 0;
+    uint32_t alloc_flags = 0;          // policy in the low byte, alignment above
+    inline HostAllocationPolicy mem_type() const { return static_cast<HostAllocationPolicy>( alloc_flags & 0xFF ); }
+    inline unsigned int alignment() const { return alloc_flags >> 8; }
+    inline void * base_ptr() const { return alloc_base; }
+    inline size_t size() const { return alloc_size; }
+  };
+
   struct GenericHostAllocator
   {
     static inline constexpr size_t DefaultAlignBytes = std::max( MINIMUM_CUDA_ALIGNMENT , DEFAULT_ALIGNMENT );
+    static inline bool s_enable_debug_log = false;
+    static inline void set_debug_log(bool b) { s_enable_debug_log = b; }
     static inline bool s_enable_cuda = true;
     static inline bool cuda_enabled() { return s_enable_cuda; }
     static inline void set_cuda_enabled(bool yn) { s_enable_cuda = yn; }
@@ -51,6 +69,20 @@ namespace onika { namespace memory {
     inline bool allocates_gpu_addressable() const { return get_policy() == HostAllocationPolicy::CUDA_HOST; }
     inline void set_gpu_addressable_allocation(bool yn) { m_alloc_policy = yn ? HostAllocationPolicy::CUDA_HOST : HostAllocationPolicy::MALLOC; }
     inline bool operator == (const GenericHostAllocator& o) const { return m_alloc_policy == o.m_alloc_policy; }
+
+    // base / size / policy / alignment of a block of `bytes` bytes handed out by allocate(); the alignment reported is the
+    // largest power of two (up to 4096) the address satisfies
+    inline MemoryChunkInfo memory_info(void* ptr, size_t bytes) const
+    {
+      MemoryChunkInfo info;
+      if( ptr == nullptr ) return info;
+      int gpu = 0;
+      ONIKA_B200_CHECK( onk_is_gpu_addressable( ptr , &gpu ) );
+      unsigned int a = 1; while( a < 4096u && ( reinterpret_cast<uintptr_t>(ptr) % ( 2u * a ) ) == 0 ) a *= 2u;
+      info.alloc_base = ptr; info.alloc_size = bytes;
+      info.alloc_flags = ( a << 8 ) | static_cast<uint32_t>( gpu ? HostAllocationPolicy::CUDA_HOST : HostAllocationPolicy::MALLOC );
+      return info;
+    }
 
     inline void* allocate(size_t bytes, size_t align) const
     {
@@ -65,6 +97,7 @@ namespace onika { namespace memory {
         align = std::max( align , sizeof(void*) );
         if( posix_memalign( &p , align , bytes ) != 0 ) { std::fprintf(stderr,"Allocation failed. aborting.\n"); std::abort(); }
       }
+      if( s_enable_debug_log ) std::fprintf( stderr , "GenericHostAllocator: allocate %zu bytes, alignment %zu, %s -> %p\n" , bytes , align , get_policy()==HostAllocationPolicy::CUDA_HOST ? "managed" : "malloc" , p );
       return p;
     }
 

@@ -441,6 +441,17 @@ def test_list_macros_field_combiner_declarations_and_including_sequences_match_t
     assert theirs is None or theirs == ours
 
 
+def test_utility_headers_match_the_reference_headers(tmp_path):
+    """lambda_is_compatible_with_v / lambda_is_callable_with_args_v and their class forms (include/onika/lambda_tools.h:33-49 in
+    the reference; a void-returning call is not "callable with args" there, nor here), IntegralConst arithmetic, comparisons and
+    GetAsConstTypeOrValue (integral_constant.h:27-66), FlatTuple get / get_copy / get_nth_const / flat_tuple_subset /
+    tuple_size_const_v / make_flat_tuple (flat_tuple.h:27-112), ONIKA_AUTORUN_INIT and the USTAMP / MAKE_UNIQUE_NAME macros
+    (cpp_utils.h:23-44)"""
+    ours, theirs = _probe_on_both_header_trees(tmp_path, "utility_headers")
+    assert ours == ["1 0 1 0 | 1 0 0", "40 1 0 3 3", "4 2 1 2.5 x str | x 1 | 2.5 1", "7 abcd 10203"]
+    assert theirs is None or theirs == ours
+
+
 def test_msp_yaml_reader_on_the_reference_files(tmp_path):
     """tests/cxx/msp_yaml.h (what `run_operator --app` reads): block maps / sequences, `- key:` items continuing as maps, nested
     flow maps, quoted scalars with escapes, comments, document layering -- on the reference's own data/config/main-config.msp
