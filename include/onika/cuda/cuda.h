@@ -19,6 +19,9 @@
 
 #include <onika/macro_utils.h>
 #include <onika/atomic.h>
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
 
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
@@ -158,10 +161,10 @@ namespace onika { namespace cuda {
 #  define ONIKA_CU_ATOMIC_LOAD(x,...)          ( * (volatile const std::remove_reference_t<decltype(x)> *) &(x) )
 #  define ONIKA_CU_ATOMIC_ADD(x,a,...)         atomicAdd( &(x) , static_cast<std::remove_reference_t<decltype(x)> >(a) )
 #  define ONIKA_CU_INPLACE_ATOMIC_ADD(x,a,...) atomicAdd( &(x) , static_cast<std::remove_reference_t<decltype(x)> >(a) )
-#  define ONIKA_CU_BLOCK_ATOMIC_ADD(x,a,...)   atomicAdd_block( &(x) , static_cast<std::remove_reference_t<decltype(x)> >(a) )
+#  define ONIKA_CU_BLOCK_ATOMIC_ADD(x,a,...)   atomicAdd( &(x) , static_cast<std::remove_reference_t<decltype(x)> >(a) )   /* device scope, as in the reference: callers also use it on global memory */
 #  define ONIKA_CU_ATOMIC_SUB(x,a,...)         atomicSub( &(x) , static_cast<std::remove_reference_t<decltype(x)> >(a) )
 #  define ONIKA_CU_INPLACE_ATOMIC_SUB(x,a,...) atomicSub( &(x) , static_cast<std::remove_reference_t<decltype(x)> >(a) )
-#  define ONIKA_CU_BLOCK_ATOMIC_SUB(x,a,...)   atomicSub_block( &(x) , static_cast<std::remove_reference_t<decltype(x)> >(a) )
+#  define ONIKA_CU_BLOCK_ATOMIC_SUB(x,a,...)   atomicSub( &(x) , static_cast<std::remove_reference_t<decltype(x)> >(a) )
 #  define ONIKA_CU_ATOMIC_MIN(x,a,...)         atomicMin( &(x) , static_cast<std::remove_reference_t<decltype(x)> >(a) )
 #  define ONIKA_CU_ATOMIC_MAX(x,a,...)         atomicMax( &(x) , static_cast<std::remove_reference_t<decltype(x)> >(a) )
 #  define ONIKA_CU_ATOMIC_FLAG_TEST_AND_SET(f) ( ! atomicCAS((uint32_t*)&(f),0u,1u) )
@@ -182,10 +185,19 @@ namespace onika { namespace cuda { using onika_cu_clock_t = long long int; } }
 #  define ONIKA_CU_BLOCK_SHARED
 #  define ONIKA_CU_GLOBAL_VARIABLE
 
-#  define ONIKA_CU_GRID_SIZE    1u
-#  define ONIKA_CU_GRID_DIMS    onikaDim3_t{1,1,1}
-#  define ONIKA_CU_BLOCK_IDX    0u
-#  define ONIKA_CU_BLOCK_COORD  onikaDim3_t{0,0,0}
+// host items run inside an OpenMP region: the "grid" is the team and the "block index" the thread's rank in it, as in the
+// reference (cuda.h:221-224 there) -- functors index per-block scratch with it.  Without OpenMP: one block.
+#  if defined(_OPENMP)
+#    define ONIKA_CU_GRID_SIZE    static_cast<unsigned int>(omp_get_num_threads())
+#    define ONIKA_CU_GRID_DIMS    onikaDim3_t{ static_cast<unsigned int>(omp_get_num_threads()) , 1 , 1 }
+#    define ONIKA_CU_BLOCK_IDX    static_cast<unsigned int>(omp_get_thread_num())
+#    define ONIKA_CU_BLOCK_COORD  onikaDim3_t{ static_cast<unsigned int>(omp_get_thread_num()) , 0 , 0 }
+#  else
+#    define ONIKA_CU_GRID_SIZE    1u
+#    define ONIKA_CU_GRID_DIMS    onikaDim3_t{1,1,1}
+#    define ONIKA_CU_BLOCK_IDX    0u
+#    define ONIKA_CU_BLOCK_COORD  onikaDim3_t{0,0,0}
+#  endif
 #  define ONIKA_CU_BLOCK_SIZE   1
 #  define ONIKA_CU_BLOCK_DIMS   onikaDim3_t{1,1,1}
 #  define ONIKA_CU_THREAD_IDX   0

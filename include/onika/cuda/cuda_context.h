@@ -152,6 +152,7 @@ namespace onika { namespace cuda {
   struct CudaContext
   {
     std::vector<CudaDevice> m_devices;
+    std::vector<onikaStream_t> m_threadStream;          // streams handed out so far, by lane (the reference's lazily filled table)
 
     static inline bool s_global_gpu_enable = true;
     static inline std::shared_ptr<CudaContext> s_default_cuda_ctx = nullptr;
@@ -162,6 +163,8 @@ namespace onika { namespace cuda {
     {
       void* s = nullptr;
       ONIKA_B200_CHECK( onk_lane_stream( int(lane) , &s ) );
+      if( lane >= m_threadStream.size() ) m_threadStream.resize( lane + 1 , onikaStream_t{} );
+      m_threadStream[lane] = (onikaStream_t) s;
       return (onikaStream_t) s;
     }
 

@@ -385,6 +385,10 @@ int main()
   onika::cuda::memmove( buf , buf+8 , 24 ); onika::cuda::memmove( buf+1 , buf+4 , 7 ); onika::cuda::memmove( buf+30 , buf+30 , 5 );
   for(int i=0;i<40;i++) std::printf("%d ", int(buf[i]));
   std::printf("\n");
+  unsigned int grid = 0, idx_sum = 0, blk = 0, tid = 0;
+# pragma omp parallel num_threads(4) reduction(+:idx_sum) reduction(max:grid,blk,tid)
+  { grid = ONIKA_CU_GRID_SIZE; idx_sum += ONIKA_CU_BLOCK_IDX; blk = ONIKA_CU_BLOCK_SIZE; tid = ONIKA_CU_THREAD_IDX; }
+  std::printf("%u %u %u %u %u %u\n", grid, idx_sum, blk, tid, (unsigned int) ONIKA_CU_GRID_SIZE, (unsigned int) ONIKA_CU_BLOCK_IDX);
   onika::cuda::cout << "cout " << uint64_t(7) << " " << int32_t(-3) << " " << 2.5 << " " << 1.5f << " " << int16_t(-2) << "\n";
   return 0;
 }
@@ -405,7 +409,8 @@ int main()
     assert ours[2] == "10 20"
     assert ours[5] == "0 0 1 1 3 1 4 3 5 3 5 6 "          # sorted: std::lower_bound; unsorted: the first element that is not less
     assert ours[8].split()[:12] == ["8", "12", "13", "14", "15", "16", "17", "18", "16", "17", "18", "19"]
-    assert ours[9] == "cout 7 -3  2.500000000e+00  1.500000000e+00 -2"
+    assert ours[9] == "4 6 1 0 1 0"          # host items: the OpenMP team is the grid, the thread's rank the block index
+    assert ours[10] == "cout 7 -3  2.500000000e+00  1.500000000e+00 -2"
     ref_inc = "/root/reference/include"
     if os.path.isdir(ref_inc):
         theirs = build_and_run(ref_inc, "theirs")
