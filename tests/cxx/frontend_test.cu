@@ -1076,6 +1076,38 @@ static int scenario_sub_block_box(Out& out, ssize_t nx, ssize_t ny, ssize_t nz)
   return 0;
 }
 
+// a HOST-only functor (CudaCompatible = false) that keeps one accumulator per "block", indexed by ONIKA_CU_BLOCK_IDX and sized by
+// the grid: on the host the grid is the OpenMP team and the block index the thread's rank (the reference's meaning,
+// cuda.h:221-224 there), so the plain `+=` below is race-free only if every thread really sees its own index
+struct HostBlockScratchFunctor
+{
+  const double * values; double * per_block; unsigned int * max_grid; unsigned int * bad;
+  inline void operator () ( size_t i ) const
+  {
+    const unsigned int b = ONIKA_CU_BLOCK_IDX , g = ONIKA_CU_GRID_SIZE;
+    if( b >= g || b >= 1024u || ONIKA_CU_BLOCK_SIZE != 1 || ONIKA_CU_THREAD_IDX != 0 ) { ONIKA_CU_ATOMIC_ADD( *bad , 1u ); return; }
+    per_block[ b * 8 ] += values[i];                      // 64-byte stride: one cache line per block
+    ONIKA_CU_ATOMIC_MAX( *max_grid , g );
+  }
+};
+namespace onika { namespace parallel { template<> struct BlockParallelForFunctorTraits<HostBlockScratchFunctor> { static inline constexpr bool CudaCompatible = false; }; } }
+
+static int scenario_host_block_scratch(Out& out, size_t n)
+{
+  std::vector<double> v(n); for(size_t i=0;i<n;i++) v[i] = double( int( lcg(i,77,0.0,1000.0) ) );      // integers: any summation order is exact
+  std::vector<double> per_block( 1024 * 8 , 0.0 );
+  unsigned int max_grid = 0 , bad = 0;
+  HostBlockScratchFunctor f = { v.data() , per_block.data() , &max_grid , &bad };
+  block_parallel_for( n , f , parallel_execution_context("host","scratch") );      // synchronous: runs as a host node of lane 0
+  double total = 0.0 , expect = 0.0; unsigned int used = 0;
+  for(size_t b=0;b<1024;b++) { total += per_block[b*8]; used += ( per_block[b*8] != 0.0 ); }
+  for(size_t i=0;i<n;i++) expect += v[i];
+  const double r[5] = { total , expect , double(max_grid) , double(used) , double(bad) };
+  std::printf("host_block_scratch: total %.0f expect %.0f team %u blocks used %u bad %u\n", total, expect, max_grid, used, bad);
+  out.doubles( r , 5 );
+  return 0;
+}
+
 // reduction helpers queued on lanes together with the kernels that produce their input
 static int scenario_reduce_helpers(Out& out, size_t rows, size_t cols)
 {
@@ -1175,6 +1207,7 @@ int main(int argc, char* argv[])
   else if( sc == "soatl" ) rc = scenario_soatl( out , arg(3,53) );
   else if( sc == "soatl_apply_mixed" ) rc = scenario_soatl_apply_mixed( out , arg(3,5000) );
   else if( sc == "sub_block_listed" ) rc = scenario_sub_block_listed( out , arg(3,1001) );
+  else if( sc == "host_block_scratch" ) rc = scenario_host_block_scratch( out , arg(3,200000) );
   else if( sc == "sub_block_box" ) rc = scenario_sub_block_box( out , ssize_t(arg(3,13)) , ssize_t(arg(4,11)) , ssize_t(arg(5,7)) );
   else if( sc == "soatl_apply" ) rc = scenario_soatl_apply( out , arg(3,100003) , arg(4,0) != 0 );
   else if( sc == "perf" ) rc = scenario_perf( out , arg(3,1<<27) );

@@ -466,6 +466,18 @@ def test_sub_block_items_over_2d_and_3d_boxes(prog, tmp_path, orc, dims):
     assert np.all(packed3[in3 & (sizes.reshape(nz, ny, nx) == 0)] == 16.0)
 
 
+def test_host_only_functor_sees_the_openmp_team_as_its_grid(prog, tmp_path):
+    """a CudaCompatible = false functor with per-block accumulators indexed by ONIKA_CU_BLOCK_IDX (reference meaning on the host:
+    cuda.h:221-224, grid = OpenMP team, block index = thread rank): the unsynchronised `+=` per block adds up exactly"""
+    env = dict(os.environ, OMP_NUM_THREADS="6")
+    out = os.path.join(tmp_path, "hbs.bin")
+    r = subprocess.run([prog, "host_block_scratch", out, "200000"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, (r.returncode, r.stdout[-800:], r.stderr[-800:])
+    total, expect, team, used, bad = np.fromfile(out, dtype=np.float64)
+    assert bad == 0 and total == expect
+    assert team == 6 and 1 <= used <= 6          # the lane's worker thread runs the region with the caller's OpenMP settings
+
+
 def test_host_compiler_and_nvcc_translation_units_share_one_context():
     """a plugin = .cpp files compiled by g++ plus .cu files compiled by nvcc: the default CUDA context is created by the g++
     half and read by the nvcc half (tests/cxx/mixed_tu_*): every shared type has one layout, the SM count that sizes fixed
