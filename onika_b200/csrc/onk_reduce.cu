@@ -145,14 +145,32 @@ namespace onk
     }
   }
 
+  // What a reduction does before it may touch memory its predecessor on the lane wrote (programmatic dependent launch, see
+  // launch_pdl).  Launched early -- the predecessor was a reduction that released its dependents -- the CTAs become resident
+  // while the predecessor's last CTA is still folding partials and exchanging with the other GPUs; in that window they ask the
+  // L2 for the first tiles they are going to read (a prefetch has no semantics: whatever the predecessor still writes lands in
+  // the L2 as well, and the loads come after the wait), then wait for the predecessor's completion and memory flush, then
+  // release their own dependents (after the wait: at most ONE successor is in flight behind a running reduction).
+  constexpr unsigned PDL_RELEASE = 1u;              // release this kernel's dependents once it passed its own wait
+  constexpr unsigned PDL_PREFETCH_SHIFT = 8;        // bits 8..15: tiles per CTA to prefetch into L2 before the wait
+  __device__ __forceinline__ void pdl_prologue(const double* body, uint64_t ntiles, unsigned tile_bytes, unsigned flags)
+  {
+    const unsigned pf = (flags >> PDL_PREFETCH_SHIFT) & 0xffu;
+    if (pf != 0 && threadIdx.x == 0)                   // bulk requests are issued from uniform registers: one thread, one tile after the other
+      for (uint64_t k = 0, t = blockIdx.x; k < pf && t < ntiles; k++, t += gridDim.x)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(reinterpret_cast<const char*>(body) + t * tile_bytes), "r"(tile_bytes) : "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // no-op unless launched as a programmatic dependent
+    if (flags & PDL_RELEASE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+
   template<int OP, bool XCHG>
   __global__ void __launch_bounds__(THREADS, RED_CTAS_PER_SM)
   reduce_f64_kernel(const double* __restrict__ in, uint64_t n, uint64_t head, uint64_t ntiles,
                     double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ out,
-                    const __grid_constant__ XchgParams xp)
+                    const __grid_constant__ XchgParams xp, unsigned pdl_flags)
   {
     using R = Red<OP>;
-    asm volatile("griddepcontrol.wait;" ::: "memory");          // no-op unless launched as a programmatic dependent (launch_pdl)
+    pdl_prologue(in + head, ntiles, RED_TILE * 8u, pdl_flags);
 
     double acc[RED_UNROLL * 4];
 #pragma unroll
@@ -210,10 +228,10 @@ namespace onk
   __global__ void __launch_bounds__(THREADS, 1)
   reduce_f64_tma_kernel(const double* __restrict__ in, uint64_t n, uint64_t head, uint64_t ntiles,
                         double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ out,
-                        const __grid_constant__ XchgParams xp)
+                        const __grid_constant__ XchgParams xp, unsigned pdl_flags)
   {
     using R = Red<OP>;
-    asm volatile("griddepcontrol.wait;" ::: "memory");          // no-op unless launched as a programmatic dependent (launch_pdl)
+    pdl_prologue(in + head, ntiles, TMA_TILE_BYTES, pdl_flags);
 
     extern __shared__ __align__(128) unsigned char tsm[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(tsm + (size_t)TMA_STAGES * TMA_TILE_BYTES);
@@ -293,9 +311,12 @@ namespace onk
   // drains -- it waits for the predecessor's completion and memory flush in griddepcontrol.wait, its first instruction, before it
   // touches anything -- so part of the launch latency between back-to-back kernels of a lane is hidden.  A/B on one 2-GPU box
   // (bench.py --gpus 2, two runs each): weak step 0.2997 -> 0.2987 ms, 2^28 in total 0.1562 -> 0.1536 ms, two-lane C5 sequence
-  // unchanged within noise.  The kernels do NOT trigger their dependents early (griddepcontrol.launch_dependents at the top):
-  // that hides more (1 GiB 151.4 -> 149.3 us, 64 MiB 12.2 -> 8.9 us) but parks the dependent's CTAs on the SMs while the
-  // predecessor runs, which takes slots from the kernels of OTHER lanes (C5 on 2 GPUs +1-2 %).
+  // unchanged within noise.  By default the kernels do NOT release their dependents early: an early release parks the
+  // dependent's CTAs on the SMs while the predecessor drains, which takes slots from the kernels of OTHER lanes.  ONK_PDL_EARLY=2
+  // turns it on for the register-staged kernel, with an L2 prefetch of the dependent's first tiles while it waits (pdl_prologue):
+  // one GPU, back to back, 128 MiB 22.5 -> 20.9 us, 256 MiB 42.0 -> 40.7 us; 8 GPUs, 2^28 doubles in total (tools/exp_strong.py,
+  // two runs each): 46.2 / 46.4 -> 45.5 / 45.4 us per step (6.34x -> 6.47x), but the two-lane C5 sequence 0.5298 / 0.5310 ->
+  // 0.5366 / 0.5333 ms: a 2 % gain on single-lane chains of medium reductions against 0.4-1.3 % on multi-lane work, hence opt-in.
   template<class... KArgs, class... Args>
   static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args)
   {
@@ -326,6 +347,18 @@ namespace onk
     // its 4 CTAs per SM ramps up and drains a little faster (256 MiB back to back: 41.7 vs 43.1 us, 128 MiB: 20.7 vs 25.0 us;
     // tools/exp_reduce_small.py) -- the per-GPU shards of a strong-scaling run are in that range
     const uint64_t tma_tiles = (n - head) / TMA_TILE;
+    // ONK_PDL_EARLY (A/B knob): 0 = dependents start when the predecessor has completed, 1 = released early, 2 = released early
+    // and prefetching ONK_PDL_PREFETCH_MB (default 32) of their input into L2 while they wait; 1 and 2 concern the register-staged
+    // kernel (shards below 768 MiB, where the gap between two kernels is a visible share of the step), 3 = 2 for both kernels
+    static const int early = []{ const char* e = getenv("ONK_PDL_EARLY"); return e ? atoi(e) : 0; }();
+    static const unsigned prefetch_mb = []{ const char* e = getenv("ONK_PDL_PREFETCH_MB"); const int v = e ? atoi(e) : 32; return (unsigned)(v < 0 ? 0 : v); }();
+    auto flags_for = [&](unsigned grid, unsigned tile_bytes) -> unsigned
+    {
+      if (early <= 0) return 0u;
+      unsigned pf = 0;
+      if (early >= 2 && grid > 0) { pf = (unsigned)((((uint64_t)prefetch_mb << 20) + (uint64_t)grid * tile_bytes - 1) / ((uint64_t)grid * tile_bytes)); if (pf > 64) pf = 64; }
+      return PDL_RELEASE | (pf << PDL_PREFETCH_SHIFT);
+    };
     if (allow_tma && tma_tiles >= (red_mode == 2 ? 2ull * (uint64_t)rt().sm_count : 12288ull))
     {
       static bool configured = false;
@@ -336,10 +369,11 @@ namespace onk
         configured = true;
       }
       const unsigned g = (unsigned)rt().sm_count;
+      const unsigned pdl_flags = (early >= 3) ? flags_for(g, TMA_TILE_BYTES) : 0u;
       if (xp != nullptr && xp->world > 1)
-        ONK_CUDA(launch_pdl(reduce_f64_tma_kernel<OP, true>, g, THREADS, TMA_SMEM, L->stream, in, n, head, tma_tiles, L->ws.partials, L->ws.ticket, out, *xp));
+        ONK_CUDA(launch_pdl(reduce_f64_tma_kernel<OP, true>, g, THREADS, TMA_SMEM, L->stream, in, n, head, tma_tiles, L->ws.partials, L->ws.ticket, out, *xp, pdl_flags));
       else
-        ONK_CUDA(launch_pdl(reduce_f64_tma_kernel<OP, false>, g, THREADS, TMA_SMEM, L->stream, in, n, head, tma_tiles, L->ws.partials, L->ws.ticket, out, XchgParams{}));
+        ONK_CUDA(launch_pdl(reduce_f64_tma_kernel<OP, false>, g, THREADS, TMA_SMEM, L->stream, in, n, head, tma_tiles, L->ws.partials, L->ws.ticket, out, XchgParams{}, pdl_flags));
       ONK_CHECK_LAUNCH();
       count_launch();
       return ONK_OK;
@@ -350,10 +384,11 @@ namespace onk
     unsigned grid = grid_for(ntiles, 1, ctas_per_sm);
     if (ntiles == 0) grid = (unsigned)((edge + THREADS - 1) / THREADS ? (edge + THREADS - 1) / THREADS : 1);
     if (grid > (unsigned)MAX_PARTIALS) grid = MAX_PARTIALS;
+    const unsigned pdl_flags = flags_for(grid, RED_TILE * 8u);
     if (xp != nullptr && xp->world > 1)
-      ONK_CUDA(launch_pdl(reduce_f64_kernel<OP, true>, grid, THREADS, 0, L->stream, in, n, head, ntiles, L->ws.partials, L->ws.ticket, out, *xp));
+      ONK_CUDA(launch_pdl(reduce_f64_kernel<OP, true>, grid, THREADS, 0, L->stream, in, n, head, ntiles, L->ws.partials, L->ws.ticket, out, *xp, pdl_flags));
     else
-      ONK_CUDA(launch_pdl(reduce_f64_kernel<OP, false>, grid, THREADS, 0, L->stream, in, n, head, ntiles, L->ws.partials, L->ws.ticket, out, XchgParams{}));
+      ONK_CUDA(launch_pdl(reduce_f64_kernel<OP, false>, grid, THREADS, 0, L->stream, in, n, head, ntiles, L->ws.partials, L->ws.ticket, out, XchgParams{}, pdl_flags));
     ONK_CHECK_LAUNCH();
     count_launch();
     return ONK_OK;

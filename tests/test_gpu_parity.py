@@ -166,6 +166,68 @@ print("ok")
     assert r.returncode == 0 and "ok" in r.stdout, (r.stdout[-1000:], r.stderr[-2000:])
 
 
+@pytest.mark.parametrize("mode", ["2", "3"])
+def test_reductions_released_early_with_l2_prefetch_keep_their_results(orc, mode):
+    """ONK_PDL_EARLY=2 / 3: a reduction lets its successor on the lane become resident early; the successor prefetches its first
+    tiles into L2, waits for the predecessor's completion, then runs.  The data path is untouched, so every result must be what
+    the default mode gives: chains of reductions over the same and over different inputs, a reduction right after kernels that
+    WRITE its input (value-add, axpy: the wait must order them), the reduction's own output as the next one's input, unaligned
+    starts and ragged tails, both kernels (register-staged and, with ONK_RED_KERNEL=tma, TMA-staged)."""
+    import subprocess
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import onika_b200 as ob
+from onika_b200 import parallel as P
+from tests._inputs import lcg_uniform
+import oracle
+ob.init(0)
+orc = oracle.orc
+for n, offset in ((5_000_001, 1), (296 * 8192 + 3, 0), (1 << 22, 2), (33, 3), (1, 0)):
+    d = lcg_uniform(n + offset, 91, -1.0, 1.0)
+    t = torch.from_numpy(d).cuda()[offset:]
+    h = d[offset:].copy()
+    out = torch.empty(64, dtype=torch.float64, device="cuda")
+    # a chain on one lane: min, max, sum, min ... back to back, results into different slots
+    for k in range(24):
+        P.ReduceFunctor((ob.OP_MIN, ob.OP_MAX, ob.OP_SUM)[k %% 3], t, out[k:k + 1]).launch(n, 0)
+    got = out.cpu().numpy()
+    assert np.all(got[0:24:3] == orc.reduce_min(h)) and np.all(got[1:24:3] == orc.reduce_max(h)), (n, offset)
+    assert np.all(got[2:24:3] == got[2]) and abs(got[2] - orc.reduce_sum_ld(h)) <= 1e-12 * np.abs(h).sum(), (n, offset)
+    # writers in between: every reduction must see what the kernel before it wrote
+    x = torch.from_numpy(lcg_uniform(n, 92, -1.0, 1.0)).cuda()
+    hx = x.cpu().numpy()
+    for k in range(6):
+        P.BlockParallelValueAddFunctor(t.view(1, -1), 0.25).launch(1, 0)
+        h = h + 0.25
+        want_min = h.min()
+        P.ReduceFunctor(ob.OP_MIN, t, out[2 * k:2 * k + 1]).launch(n, 0)
+        P.AxpyFunctor(t, x, 0.5).launch(n, 0)
+        h = h + 0.5 * hx
+        P.ReduceFunctor(ob.OP_MAX, t, out[2 * k + 1:2 * k + 2]).launch(n, 0)
+        got = out[2 * k:2 * k + 2].cpu().numpy()
+        assert got[0] == want_min and got[1] == h.max(), ("min after value-add, max after axpy", n, offset, k)
+    assert np.array_equal(t.cpu().numpy(), h)
+# a reduction whose INPUT holds the previous reduction's OUTPUT (written by the predecessor's last CTA)
+n = 1 << 20
+buf = torch.from_numpy(lcg_uniform(n, 93, 1.0, 2.0)).cuda()
+src = torch.from_numpy(lcg_uniform(n, 94, -3.0, -2.0)).cuda()
+res = torch.empty(1, dtype=torch.float64, device="cuda")
+for k in range(20):
+    P.ReduceFunctor(ob.OP_MIN, src, buf[k * 1000:k * 1000 + 1]).launch(n, 0)       # plants a negative value in buf
+    P.ReduceFunctor(ob.OP_MIN, buf, res).launch(n, 0)
+    assert float(res.item()) == float(src.min().item()), k
+    buf[k * 1000] = 1.5
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for red in ("", "tma"):
+        env = {**os.environ, "ONK_PDL_EARLY": mode}
+        if red:
+            env["ONK_RED_KERNEL"] = red
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=env)
+        assert r.returncode == 0 and "ok" in r.stdout, (red, r.stdout[-1000:], r.stderr[-2000:])
+
+
 def test_more_than_2pow32_elements(ob):
     """maximum sizes: the reference's GPU trampoline carries the start index as `unsigned int`
     (block_parallel_for_adapter.h:51-66), i.e. N <= 2^32; here indices are 64-bit throughout.  2^32 + 4099 doubles (34.4 GB):
