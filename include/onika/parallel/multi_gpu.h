@@ -27,7 +27,9 @@ namespace onika { namespace parallel {
 
   // all-gather of `bytes` bytes per rank through files in a directory every process of the node can see (/dev/shm, /tmp):
   // rank r writes <dir>/<tag>.<r> atomically (write + rename) and reads the others' as they appear.  A transport for
-  // programs that have none; anything with all-gather semantics can be passed to MultiGpuExchange instead.
+  // programs that have none; anything with all-gather semantics can be passed to MultiGpuExchange instead.  The files stay
+  // behind (no rank knows when the last reader is done): use a directory or tag that is new for every run (job id, start
+  // time agreed through the launcher), otherwise the handles of an earlier run would be read.
   inline bool file_allgather( const std::string& dir , const std::string& tag , int rank , int world , const void* mine , void* all , size_t bytes , double timeout_s = 120.0 )
   {
     const std::string base = dir + "/" + tag + ".";
