@@ -51,6 +51,8 @@ namespace onika { namespace soatl {
     template<class Sig> struct call_signature;
     template<class C, class R, class... A> struct call_signature< R (C::*)(A...) const > { template<size_t K> using arg = std::tuple_element_t< K , std::tuple<A...> >; };
     template<class C, class R, class... A> struct call_signature< R (C::*)(A...) >       { template<size_t K> using arg = std::tuple_element_t< K , std::tuple<A...> >; };
+    template<class C, class R, class... A> struct call_signature< R (C::*)(A...) const noexcept > { template<size_t K> using arg = std::tuple_element_t< K , std::tuple<A...> >; };
+    template<class C, class R, class... A> struct call_signature< R (C::*)(A...) noexcept >       { template<size_t K> using arg = std::tuple_element_t< K , std::tuple<A...> >; };
     template<class F, size_t K, class = void> struct writes_argument : std::true_type {};
     template<class F, size_t K> struct writes_argument< F , K , std::void_t< decltype( & F::operator() ) > >
     {
