@@ -457,6 +457,35 @@ def test_utility_headers_match_the_reference_headers(tmp_path):
     assert theirs is None or theirs == ours
 
 
+def test_device_memmove_both_directions_against_std_memmove(tmp_path):
+    """onika::cuda::memmove copies forwards (the only direction the reference implements, stl_adaptors.h:46-70 there: it aborts
+    when dst > src) and backwards: every (dst offset, src offset, length) of a 96-byte window against std::memmove"""
+    src = tmp_path / "mm.cpp"
+    src.write_text(r'''
+#include <onika/cuda/stl_adaptors.h>
+#include <cstdio>
+#include <cstring>
+int main()
+{
+  alignas(8) unsigned char a[96], b[96];
+  long bad = 0, n = 0;
+  for(unsigned d=0; d<40; d++) for(unsigned s=0; s<40; s++) for(unsigned len=0; len<=48; len++)
+  {
+    for(int i=0;i<96;i++) a[i] = b[i] = (unsigned char)( i * 7 + 3 );
+    onika::cuda::memmove( a + d , a + s , len );
+    std::memmove( b + d , b + s , len );
+    bad += ( std::memcmp( a , b , 96 ) != 0 ); n++;
+  }
+  std::printf("%ld %ld\n", n, bad);
+  return bad != 0;
+}
+''')
+    exe = tmp_path / "mm"
+    subprocess.check_call(["g++", "-std=c++20", "-O1", f"-I{INC}", str(src), "-o", str(exe)], env=_env())
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == ["78400", "0"], out.stdout
+
+
 def test_msp_yaml_reader_on_the_reference_files(tmp_path):
     """tests/cxx/msp_yaml.h (what `run_operator --app` reads): block maps / sequences, `- key:` items continuing as maps, nested
     flow maps, quoted scalars with escapes, comments, document layering -- on the reference's own data/config/main-config.msp
