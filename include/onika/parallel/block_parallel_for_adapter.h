@@ -371,12 +371,17 @@ namespace onika { namespace parallel {
       const auto T0 = std::chrono::high_resolution_clock::now();
       execute_prolog( pec , pes );
       const auto & ps = m_parallel_space;
+      // the caller's OpenMP schedule (opts.omp_scheduling, default guided) through the run-time schedule of this thread: one loop
+      // per dimensionality instead of one per (dimensionality, schedule) as in the reference (block_parallel_for_adapter.h:272-360)
+#     if defined(_OPENMP)
+      omp_set_schedule( pec->m_omp_sched == OMP_SCHED_STATIC ? omp_sched_static : ( pec->m_omp_sched == OMP_SCHED_DYNAMIC ? omp_sched_dynamic : omp_sched_guided ) , 0 );
+#     endif
       if constexpr ( functor_is_single_task ) { m_func( block_parallel_for_single_task_t{} ); }
       else if constexpr ( ND == 1 )
       {
         const auto * idx = ps.m_elements.data();
         (void) idx;
-#       pragma omp parallel for schedule(guided)
+#       pragma omp parallel for schedule(runtime)
         for(ssize_t i=ps.m_start[0]; i<ps.m_end[0]; i++)
         {
           if constexpr ( ElemND==0 ) m_func( i );
@@ -385,13 +390,13 @@ namespace onika { namespace parallel {
       }
       else if constexpr ( ND == 2 )
       {
-#       pragma omp parallel for collapse(2) schedule(guided)
+#       pragma omp parallel for collapse(2) schedule(runtime)
         for(ssize_t j=ps.m_start[1]; j<ps.m_end[1]; j++)
         for(ssize_t i=ps.m_start[0]; i<ps.m_end[0]; i++) m_func( onikaInt3_t{i,j,0} );
       }
       else
       {
-#       pragma omp parallel for collapse(3) schedule(guided)
+#       pragma omp parallel for collapse(3) schedule(runtime)
         for(ssize_t k=ps.m_start[2]; k<ps.m_end[2]; k++)
         for(ssize_t j=ps.m_start[1]; j<ps.m_end[1]; j++)
         for(ssize_t i=ps.m_start[0]; i<ps.m_end[0]; i++) m_func( onikaInt3_t{i,j,k} );

@@ -1092,6 +1092,9 @@ struct HostBlockScratchFunctor
 };
 namespace onika { namespace parallel { template<> struct BlockParallelForFunctorTraits<HostBlockScratchFunctor> { static inline constexpr bool CudaCompatible = false; }; } }
 
+struct HostOwnerFunctor { double * owner; inline void operator () ( size_t i ) const { owner[i] = double( ONIKA_CU_BLOCK_IDX ); } };
+namespace onika { namespace parallel { template<> struct BlockParallelForFunctorTraits<HostOwnerFunctor> { static inline constexpr bool CudaCompatible = false; }; } }
+
 static int scenario_host_block_scratch(Out& out, size_t n)
 {
   std::vector<double> v(n); for(size_t i=0;i<n;i++) v[i] = double( int( lcg(i,77,0.0,1000.0) ) );      // integers: any summation order is exact
@@ -1105,6 +1108,12 @@ static int scenario_host_block_scratch(Out& out, size_t n)
   const double r[5] = { total , expect , double(max_grid) , double(used) , double(bad) };
   std::printf("host_block_scratch: total %.0f expect %.0f team %u blocks used %u bad %u\n", total, expect, max_grid, used, bad);
   out.doubles( r , 5 );
+  // opts.omp_scheduling reaches the host loop: with OMP_SCHED_STATIC thread t owns one contiguous run of items
+  std::vector<double> owner( 4096 , -1.0 );
+  HostOwnerFunctor g = { owner.data() };
+  BlockParallelForOptions o; o.omp_scheduling = OMP_SCHED_STATIC;
+  block_parallel_for( owner.size() , g , parallel_execution_context("host","static") , o );
+  out.doubles( owner.data() , owner.size() );
   return 0;
 }
 

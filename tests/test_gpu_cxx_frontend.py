@@ -473,9 +473,14 @@ def test_host_only_functor_sees_the_openmp_team_as_its_grid(prog, tmp_path):
     out = os.path.join(tmp_path, "hbs.bin")
     r = subprocess.run([prog, "host_block_scratch", out, "200000"], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, (r.returncode, r.stdout[-800:], r.stderr[-800:])
-    total, expect, team, used, bad = np.fromfile(out, dtype=np.float64)
+    d = np.fromfile(out, dtype=np.float64)
+    total, expect, team, used, bad = d[:5]
     assert bad == 0 and total == expect
     assert team == 6 and 1 <= used <= 6          # the lane's worker thread runs the region with the caller's OpenMP settings
+    # opts.omp_scheduling = OMP_SCHED_STATIC (reference: block_parallel_for_adapter.h:296-303): thread t owns items [t*ceil(n/T), ...)
+    owner = d[5:]
+    assert owner.size == 4096 and np.all(np.diff(owner) >= 0) and owner[0] == 0 and owner[-1] == 5      # contiguous runs, in thread order
+    assert set(np.bincount(owner.astype(np.int64)).tolist()) <= {682, 683}                                # of near-equal length
 
 
 def test_host_compiler_and_nvcc_translation_units_share_one_context():
