@@ -486,6 +486,44 @@ int main()
     assert out.returncode == 0 and out.stdout.split() == ["78400", "0"], out.stdout
 
 
+def test_file_rendezvous_all_gather_between_processes(tmp_path):
+    """the handle all-gather MultiGpuExchange falls back to when the application has none (include/onika/parallel/multi_gpu.h:
+    file_allgather): 4 processes, 64 bytes each, every process ends with everybody's bytes in rank order; a missing rank times out"""
+    from onika_b200 import _build
+    lib = _build.build()
+    src = tmp_path / "fag.cpp"
+    src.write_text(r'''
+#include <onika/parallel/multi_gpu.h>
+#include <cstdio>
+#include <cstdlib>
+int main(int argc, char** argv)
+{
+  const int rank = std::atoi(argv[1]) , world = std::atoi(argv[2]);
+  const double timeout = std::atof(argv[4]);
+  unsigned char mine[64] , all[64*8];
+  for(int i=0;i<64;i++) mine[i] = (unsigned char)( rank * 64 + i );
+  const bool ok = onika::parallel::file_allgather( argv[3] , "probe" , rank , world , mine , all , 64 , timeout );
+  if( ! ok ) { std::printf("timeout\n"); return 3; }
+  for(int r=0;r<world;r++) for(int i=0;i<64;i++) if( all[r*64+i] != (unsigned char)( r * 64 + i ) ) return 4;
+  std::printf("ok %d\n", rank);
+  return 0;
+}
+''')
+    exe = tmp_path / "fag"
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-fopenmp", f"-I{INC}", str(src), "-o", str(exe), f"-L{os.path.dirname(lib)}", "-lonika_b200",
+                           f"-Wl,-rpath,{os.path.dirname(lib)}"], env=_env())
+    d1 = tmp_path / "rdv1"
+    d1.mkdir()
+    procs = [subprocess.Popen([str(exe), str(r), "4", str(d1), "60"], stdout=subprocess.PIPE, text=True) for r in (2, 0, 3, 1)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert sorted(outs) == [f"ok {r}\n" for r in range(4)]
+    d2 = tmp_path / "rdv2"
+    d2.mkdir()
+    lone = subprocess.run([str(exe), "0", "2", str(d2), "0.3"], capture_output=True, text=True, timeout=60)      # rank 1 never comes
+    assert lone.returncode == 3 and "timeout" in lone.stdout
+
+
 def test_msp_yaml_reader_on_the_reference_files(tmp_path):
     """tests/cxx/msp_yaml.h (what `run_operator --app` reads): block maps / sequences, `- key:` items continuing as maps, nested
     flow maps, quoted scalars with escapes, comments, document layering -- on the reference's own data/config/main-config.msp
